@@ -1,0 +1,197 @@
+/*
+ * twopaco_b200.h -- C ABI of libtwopaco_b200.so: TwoPaCo's two-pass junction-finding hot
+ * path on NVIDIA B200 (sm_100a).  Plain pointers and sizes only; no C++/torch types cross
+ * this boundary; nothing throws across it (errors: non-zero return + tpc_last_error()).
+ *
+ * Citations are relative to the reference tree (medvedevgroup/TwoPaCo, /root/reference).
+ *
+ * Three levels, top to bottom:
+ *   1. tpc_build()            == TwoPaCo::CreateEnumerator(...)   (FASTA files -> de_bruijn.bin)
+ *   2. tpc_junctions_host()   == the same work on an already packed genome in host memory
+ *                                (the "e2e" timed region of bench.py: H2D + kernels + D2H)
+ *   3. tpc_session_*()        == the stages on a device-resident genome, one session per GPU
+ *                                (hash-range shard), so that the caller can put collectives
+ *                                between the stages (multi-GPU) and time kernels alone.
+ */
+#ifndef TWOPACO_B200_H_
+#define TWOPACO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPC_ABI_VERSION 1
+#define TPC_INVALID_VERTEX INT64_MAX          /* src/graphconstructor/common.cpp:5 */
+#define TPC_SEPARATOR_POS 0xFFFFFFFFu         /* src/common/junctionapi.h:36-37 */
+#define TPC_MAX_K 127                         /* 4 x 64-bit words per packed k-mer in this build
+                                                 (reference: MAX_CAPACITY 20, vertexenumerator.h:4) */
+#define TPC_STUB_ID_OFFSET 42                 /* vertexenumerator.h:419 */
+
+typedef struct tpc_handle tpc_handle;         /* result of tpc_build (a VertexEnumerator) */
+typedef struct tpc_session tpc_session;       /* one GPU's shard of a run */
+typedef void (*tpc_log_fn)(void *ctx, const char *text); /* receives the std::ostream & log text */
+
+/* ------------------------------------------------------------------------------------------
+ * Parameters of one run == the arguments of CreateEnumerator
+ * (src/graphconstructor/vertexenumerator.h:37-46; CLI: constructor.cpp:60-143).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct tpc_params {
+    uint32_t k;            /* vertexLength, odd, 1..TPC_MAX_K            (-k, default 25)      */
+    uint32_t filter_bits;  /* filterSize: the Bloom filter has 2^f bits   (-f)                  */
+    uint32_t q;            /* hashFunctions: bits set per edge            (-q, default 5)       */
+    uint32_t rounds;       /* rounds: hash-range rounds run in sequence   (-r, default 1)       */
+    uint64_t abundance;    /* junctions seen more often are dropped       (-a, default 2^64-1)  */
+    uint32_t shard_index;  /* this GPU's hash-range shard, 0..shard_count-1 (spatial analogue   */
+    uint32_t shard_count;  /*   of -r: vertexenumerator.h:234-254, 638, 1066); 1 = unsharded    */
+    uint64_t seed;         /* hash seed; fixed default 0 (the reference seeds from /dev/urandom, */
+                           /*   mersennetwister.h:242-263, which only permutes ids)             */
+} tpc_params;
+
+/* Counters the reference prints to its log (vertexenumerator.h:384-387, 463) plus timings. */
+typedef struct tpc_stats {
+    uint64_t positions;          /* genome positions incl. separators                         */
+    uint64_t candidate_marks;    /* "Candidate marks count"                                   */
+    uint64_t candidate_kmers;    /* "Hash table size" (distinct candidate k-mers)             */
+    uint64_t junctions;          /* "True junctions count" == "Distinct junctions"            */
+    uint64_t occurrences;        /* "True marks count" (records written, incl. stubs)         */
+    uint64_t stubs;              /* records that are end-of-sequence stubs                    */
+    uint64_t out_bytes;          /* size of the de_bruijn.bin image                           */
+    uint64_t filter_edges_set;   /* fill: (vertex, edge-slot) items that set a new bit        */
+    float ms_fill, ms_query, ms_insert, ms_classify, ms_index, ms_emit, ms_total; /* CUDA events */
+    uint32_t kernel_launches;    /* kernels of this library launched by the call              */
+    uint32_t reserved;
+} tpc_stats;
+
+/* ------------------------------------------------------------------------------------------
+ * Packed genome (2-bit DNA packing of src/graphconstructor/compressedstring.h:239-264: base i
+ * -> bits 2(i%32) of 64-bit word i/32, A0 C1 G2 T3, dnachar.cpp:18-33), applied to the WHOLE
+ * input instead of per k-mer:
+ *   all records are laid out in one position space, separated by one 'N' position -- the
+ *   sentinel 'N' the reference puts before and after every record (vertexenumerator.h:1154,
+ *   1191):   pos 0 = N, record 0 at [1, 1+len0), N, record 1, N, ...
+ *   codes : 2 bits / position (0 where N), n_mask : 1 bit / position (1 = not ACGT).
+ * Both arrays must be readable up to the word counts returned by the helpers below.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct tpc_genome {
+    const uint64_t *codes;      /* tpc_code_words(n_positions) words                            */
+    const uint64_t *n_mask;     /* tpc_mask_words(n_positions) words                            */
+    uint64_t n_positions;       /* 1 + sum(len_i + 1)                                           */
+    const uint64_t *rec_start;  /* n_records position of the first base of each record          */
+    const uint64_t *rec_len;    /* n_records lengths (< 2^32: junctionapi.h:33-34)              */
+    uint64_t n_records;
+} tpc_genome;
+
+uint64_t tpc_code_words(uint64_t n_positions);  /* incl. the read-ahead padding the kernels need */
+uint64_t tpc_mask_words(uint64_t n_positions);
+uint64_t tpc_positions_for(const uint64_t *rec_len, uint64_t n_records);
+
+/* Host packer: normalised records (bytes over ACGTN, anything else -> N; lower case folded,
+ * DistributeTasks vertexenumerator.h:1174) -> codes / n_mask / rec_start at the layout above.
+ * Outputs are caller-allocated (sizes from the helpers above); threads = host worker threads. */
+int tpc_pack_records(const char *const *records, const uint64_t *rec_len, uint64_t n_records,
+                     uint32_t threads, uint64_t *codes, uint64_t *n_mask, uint64_t *rec_start);
+
+/* FASTA framing of src/common/streamfastaparser.cpp:29-133 (header = line starting with '>',
+ * whitespace skipped, upper-cased, characters outside ACGTURYKMSWBDHWNXV are an error).
+ * Appends the records of one file; *records / *rec_len are malloc'ed/realloc'ed by the callee
+ * and released with tpc_free_records. */
+int tpc_read_fasta(const char *path, char ***records, uint64_t **rec_len, uint64_t *n_records);
+void tpc_free_records(char **records, uint64_t *rec_len, uint64_t n_records);
+
+/* ------------------------------------------------------------------------------------------
+ * Level 1 -- replaces  std::unique_ptr<VertexEnumerator> TwoPaCo::CreateEnumerator(fileName,
+ * vertexLength, filterSize, hashFunctions, rounds, threads, abundance, tmpDirName,
+ * outFileName, logStream)   (vertexenumerator.h:37-46, vertexenumerator.cpp:73-94).
+ * Blocking; all work happens inside the call (as in VertexEnumeratorImpl's constructor,
+ * vertexenumerator.h:122-466); writes `outfile` in the de_bruijn.bin format
+ * (junctionapi.h:107-137).  `threads` = host threads for FASTA parsing/packing; the GPU is
+ * the current CUDA device.  `tmpdir` is accepted for CLI compatibility (no temp files are
+ * needed: candidate masks and junction keys stay in HBM; reference: h:219, 292).
+ * Error strings follow the reference ("Can't open file ...", "Found an invalid character",
+ * "The value of K is too big. ...", "Can't create the output file").
+ * ---------------------------------------------------------------------------------------- */
+int tpc_build(const char *const *fasta_paths, size_t n_files, uint32_t k, uint32_t filter_bits,
+              uint32_t q, uint32_t rounds, uint32_t threads, uint64_t abundance,
+              const char *tmpdir, const char *outfile, tpc_log_fn log, void *log_ctx,
+              tpc_handle **out);
+uint64_t tpc_vertices(const tpc_handle *h);                 /* VertexEnumerator::GetVerticesCount, h:104-107 */
+int64_t tpc_get_id(const tpc_handle *h, const char *kmer);  /* VertexEnumerator::GetId, h:98-102;
+                                                               TPC_INVALID_VERTEX when absent           */
+int tpc_handle_stats(const tpc_handle *h, tpc_stats *out);
+void tpc_free(tpc_handle *h);
+
+/* ------------------------------------------------------------------------------------------
+ * Level 2 -- packed genome in HOST memory -> de_bruijn.bin image in HOST memory, one GPU.
+ * out_image (capacity bytes; pinned memory recommended) receives the exact file content.
+ * Returns 0, or 2 when out_capacity is too small (*out_bytes then holds the required size).
+ * ---------------------------------------------------------------------------------------- */
+int tpc_junctions_host(const tpc_params *params, const tpc_genome *host_genome,
+                       uint8_t *out_image, uint64_t out_capacity, uint64_t *out_bytes,
+                       tpc_stats *stats);
+
+/* ------------------------------------------------------------------------------------------
+ * Level 3 -- sessions.  One session = one GPU (current device at creation) = one hash-range
+ * shard (params->shard_index / shard_count).  All device pointers returned stay owned by the
+ * session.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *
+ *   create -> set_genome_{host,device} -> find_candidates -> local_junctions
+ *          [multi-GPU: all-gather the junction lists]      -> set_junctions
+ *          [multi-GPU: OR-reduce the candidate masks]      -> emit_count -> emit_write
+ * ---------------------------------------------------------------------------------------- */
+int tpc_session_create(const tpc_params *params, void *stream, tpc_session **out);
+void tpc_session_destroy(tpc_session *s);
+
+/* Copy a packed genome host->device (async on the session stream; buffers must stay alive
+ * until the next synchronising call) or adopt device-resident arrays (not copied, not freed;
+ * rec_start / rec_len are HOST arrays in both cases). */
+int tpc_session_set_genome_host(tpc_session *s, const tpc_genome *host_genome);
+int tpc_session_set_genome_device(tpc_session *s, const tpc_genome *genome_with_device_arrays);
+
+/* Pass 1 + pass 2 for this shard (reference stages 1a, 1b, 2: FilterFillerWorker h:995-1105,
+ * CandidateCheckingWorker h:586-704, CandidateFinalFilteringWorker h:708-829), `rounds` times
+ * over disjoint hash sub-ranges. */
+int tpc_session_find_candidates(tpc_session *s);
+
+/* TrueBifurcations (h:1228-1256): this shard's junctions as a device array of 64-bit words
+ * (low 40 bits: position of the first occurrence of the k-mer in the genome; the k-mer is
+ * read back from the genome, so the word is meaningful on every GPU holding the genome). */
+int tpc_session_local_junctions(tpc_session *s, const uint64_t **dev_words, uint64_t *count);
+
+/* BifurcationStorage::Init (bifurcationstorage.h:27-66): build the id index from the junction
+ * words of ALL shards (device array).  Ids are 1..J in order of first occurrence. */
+int tpc_session_set_junctions(tpc_session *s, const uint64_t *dev_words_all, uint64_t count_all);
+
+/* Candidate mask of this shard: 1 bit per position, 32-bit words (bit i of word w = position
+ * 32w+i).  Masks of different shards are disjoint; OR (== sum) them before emitting. */
+int tpc_session_candidate_mask(tpc_session *s, uint32_t **dev_mask, uint64_t *n_words);
+
+/* EdgeConstructionWorker (h:856-993) + JunctionPositionWriter (junctionapi.h:107-137) for the
+ * positions [pos_begin, pos_end) (multiples of 8192, or n_positions).  emit_count returns the
+ * number of junction records and stubs of the slice; emit_write writes the slice's part of the
+ * file image (records + the separators that precede its records) into dev_out, given how many
+ * records / stubs precede the slice.  Image offset of the slice = 12 * (records_before +
+ * index of the sequence of its first record ... ) is returned in *image_offset. */
+int tpc_session_emit_count(tpc_session *s, uint64_t pos_begin, uint64_t pos_end,
+                           uint64_t *n_records, uint64_t *n_stubs);
+int tpc_session_emit_write(tpc_session *s, uint64_t records_before, uint64_t stubs_before,
+                           uint8_t *dev_out, uint64_t out_capacity,
+                           uint64_t *image_offset, uint64_t *image_bytes);
+
+int tpc_session_get_id(tpc_session *s, const char *kmer, int64_t *id);
+int tpc_session_stats(tpc_session *s, tpc_stats *out);   /* synchronises the stream */
+
+/* Random-access roofline probe: uniform random 32-byte sector touches into a
+ * 2^filter_bits-bit table on the current device. mode 0 = 32-byte loads, 1 = 4-byte atomicOr,
+ * 2 = load + conditional atomicOr (the fill pattern).  Returns sector touches per second. */
+int tpc_random_access_probe(uint32_t filter_bits, uint32_t mode, uint64_t touches, double *touches_per_s);
+
+const char *tpc_last_error(void);
+uint32_t tpc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TWOPACO_B200_H_ */

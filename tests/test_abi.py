@@ -1,0 +1,96 @@
+"""CPU: the C-ABI library loads and exports every symbol include/twopaco_b200.h declares; the
+host-side pieces (FASTA framing, 2-bit packing) match the oracle / a numpy restatement.
+No GPU compute is called here."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.cases import CASES
+from tests.util import case_files
+from twopaco_b200 import api, synth
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    header = (ROOT / "include" / "twopaco_b200.h").read_text()
+    declared = set(re.findall(r"\b(tpc_[a-z0-9_]+)\s*\(", header)) - {"tpc_log_fn"}
+    L = api.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert declared == set(api.SIGNATURES), declared ^ set(api.SIGNATURES)
+    assert L.tpc_abi_version() == 1
+
+
+def numpy_pack(records):
+    """Independent restatement of the layout in include/twopaco_b200.h (tpc_genome)."""
+    npos = 1 + sum(len(r) + 1 for r in records)
+    code = np.zeros(npos, dtype=np.uint64)
+    isn = np.ones(npos, dtype=np.uint64)
+    lut = np.full(256, 4, dtype=np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        lut[ch] = i
+        lut[ord(chr(ch).lower())] = i
+    p = 1
+    starts = []
+    for r in records:
+        starts.append(p)
+        c = lut[np.frombuffer(r, dtype=np.uint8)]
+        code[p:p + len(r)] = np.where(c < 4, c, 0)
+        isn[p:p + len(r)] = (c >= 4)
+        p += len(r) + 1
+    return npos, code, isn, starts
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_pack_records_layout(threads):
+    recs = synth.founder_family(5, 3, 2, 10_000, 0.01, n_runs=2) + [b"", b"ACG", b"acgtnNRY" * 3]
+    g = api.pack_records(recs, threads=threads)
+    npos, code, isn, starts = numpy_pack(recs)
+    assert g.n_positions == npos and list(g.rec_start) == starts
+    L = api.lib()
+    assert len(g.codes) == L.tpc_code_words(npos) and len(g.n_mask) == L.tpc_mask_words(npos)
+    pos = np.arange(npos, dtype=np.uint64)
+    got_code = (g.codes[pos >> np.uint64(5)] >> (np.uint64(2) * (pos & np.uint64(31)))) & np.uint64(3)
+    got_n = (g.n_mask[pos >> np.uint64(6)] >> (pos & np.uint64(63))) & np.uint64(1)
+    assert np.array_equal(got_code, code) and np.array_equal(got_n, isn)
+    # padding: codes 0, n_mask 1 beyond n_positions
+    tail = np.arange(npos, len(g.n_mask) * 64, dtype=np.uint64)
+    assert np.all((g.n_mask[tail >> np.uint64(6)] >> (tail & np.uint64(63))) & np.uint64(1) == 1)
+
+
+@pytest.mark.parametrize("name", ["example_k11", "edge_mixed_k11", "edge_leading_short_k5", "family_twofiles_k25"])
+def test_read_fasta_matches_oracle(name):
+    with case_files(CASES[name]) as (paths, _, _):
+        ours = api.read_fasta(paths)
+        ref = []
+        for p in paths:
+            ref += O.parse_fasta(p)
+    assert ours == ref
+
+
+def test_read_fasta_errors(tmp_path):
+    with pytest.raises(api.TpcError, match="Can't open file"):
+        api.read_fasta([str(tmp_path / "missing.fa")])
+    bad = tmp_path / "bad.fa"
+    bad.write_bytes(b">x y\nACGTJACGT\n")
+    with pytest.raises(api.TpcError, match="invalid character 'J' in sequence x"):
+        api.read_fasta([str(bad)])
+    bad.write_bytes(b"ACGT\n")
+    with pytest.raises(api.TpcError, match="should start with a '>'"):
+        api.read_fasta([str(bad)])
+
+
+def test_parameter_validation_and_no_cpu_fallback():
+    import torch
+    with pytest.raises(api.TpcError, match="must be odd"):
+        api.Session(k=24, filter_bits=20)
+    with pytest.raises(api.TpcError, match="K is too big"):
+        api.Session(k=129, filter_bits=20)
+    if not torch.cuda.is_available():
+        # the product path must fail loudly without a GPU
+        with pytest.raises(api.TpcError, match="no CUDA device"):
+            api.Session(k=25, filter_bits=20)

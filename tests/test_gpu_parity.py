@@ -1,0 +1,220 @@
+"""GPU (-m gpu): the CUDA path through the C ABI, bit-exact against
+  * golden.json  (canonical streams of the UNMODIFIED reference's outputs, committed), and
+  * the C oracle on the same seeded inputs.
+Integer / byte work: the bar is bit-exact equality of the canonical stream."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.cases import CASES
+from tests.util import canon_md5, case_files, oracle_on_paths
+from twopaco_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_create_enumerator_matches_reference_golden(name, golden, tmp_path):
+    """Level 1 (tpc_build == CreateEnumerator): FASTA files -> de_bruijn.bin."""
+    spec, g = CASES[name], golden[name]
+    out = str(tmp_path / "de_bruijn.bin")
+    with case_files(spec) as (paths, _, d):
+        ve = api.CreateEnumerator(paths, spec["k"], spec.get("f", 24), hashFunctions=spec.get("q", 5), rounds=1, threads=4,
+                                  abundance=spec.get("abundance", api.ABUNDANCE_MAX), tmpDirName=d, outFileName=out)
+        oracle_img, nj, nm = oracle_on_paths(paths, spec["k"], spec.get("abundance", 2**64 - 1))
+    img = open(out, "rb").read()
+    assert len(img) == g["image_bytes"]
+    assert ve.GetVerticesCount() == g["distinct_junctions"] == nj
+    assert canon_md5(img) == g["canon_md5"], "canonical stream differs from the reference's"
+    assert O.canon_equal(img, oracle_img)
+    st = ve.stats()
+    assert st.occurrences == g["true_marks"] == nm
+    assert f"True junctions count = {nj}" in ve.log and f"True marks count: {nm}" in ve.log
+    # ids: junctions 1..J by first appearance (first occurrence positive), stubs J+42.. in stream order
+    seq, pos, ids = O.decode(img)
+    _, _, oids = O.decode(oracle_img)
+    assert np.array_equal(ids, oids), "ids differ from the oracle's first-appearance numbering"
+    ve.close()
+
+
+@pytest.mark.parametrize("rounds", [2, 3, 4])
+@pytest.mark.parametrize("name", ["selftest_s1_k7", "selftest_s2_k9", "family_k25", "family_k63", "edge_mixed_k5"])
+def test_rounds_do_not_change_the_result(name, rounds, golden, tmp_path):
+    """-r: hash-range rounds (vertexenumerator.h:228-392) -- the reference's --test sweeps 1..4."""
+    spec, g = CASES[name], golden[name]
+    out = str(tmp_path / "o.bin")
+    with case_files(spec) as (paths, _, d):
+        ve = api.CreateEnumerator(paths, spec["k"], spec.get("f", 24), hashFunctions=spec.get("q", 5), rounds=rounds,
+                                  threads=2, tmpDirName=d, outFileName=out)
+    assert canon_md5(open(out, "rb").read()) == g["canon_md5"]
+    assert ve.GetVerticesCount() == g["distinct_junctions"]
+    ve.close()
+
+
+@pytest.mark.parametrize("q,f", [(1, 20), (2, 12), (3, 16), (8, 22), (5, 9)])
+def test_filter_shape_never_changes_the_result(q, f, golden):
+    """Tiny / saturated filters only add false candidates; pass 2 must remove them all."""
+    spec, g = CASES["family_k25"], golden["family_k25"]
+    with case_files(spec) as (paths, _, _):
+        recs = api.read_fasta(paths)
+    img, st = api.junctions_host(api.pack_records(recs), k=25, filter_bits=f, q=q)
+    assert canon_md5(bytes(img)) == g["canon_md5"]
+    assert st.junctions == g["distinct_junctions"] and st.candidate_kmers >= st.junctions
+
+
+def test_get_id_surface(golden):
+    """VertexEnumerator::GetId (vertexenumerator.h:98-102; test.cpp:234-242): every junction
+    k-mer has an id, its reverse complement the negated id, anything else INVALID_VERTEX."""
+    recs = synth.reference_selftest_set(77)
+    k = 9
+    oracle_img, nj, _ = O.find_junctions(recs, k)
+    s = api.Session(k=k, filter_bits=20)
+    s.set_genome_host(api.pack_records(recs))
+    s.find_candidates()
+    ptr, n = s.local_junctions()
+    assert n == nj
+    s.set_junctions(ptr, n)
+    seq, pos, ids = O.decode(oracle_img)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    seen = 0
+    for sq, p, i in list(zip(seq, pos, ids))[:400]:
+        kmer = recs[sq][p:p + k]
+        if abs(i) <= nj:
+            assert s.get_id(kmer.decode()) == i
+            assert s.get_id(kmer.translate(comp)[::-1].decode()) == -i
+            seen += 1
+        elif b"N" not in kmer:
+            assert s.get_id(kmer.decode()) == api.INVALID_VERTEX
+    assert seen > 50
+    assert s.get_id("ACGT") == api.INVALID_VERTEX          # wrong length
+    assert s.get_id("ACGTNACGT") == api.INVALID_VERTEX     # not definite
+    s.close()
+
+
+def test_empty_and_degenerate_inputs():
+    for recs in ([], [b""], [b"ACG"], [b"N" * 40], [b"ACGTACGTACG"], [b"", b"ACGTTGCAAGC", b""]):
+        ref, nj, nm = O.find_junctions(recs, 11)
+        img, st = api.junctions_host(api.pack_records(recs), k=11, filter_bits=16)
+        assert bytes(img) == ref, recs
+        assert st.junctions == nj and st.occurrences == nm
+
+
+def test_sharded_sessions_union_equals_unsharded():
+    """Hash-range shards (spatial -r): the union of the shards' junction sets and the OR of
+    their masks reproduce the single-GPU result (all shards run on this one GPU here)."""
+    import torch
+    recs = synth.founder_family(31, 6, 2, 40_000, 0.01, n_runs=2)
+    k = 25
+    ref, nj, _ = O.find_junctions(recs, k)
+    g = api.pack_records(recs)
+    shards = [api.Session(k=k, filter_bits=22, shard_index=i, shard_count=3) for i in range(3)]
+    lists, masks = [], []
+    for s in shards:
+        s.set_genome_host(g)
+        s.find_candidates()
+        ptr, n = s.local_junctions()
+        lists.append(_dev_to_torch(ptr, n, torch.int64).clone())
+        mptr, mw = s.candidate_mask()
+        masks.append(_dev_to_torch(mptr, mw, torch.int32))
+    allj = torch.cat(lists)
+    assert allj.numel() == nj
+    total = masks[0].clone()
+    for m in masks[1:]:
+        assert int((total & m).ne(0).sum()) == 0, "shard masks must be disjoint"
+        total |= m
+    s0 = shards[0]
+    masks[0].copy_(total)
+    s0.set_junctions(allj.data_ptr(), allj.numel())
+    nrec, nstub = s0.emit_count(0, g.n_positions)
+    out = torch.empty(12 * (nrec + len(recs)) + 16, dtype=torch.uint8, device="cuda")
+    off, nb = s0.emit_write(0, 0, out.data_ptr(), out.numel())
+    torch.cuda.synchronize()
+    assert off == 0 and bytes(out[:nb].cpu().numpy()) == ref
+    for s in shards:
+        s.close()
+
+
+def test_position_sliced_emit_concatenates():
+    """Position-sharded emit (multi-GPU output path): slices concatenate to the full image."""
+    import torch
+    recs = synth.founder_family(32, 5, 3, 30_000, 0.01, n_runs=1) + [b"ACG", b""] + synth.founder_family(33, 2, 1, 9_000, 0.02)
+    k = 31
+    ref, nj, _ = O.find_junctions(recs, k)
+    g = api.pack_records(recs)
+    s = api.Session(k=k, filter_bits=22)
+    s.set_genome_host(g)
+    s.find_candidates()
+    ptr, n = s.local_junctions()
+    s.set_junctions(ptr, n)
+    cuts = [0, 8192 * 3, 8192 * 20, 8192 * 21, 8192 * 40, g.n_positions]
+    counts = []
+    for a, b in zip(cuts, cuts[1:]):
+        counts.append(s.emit_count(a, b))
+    image = bytearray()
+    rb = sb = 0
+    for (a, b), (nr, ns) in zip(zip(cuts, cuts[1:]), counts):
+        s.emit_count(a, b)
+        out = torch.empty(12 * (nr + len(recs)) + 16, dtype=torch.uint8, device="cuda")
+        off, nb = s.emit_write(rb, sb, out.data_ptr(), out.numel())
+        torch.cuda.synchronize()
+        assert off == len(image)
+        image += bytes(out[:nb].cpu().numpy())
+        rb += nr
+        sb += ns
+    assert bytes(image) == ref
+    s.close()
+
+
+class _DevArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _dev_to_torch(ptr, n, dtype):
+    import torch
+    typestr = {torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+    if n == 0:
+        return torch.empty(0, dtype=dtype, device="cuda")
+    return torch.as_tensor(_DevArray(ptr, n, typestr), device="cuda")
+
+
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref binaries did not travel")
+def test_live_reference_binary_on_the_gpu_box(tmp_path):
+    recs = synth.founder_family(808, 6, 2, 80_000, 0.01, n_runs=2)
+    p = tmp_path / "in.fa"
+    O.write_fasta(str(p), recs)
+    ref_img, _ = O.run_reference([str(p)], 25, 24, q=5, r=1, t=os.cpu_count() or 1)
+    out = str(tmp_path / "o.bin")
+    ve = api.CreateEnumerator([str(p)], 25, 24, outFileName=out, tmpDirName=str(tmp_path))
+    assert O.canon_equal(open(out, "rb").read(), ref_img)
+    ve.close()
+
+
+def test_full_size_properties_c2_slice():
+    """Size-independent properties at a larger size (oracle too slow): idempotence across
+    filter shapes / rounds, strand symmetry (reverse-complemented input gives the mirrored
+    stream), sortedness, and the id/stub invariants."""
+    recs = synth.founder_family(0xEC01, 12, 1, 1_000_000, 0.01)
+    g = api.pack_records(recs)
+    img_a, st_a = api.junctions_host(g, k=25, filter_bits=30, q=5)
+    img_b, st_b = api.junctions_host(g, k=25, filter_bits=24, q=2, rounds=3)
+    assert bytes(img_a) == bytes(img_b) and st_a.junctions == st_b.junctions
+    seq, pos, ids = O.decode(bytes(img_a))
+    order = np.lexsort((pos, seq))
+    assert np.array_equal(order, np.arange(len(pos))), "records must be sorted by (seq, pos)"
+    J = st_a.junctions
+    junction = np.abs(ids) <= J
+    assert set(np.abs(ids[junction]).tolist()) == set(range(1, J + 1))
+    stubs = ids[~junction]
+    assert np.array_equal(stubs, J + 42 + np.arange(len(stubs)))
+    # strand symmetry: reverse-complement every record
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    rc = [r.translate(comp)[::-1] for r in recs]
+    img_c, st_c = api.junctions_host(api.pack_records(rc), k=25, filter_bits=30)
+    assert st_c.junctions == J
+    seq_c, pos_c, ids_c = O.decode(bytes(img_c))
+    lens = np.array([len(r) for r in recs], dtype=np.int64)
+    mirrored = sorted(zip(seq_c.tolist(), (lens[seq_c] - 25 - pos_c.astype(np.int64)).tolist()))
+    assert mirrored == sorted(zip(seq.tolist(), pos.astype(np.int64).tolist()))

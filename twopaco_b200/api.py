@@ -1,0 +1,299 @@
+"""ctypes binding of libtwopaco_b200.so (include/twopaco_b200.h) -- plumbing only.
+
+Every function here calls straight into the CUDA library; there is no Python or CPU
+implementation of the path behind it.  If the library is missing, or no GPU is present,
+calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libtwopaco_b200.so"
+
+ABUNDANCE_MAX = 2**64 - 1
+INVALID_VERTEX = 2**63 - 1
+TILE_POSITIONS = 8192
+
+
+class TpcError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("filter_bits", C.c_uint32), ("q", C.c_uint32), ("rounds", C.c_uint32),
+                ("abundance", C.c_uint64), ("shard_index", C.c_uint32), ("shard_count", C.c_uint32),
+                ("seed", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("positions", C.c_uint64), ("candidate_marks", C.c_uint64), ("candidate_kmers", C.c_uint64),
+                ("junctions", C.c_uint64), ("occurrences", C.c_uint64), ("stubs", C.c_uint64),
+                ("out_bytes", C.c_uint64), ("filter_edges_set", C.c_uint64),
+                ("ms_fill", C.c_float), ("ms_query", C.c_float), ("ms_insert", C.c_float), ("ms_classify", C.c_float),
+                ("ms_index", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float),
+                ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+
+    def asdict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+class Genome(C.Structure):
+    _fields_ = [("codes", C.c_void_p), ("n_mask", C.c_void_p), ("n_positions", C.c_uint64),
+                ("rec_start", C.c_void_p), ("rec_len", C.c_void_p), ("n_records", C.c_uint64)]
+
+
+LOG_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
+
+# name -> (restype, argtypes); also the list test_abi checks against the header
+SIGNATURES = {
+    "tpc_code_words": (C.c_uint64, [C.c_uint64]),
+    "tpc_mask_words": (C.c_uint64, [C.c_uint64]),
+    "tpc_positions_for": (C.c_uint64, [C.c_void_p, C.c_uint64]),
+    "tpc_pack_records": (C.c_int, [C.POINTER(C.c_char_p), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tpc_read_fasta": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(C.c_char_p)), C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]),
+    "tpc_free_records": (None, [C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint64]),
+    "tpc_build": (C.c_int, [C.POINTER(C.c_char_p), C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                            C.c_uint64, C.c_char_p, C.c_char_p, LOG_FN, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tpc_vertices": (C.c_uint64, [C.c_void_p]),
+    "tpc_get_id": (C.c_int64, [C.c_void_p, C.c_char_p]),
+    "tpc_handle_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "tpc_free": (None, [C.c_void_p]),
+    "tpc_junctions_host": (C.c_int, [C.POINTER(Params), C.POINTER(Genome), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(Stats)]),
+    "tpc_session_create": (C.c_int, [C.POINTER(Params), C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tpc_session_destroy": (None, [C.c_void_p]),
+    "tpc_session_set_genome_host": (C.c_int, [C.c_void_p, C.POINTER(Genome)]),
+    "tpc_session_set_genome_device": (C.c_int, [C.c_void_p, C.POINTER(Genome)]),
+    "tpc_session_find_candidates": (C.c_int, [C.c_void_p]),
+    "tpc_session_local_junctions": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "tpc_session_set_junctions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "tpc_session_candidate_mask": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "tpc_session_emit_count": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "tpc_session_emit_write": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "tpc_session_get_id": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
+    "tpc_session_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "tpc_random_access_probe": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_double)]),
+    "tpc_last_error": (C.c_char_p, []),
+    "tpc_abi_version": (C.c_uint32, []),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise TpcError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(twopaco_b200 has no CPU fallback)")
+        L = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise TpcError(lib().tpc_last_error().decode(errors="replace"))
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side packing
+# ---------------------------------------------------------------------------------------------
+class PackedGenome:
+    """2-bit packed genome in host memory (numpy arrays; layout: include/twopaco_b200.h)."""
+
+    def __init__(self, codes, n_mask, n_positions, rec_start, rec_len):
+        self.codes, self.n_mask, self.n_positions = codes, n_mask, int(n_positions)
+        self.rec_start, self.rec_len = rec_start, rec_len
+
+    @property
+    def n_records(self) -> int:
+        return len(self.rec_len)
+
+    @property
+    def total_bp(self) -> int:
+        return int(self.rec_len.sum())
+
+    def struct(self) -> Genome:
+        return Genome(self.codes.ctypes.data, self.n_mask.ctypes.data, self.n_positions,
+                      self.rec_start.ctypes.data, self.rec_len.ctypes.data, self.n_records)
+
+
+def pack_records(records: list[bytes], threads: int = 0) -> PackedGenome:
+    L = lib()
+    n = len(records)
+    rec_len = np.array([len(r) for r in records], dtype=np.uint64)
+    npos = L.tpc_positions_for(rec_len.ctypes.data, n)
+    codes = np.empty(L.tpc_code_words(npos), dtype=np.uint64)
+    n_mask = np.empty(L.tpc_mask_words(npos), dtype=np.uint64)
+    rec_start = np.empty(max(n, 1), dtype=np.uint64)[:n]
+    arr = (C.c_char_p * max(n, 1))(*records)
+    _check(L.tpc_pack_records(arr, rec_len.ctypes.data, n, threads or os.cpu_count() or 1,
+                              codes.ctypes.data, n_mask.ctypes.data, rec_start.ctypes.data if n else None))
+    return PackedGenome(codes, n_mask, npos, rec_start, rec_len)
+
+
+def read_fasta(paths: list[str]) -> list[bytes]:
+    L = lib()
+    recs = C.POINTER(C.c_char_p)()
+    lens = C.POINTER(C.c_uint64)()
+    n = C.c_uint64(0)
+    try:
+        for p in paths:
+            _check(L.tpc_read_fasta(os.fsencode(p), C.byref(recs), C.byref(lens), C.byref(n)))
+        return [C.string_at(recs[i], lens[i]) for i in range(n.value)]
+    finally:
+        L.tpc_free_records(recs, lens, n.value)
+
+
+# ---------------------------------------------------------------------------------------------
+# level 2: packed host genome -> image
+# ---------------------------------------------------------------------------------------------
+def junctions_host(genome: PackedGenome, k: int, filter_bits: int, q: int = 5, rounds: int = 1,
+                   abundance: int = ABUNDANCE_MAX, seed: int = 0, out: np.ndarray | None = None):
+    """-> (image bytes as numpy uint8 view, Stats).  `out` may be a preallocated (pinned) buffer."""
+    L = lib()
+    prm = Params(k, filter_bits, q, rounds, abundance, 0, 1, seed)
+    g = genome.struct()
+    st = Stats()
+    nbytes = C.c_uint64(0)
+    if out is None:
+        out = np.empty(max(12 * (genome.n_records * 2 + 1024), 1 << 16), dtype=np.uint8)
+    rc = L.tpc_junctions_host(C.byref(prm), C.byref(g), out.ctypes.data, out.nbytes, C.byref(nbytes), C.byref(st))
+    if rc == 2:  # buffer too small: retry with the exact size
+        out = np.empty(nbytes.value, dtype=np.uint8)
+        rc = L.tpc_junctions_host(C.byref(prm), C.byref(g), out.ctypes.data, out.nbytes, C.byref(nbytes), C.byref(st))
+    _check(rc)
+    return out[:nbytes.value], st
+
+
+# ---------------------------------------------------------------------------------------------
+# level 1: files -> file (the reference's CreateEnumerator)
+# ---------------------------------------------------------------------------------------------
+class VertexEnumerator:
+    """Mirror of TwoPaCo::VertexEnumerator (vertexenumerator.h:23-35)."""
+
+    def __init__(self, handle, log_text: str):
+        self._h = handle
+        self.log = log_text
+
+    def GetVerticesCount(self) -> int:
+        return lib().tpc_vertices(self._h)
+
+    def GetId(self, vertex: str) -> int:
+        return lib().tpc_get_id(self._h, vertex.encode())
+
+    def stats(self) -> Stats:
+        st = Stats()
+        _check(lib().tpc_handle_stats(self._h, C.byref(st)))
+        return st
+
+    def close(self) -> None:
+        if self._h:
+            lib().tpc_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def CreateEnumerator(fileName: list[str], vertexLength: int, filterSize: int, hashFunctions: int = 5, rounds: int = 1,
+                     threads: int = 1, abundance: int = ABUNDANCE_MAX, tmpDirName: str = ".",
+                     outFileName: str = "de_bruijn.bin") -> VertexEnumerator:
+    """TwoPaCo::CreateEnumerator (vertexenumerator.h:37-46) on the current CUDA device."""
+    L = lib()
+    chunks: list[str] = []
+    cb = LOG_FN(lambda ctx, text: chunks.append(text.decode(errors="replace")))
+    arr = (C.c_char_p * len(fileName))(*[os.fsencode(p) for p in fileName])
+    h = C.c_void_p()
+    _check(L.tpc_build(arr, len(fileName), vertexLength, filterSize, hashFunctions, rounds, threads, abundance,
+                       os.fsencode(tmpDirName), os.fsencode(outFileName), cb, None, C.byref(h)))
+    return VertexEnumerator(h, "".join(chunks))
+
+
+# ---------------------------------------------------------------------------------------------
+# level 3: sessions
+# ---------------------------------------------------------------------------------------------
+class Session:
+    def __init__(self, k: int, filter_bits: int, q: int = 5, rounds: int = 1, abundance: int = ABUNDANCE_MAX,
+                 shard_index: int = 0, shard_count: int = 1, seed: int = 0, stream: int = 0):
+        self._s = C.c_void_p()
+        prm = Params(k, filter_bits, q, rounds, abundance, shard_index, shard_count, seed)
+        _check(lib().tpc_session_create(C.byref(prm), C.c_void_p(stream), C.byref(self._s)))
+        self._keep = None
+
+    def set_genome_host(self, genome: PackedGenome) -> None:
+        self._keep = genome
+        g = genome.struct()
+        _check(lib().tpc_session_set_genome_host(self._s, C.byref(g)))
+
+    def set_genome_device(self, codes_ptr: int, n_mask_ptr: int, n_positions: int, rec_start: np.ndarray,
+                          rec_len: np.ndarray, keep=None) -> None:
+        self._keep = (keep, rec_start, rec_len)
+        g = Genome(codes_ptr, n_mask_ptr, n_positions, rec_start.ctypes.data, rec_len.ctypes.data, len(rec_len))
+        _check(lib().tpc_session_set_genome_device(self._s, C.byref(g)))
+
+    def find_candidates(self) -> None:
+        _check(lib().tpc_session_find_candidates(self._s))
+
+    def local_junctions(self) -> tuple[int, int]:
+        p, n = C.c_void_p(), C.c_uint64()
+        _check(lib().tpc_session_local_junctions(self._s, C.byref(p), C.byref(n)))
+        return p.value or 0, n.value
+
+    def set_junctions(self, dev_ptr: int, count: int) -> None:
+        _check(lib().tpc_session_set_junctions(self._s, C.c_void_p(dev_ptr), count))
+
+    def candidate_mask(self) -> tuple[int, int]:
+        p, n = C.c_void_p(), C.c_uint64()
+        _check(lib().tpc_session_candidate_mask(self._s, C.byref(p), C.byref(n)))
+        return p.value or 0, n.value
+
+    def emit_count(self, pos_begin: int, pos_end: int) -> tuple[int, int]:
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(lib().tpc_session_emit_count(self._s, pos_begin, pos_end, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def emit_write(self, records_before: int, stubs_before: int, dev_out: int, capacity: int) -> tuple[int, int]:
+        off, nb = C.c_uint64(), C.c_uint64()
+        _check(lib().tpc_session_emit_write(self._s, records_before, stubs_before, C.c_void_p(dev_out), capacity,
+                                            C.byref(off), C.byref(nb)))
+        return off.value, nb.value
+
+    def get_id(self, kmer: str) -> int:
+        v = C.c_int64()
+        _check(lib().tpc_session_get_id(self._s, kmer.encode(), C.byref(v)))
+        return v.value
+
+    def stats(self) -> Stats:
+        st = Stats()
+        _check(lib().tpc_session_stats(self._s, C.byref(st)))
+        return st
+
+    def close(self) -> None:
+        if self._s:
+            lib().tpc_session_destroy(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def random_access_probe(filter_bits: int, mode: int, touches: int = 1 << 30) -> float:
+    v = C.c_double()
+    _check(lib().tpc_random_access_probe(filter_bits, mode, touches, C.byref(v)))
+    return v.value

@@ -1,0 +1,303 @@
+// tpc_device.cuh -- device-side primitives shared by the junction-finding kernels (sm_100a).
+//
+// Data layout in HBM:
+//   codes   : 2 bits / position, position p -> bits 2(p%32) of 64-bit word p/32 (A0 C1 G2 T3)
+//             == the reference's CompressedString layout (compressedstring.h:239-264) applied
+//             to the whole genome.
+//   n_mask  : 1 bit / position (1 = 'N' / record separator / padding).
+//   k-mers  : W = ceil(k/32) 64-bit words, base j of the k-mer at bits 2(j%32) of word j/32
+//             ("LSB-first").  X = k-mer as written, Y = its reverse complement.  canonical =
+//             min(X, Y) compared from the most significant word.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tpc {
+
+constexpr int kTileThreads = 256;
+constexpr int kPosPerThread = 32;
+constexpr int kTilePos = kTileThreads * kPosPerThread;  // 8192 positions per CTA tile
+
+constexpr int kPosBits = 40;
+constexpr uint64_t kPosMask = (1ull << kPosBits) - 1;
+
+// meta word of a candidate-table slot (canonical orientation of the k-mer)
+constexpr uint64_t kMetaInN1 = 1ull << 8;    // an 'N' / sequence end seen on the in side
+constexpr uint64_t kMetaInN2 = 1ull << 9;    // ... seen at least twice (every N is unique)
+constexpr uint64_t kMetaOutN1 = 1ull << 10;
+constexpr uint64_t kMetaOutN2 = 1ull << 11;
+constexpr int kMetaCountShift = 16;          // occurrence count (only when -a is given)
+
+template <int W>
+struct Kmer {
+    uint64_t w[W];
+};
+
+struct GenomeView {
+    const uint64_t* __restrict__ codes;
+    const uint64_t* __restrict__ nmask;
+    uint64_t npos;
+};
+
+struct Slot {  // candidate table T and junction index J
+    unsigned long long rep;   // 0 = empty, else tag(24) << 40 | position(40) of an occurrence
+    unsigned long long meta;  // T: neighbour flags | count << 16      J: junction id
+};
+
+struct TableView {
+    Slot* slots;
+    uint32_t log2cap;
+};
+
+struct KParams {
+    uint32_t k;
+    uint32_t q;
+    uint32_t sector_shift;   // 64 - log2(#sectors)
+    uint32_t nparts;         // rounds * shard_count
+    uint32_t part;           // part processed by this launch
+    uint32_t count_occurrences;
+    uint64_t seed;
+};
+
+__device__ __forceinline__ uint64_t fmix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x85ebca6bu;
+    x ^= x >> 13; x *= 0xc2b2ae35u;
+    x ^= x >> 16;
+    return x;
+}
+
+// reverse the order of the 32 two-bit groups of a word
+__device__ __forceinline__ uint64_t pairrev64(uint64_t x) {
+    x = __brevll(x);
+    return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+}
+
+template <int W>
+__device__ __forceinline__ uint64_t top_mask(uint32_t k) {
+    uint32_t bits = 2 * k - 64 * (W - 1);  // 2..62 (k odd, W = ceil(k/32))
+    return (~0ull) >> (64 - bits);
+}
+
+// 64 consecutive 2-bit... no: 32 bases (64 bits) starting at position p
+__device__ __forceinline__ uint64_t load_bases32(const uint64_t* __restrict__ codes, uint64_t p) {
+    uint64_t wi = p >> 5;
+    uint32_t sh = 2 * (uint32_t)(p & 31);
+    uint64_t lo = __ldg(codes + wi);
+    uint64_t hi = __ldg(codes + wi + 1);
+    return (lo >> sh) | ((hi << 1) << (63 - sh));
+}
+
+__device__ __forceinline__ uint32_t load_base(const uint64_t* __restrict__ codes, uint64_t p) {
+    return (uint32_t)(__ldg(codes + (p >> 5)) >> (2 * (p & 31))) & 3u;
+}
+
+__device__ __forceinline__ uint32_t load_n(const uint64_t* __restrict__ nmask, uint64_t p) {
+    return (uint32_t)(__ldg(nmask + (p >> 6)) >> (p & 63)) & 1u;
+}
+
+// 64 n-mask bits starting at position p
+__device__ __forceinline__ uint64_t load_nbits64(const uint64_t* __restrict__ nmask, uint64_t p) {
+    uint64_t wi = p >> 6;
+    uint32_t sh = (uint32_t)(p & 63);
+    uint64_t lo = __ldg(nmask + wi);
+    uint64_t hi = __ldg(nmask + wi + 1);
+    return (lo >> sh) | ((hi << 1) << (63 - sh));
+}
+
+// any 'N' among positions [p, p+len) ?
+__device__ __forceinline__ bool any_n(const uint64_t* __restrict__ nmask, uint64_t p, uint32_t len) {
+    uint64_t acc = 0;
+    for (uint32_t off = 0; off < len; off += 64) {
+        uint64_t b = load_nbits64(nmask, p + off);
+        uint32_t rem = len - off;
+        if (rem < 64) b &= (~0ull) >> (64 - rem);
+        acc |= b;
+    }
+    return acc != 0;
+}
+
+template <int W>
+__device__ __forceinline__ Kmer<W> extract_kmer(const uint64_t* __restrict__ codes, uint64_t p, uint32_t k) {
+    Kmer<W> x;
+    uint64_t wi = p >> 5;
+    uint32_t sh = 2 * (uint32_t)(p & 31);
+    uint64_t lo = __ldg(codes + wi);
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        uint64_t hi = __ldg(codes + wi + j + 1);
+        x.w[j] = (lo >> sh) | ((hi << 1) << (63 - sh));
+        lo = hi;
+    }
+    x.w[W - 1] &= top_mask<W>(k);
+    return x;
+}
+
+template <int W>
+__device__ __forceinline__ Kmer<W> revcomp(const Kmer<W>& x, uint32_t k) {
+    uint64_t t[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) t[j] = pairrev64(~x.w[W - 1 - j]);
+    uint32_t s = 64 * W - 2 * k;  // 2..62
+    Kmer<W> y;
+#pragma unroll
+    for (int j = 0; j < W - 1; ++j) y.w[j] = (t[j] >> s) | (t[j + 1] << (64 - s));
+    y.w[W - 1] = t[W - 1] >> s;
+    return y;
+}
+
+// advance both strands by one base: X drops its first base and appends `next`
+template <int W>
+__device__ __forceinline__ void roll(Kmer<W>& x, Kmer<W>& y, uint32_t next, uint32_t k) {
+    uint32_t topbits = 2 * k - 64 * (W - 1);
+#pragma unroll
+    for (int j = 0; j < W - 1; ++j) x.w[j] = (x.w[j] >> 2) | (x.w[j + 1] << 62);
+    x.w[W - 1] = (x.w[W - 1] >> 2) | ((uint64_t)next << (topbits - 2));
+#pragma unroll
+    for (int j = W - 1; j > 0; --j) y.w[j] = (y.w[j] << 2) | (y.w[j - 1] >> 62);
+    y.w[0] = (y.w[0] << 2) | (uint64_t)(3u - next);
+    y.w[W - 1] &= (~0ull) >> (64 - topbits);
+}
+
+template <int W>
+__device__ __forceinline__ bool kmer_less(const Kmer<W>& a, const Kmer<W>& b) {
+#pragma unroll
+    for (int j = W - 1; j > 0; --j)
+        if (a.w[j] != b.w[j]) return a.w[j] < b.w[j];
+    return a.w[0] < b.w[0];
+}
+
+template <int W>
+__device__ __forceinline__ bool kmer_eq(const Kmer<W>& a, const Kmer<W>& b) {
+    bool e = true;
+#pragma unroll
+    for (int j = 0; j < W; ++j) e = e && (a.w[j] == b.w[j]);
+    return e;
+}
+
+template <int W>
+__device__ __forceinline__ uint64_t kmer_hash(const Kmer<W>& c, uint64_t seed) {
+    uint64_t h = seed ^ 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int j = 0; j < W; ++j) h = fmix64(h ^ c.w[j]);
+    return h;
+}
+
+// ---- values derived from the 64-bit hash of the canonical k-mer -------------------------
+__device__ __forceinline__ uint32_t hash_part(uint64_t h, uint32_t nparts) {
+    return __umulhi((uint32_t)h, nparts);
+}
+__device__ __forceinline__ uint64_t hash_sector(uint64_t h, uint32_t sector_shift) {
+    return h >> sector_shift;
+}
+__device__ __forceinline__ uint64_t hash_tag(uint64_t h) {
+    return ((h >> 8) & 0xFFFFFFull) << kPosBits;
+}
+__device__ __forceinline__ uint64_t hash_slot(uint64_t h, uint32_t log2cap) {
+    return (h * 0x9E3779B97F4A7C15ull) >> (64 - log2cap);
+}
+
+// Bloom bits of edge slot `slot` (0..3 in-edge by base, 4..7 out-edge by base, canonical
+// orientation) inside that slot's 32-bit word of the vertex's sector: Q bit positions.
+template <int Q>
+__device__ __forceinline__ uint32_t slot_bits(uint64_t h, uint32_t slot) {
+    uint32_t g = fmix32((uint32_t)h + slot * 0x9E3779B9u + (uint32_t)(h >> 32) * 0x85EBCA77u);
+    uint32_t m = 0;
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+        if (t == 6) g = g * 0x9E3779B1u + 0x7F4A7C15u, g ^= g >> 15;
+        m |= 1u << ((g >> (5 * (t % 6))) & 31u);
+    }
+    return m;
+}
+
+// ---- per-thread window over 32 consecutive positions ------------------------------------
+// Thread handles positions [32*w, 32*w+32).  After load(): X/Y = k-mer at 32*w; next_feed /
+// prev_feed hold the 32 "next" bases (positions 32w+k ..) and the 32 "prev" bases (32w-1 ..);
+// valid / prev_n / next_n are per-position bit masks.
+template <int W>
+struct Window {
+    Kmer<W> X, Y;
+    uint64_t next_feed, prev_feed;
+    uint32_t valid, prev_n, next_n;
+
+    __device__ __forceinline__ void load(const GenomeView& g, uint64_t w, uint32_t k) {
+        const uint64_t* __restrict__ codes = g.codes;
+        uint64_t cprev = w ? __ldg(codes + w - 1) : 0ull;
+        uint64_t c[W + 1];
+#pragma unroll
+        for (int j = 0; j <= W; ++j) c[j] = __ldg(codes + w + j);
+#pragma unroll
+        for (int j = 0; j < W; ++j) X.w[j] = c[j];
+        X.w[W - 1] &= top_mask<W>(k);
+        Y = revcomp<W>(X, k);
+        uint32_t kb2 = 2 * (k - 32 * (W - 1));  // 2..62
+        next_feed = (c[W - 1] >> kb2) | (c[W] << (64 - kb2));
+        prev_feed = (c[0] << 2) | (cprev >> 62);
+
+        uint64_t p0 = w * 32;
+        // N bits of positions [p0-1, p0+32+k]
+        bool has_n;
+        if (w == 0) has_n = true;  // position 0 is always a separator
+        else has_n = any_n(g.nmask, p0 - 1, 34 + k);
+        if (!has_n) {
+            valid = ~0u; prev_n = 0; next_n = 0;
+        } else {
+            valid = 0; prev_n = 0; next_n = 0;
+            uint32_t run = 0;
+            for (uint32_t j = 0; j + 1 < k; ++j) run = load_n(g.nmask, p0 + j) ? 0 : run + 1;
+            for (uint32_t i = 0; i < 32; ++i) {
+                run = load_n(g.nmask, p0 + i + k - 1) ? 0 : run + 1;
+                if (run >= k) valid |= 1u << i;
+                bool pn = (p0 + i == 0) ? true : load_n(g.nmask, p0 + i - 1);
+                if (pn) prev_n |= 1u << i;
+                if (load_n(g.nmask, p0 + i + k)) next_n |= 1u << i;
+            }
+        }
+    }
+};
+
+// neighbours of an occurrence in the orientation of its canonical k-mer
+// (candidateoccurence.h:34-47): a = in-edge base, b = out-edge base.
+struct Neigh {
+    uint32_t a, b;
+    bool a_n, b_n;
+};
+__device__ __forceinline__ Neigh orient(bool fwd_is_canon, uint32_t prv, uint32_t nxt, bool prv_n, bool nxt_n) {
+    Neigh r;
+    if (fwd_is_canon) { r.a = prv; r.a_n = prv_n; r.b = nxt; r.b_n = nxt_n; }
+    else { r.a = 3u - nxt; r.a_n = nxt_n; r.b = 3u - prv; r.b_n = prv_n; }
+    return r;
+}
+
+__device__ __forceinline__ uint4 ld_nc_v4(const uint32_t* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// block-wide sum of a 64-bit value (all threads must call); result valid in thread 0
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long v, unsigned long long* smem /* >= 8 */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) smem[wid] = v;
+    __syncthreads();
+    unsigned long long t = 0;
+    if (threadIdx.x < 32) {
+        t = (threadIdx.x < (blockDim.x >> 5)) ? smem[threadIdx.x] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    }
+    return t;
+}
+
+}  // namespace tpc

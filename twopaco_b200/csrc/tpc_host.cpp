@@ -1,0 +1,307 @@
+// tpc_host.cpp -- host side of libtwopaco_b200.so: FASTA framing, 2-bit packing and the level-1
+// drop-in entry point tpc_build() (== TwoPaCo::CreateEnumerator, vertexenumerator.h:37-46).
+// No CUDA kernels here; all compute goes through the session API (tpc_session.cu).
+#include <algorithm>
+#include <atomic>
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime_api.h>
+
+#include "tpc_internal.h"
+
+using tpc::set_error;
+
+namespace {
+
+// dnachar.cpp:9-11: VALID_CHARS; :18-33 MakeUpChar.  Table value: 0..3 = ACGT, 4 = valid
+// non-definite (-> 'N', vertexenumerator.h:1174), 5 = whitespace, 6 = invalid.
+struct CharTable {
+    uint8_t t[256];
+    CharTable() {
+        for (int i = 0; i < 256; ++i) t[i] = isspace(i) ? 5 : 6;
+        for (const char* p = "ACGTURYKMSWBDHWNXV"; *p; ++p) {
+            t[(unsigned char)*p] = 4;
+            t[(unsigned char)tolower(*p)] = 4;  // GetChar upper-cases first (streamfastaparser.cpp:79-88)
+        }
+        const char* acgt = "ACGT";
+        for (int i = 0; i < 4; ++i) {
+            t[(unsigned char)acgt[i]] = (uint8_t)i;
+            t[(unsigned char)tolower(acgt[i])] = (uint8_t)i;
+        }
+    }
+};
+const CharTable kChars;
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------
+// FASTA framing (streamfastaparser.cpp:29-133)
+// ---------------------------------------------------------------------------------------------
+int tpc_read_fasta(const char* path, char*** records, uint64_t** rec_len, uint64_t* n_records) {
+    if (!path || !records || !rec_len || !n_records) return set_error("null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return set_error("Can't open file %s", path);
+    std::vector<char> buf(1 << 20);  // the reference also reads 1 MiB blocks (streamfastaparser.h BUF_SIZE)
+    uint64_t n = *n_records, cap = n;
+    char** recs = *records;
+    uint64_t* lens = *rec_len;
+    std::string cur;
+    std::string header;
+    enum { kStart, kHeader, kSeq } state = kStart;
+    bool have_record = false;
+    int rc = 0;
+    auto flush = [&]() -> int {
+        if (!have_record) return 0;
+        if (n == cap) {
+            cap = cap ? cap * 2 : 16;
+            char** nr = (char**)realloc(recs, cap * sizeof(char*));
+            uint64_t* nl = (uint64_t*)realloc(lens, cap * sizeof(uint64_t));
+            if (!nr || !nl) return set_error("out of memory");
+            recs = nr; lens = nl;
+        }
+        char* s = (char*)malloc(cur.size() + 1);
+        if (!s) return set_error("out of memory");
+        memcpy(s, cur.data(), cur.size());
+        s[cur.size()] = 0;
+        recs[n] = s; lens[n] = cur.size(); ++n;
+        cur.clear();
+        have_record = false;
+        return 0;
+    };
+    size_t got;
+    while (rc == 0 && (got = fread(buf.data(), 1, buf.size(), f)) > 0) {
+        for (size_t i = 0; i < got && rc == 0; ++i) {
+            unsigned char ch = (unsigned char)buf[i];
+            switch (state) {
+                case kStart:
+                    if (ch != '>') { rc = set_error("The FASTA header should start with a '>', started with '%c'", ch); break; }
+                    state = kHeader; header.clear(); have_record = true;
+                    break;
+                case kHeader:
+                    if (ch == '\n') state = kSeq; else header.push_back((char)ch);
+                    break;
+                case kSeq: {
+                    uint8_t c = kChars.t[ch];
+                    if (c < 4) cur.push_back("ACGT"[c]);
+                    else if (c == 4) cur.push_back('N');
+                    else if (c == 5) {}
+                    else if (ch == '>') { rc = flush(); state = kHeader; header.clear(); have_record = true; }
+                    else {
+                        std::istringstream hs(header); std::string first; hs >> first;
+                        rc = set_error("Found an invalid character '%c' in sequence %s", ch, first.c_str());
+                    }
+                    break;
+                }
+            }
+        }
+    }
+    fclose(f);
+    if (rc == 0) rc = flush();
+    *records = recs; *rec_len = lens; *n_records = n;
+    return rc;
+}
+
+void tpc_free_records(char** records, uint64_t* rec_len, uint64_t n_records) {
+    if (records) for (uint64_t i = 0; i < n_records; ++i) free(records[i]);
+    free(records);
+    free(rec_len);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2-bit packing of the whole input (layout: include/twopaco_b200.h, tpc_genome)
+// ---------------------------------------------------------------------------------------------
+int tpc_pack_records(const char* const* records, const uint64_t* rec_len, uint64_t n_records, uint32_t threads,
+                     uint64_t* codes, uint64_t* n_mask, uint64_t* rec_start) {
+    if ((n_records && (!records || !rec_len)) || !codes || !n_mask) return set_error("null argument");
+    uint64_t npos = tpc_positions_for(rec_len, n_records);
+    uint64_t cw = tpc_code_words(npos), mw = tpc_mask_words(npos);
+    std::vector<uint64_t> start(n_records);
+    uint64_t p = 1;
+    for (uint64_t i = 0; i < n_records; ++i) { start[i] = p; p += rec_len[i] + 1; }
+    if (rec_start) std::copy(start.begin(), start.end(), rec_start);
+
+    // Work unit = 64 positions (one n_mask word, two code words), so threads never share words.
+    const uint64_t blocks = mw;  // covers the padding too
+    threads = std::max<uint32_t>(1, std::min<uint32_t>(threads, 256));
+    std::atomic<uint64_t> next{0};
+    const uint64_t chunk = 1 << 12;  // 4096 blocks = 256 Ki positions per grab
+    auto worker = [&]() {
+        for (;;) {
+            uint64_t b0 = next.fetch_add(chunk);
+            if (b0 >= blocks) break;
+            uint64_t b1 = std::min(blocks, b0 + chunk);
+            // record containing (or following) the first position of the chunk
+            uint64_t pos = b0 * 64;
+            uint64_t r = std::upper_bound(start.begin(), start.end(), pos) - start.begin();
+            r = r ? r - 1 : 0;
+            for (uint64_t b = b0; b < b1; ++b) {
+                uint64_t lo = 0, hi = 0, nm = 0;
+                for (uint32_t j = 0; j < 64; ++j) {
+                    uint64_t q = b * 64 + j;
+                    uint64_t code = 0, isn = 1;
+                    if (q < npos && n_records) {
+                        while (r + 1 < n_records && q >= start[r + 1]) ++r;
+                        if (q >= start[r] && q < start[r] + rec_len[r]) {
+                            uint8_t c = kChars.t[(unsigned char)records[r][q - start[r]]];
+                            if (c < 4) { code = c; isn = 0; }
+                        }
+                    }
+                    if (j < 32) lo |= code << (2 * j); else hi |= code << (2 * (j - 32));
+                    nm |= isn << j;
+                }
+                if (2 * b < cw) codes[2 * b] = lo;
+                if (2 * b + 1 < cw) codes[2 * b + 1] = hi;
+                n_mask[b] = nm;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// level 1: tpc_build == CreateEnumerator
+// ---------------------------------------------------------------------------------------------
+struct tpc_handle {
+    tpc_session* session = nullptr;
+    tpc_stats stats{};
+    uint64_t junctions = 0;
+};
+
+namespace {
+struct Logger {
+    tpc_log_fn fn; void* ctx;
+    void operator()(const std::string& s) const { if (fn) fn(ctx, s.c_str()); }
+};
+}  // namespace
+
+extern "C" {
+
+int tpc_build(const char* const* fasta_paths, size_t n_files, uint32_t k, uint32_t filter_bits, uint32_t q,
+              uint32_t rounds, uint32_t threads, uint64_t abundance, const char* tmpdir, const char* outfile,
+              tpc_log_fn log, void* log_ctx, tpc_handle** out) {
+    (void)tmpdir;  // no temp files: candidate masks and junction keys stay in HBM (reference: h:219, 292)
+    if (!fasta_paths || !outfile || !out) return set_error("null argument");
+    *out = nullptr;
+    Logger L{log, log_ctx};
+    tpc_params prm{};
+    prm.k = k; prm.filter_bits = filter_bits; prm.q = q; prm.rounds = rounds ? rounds : 1;
+    prm.abundance = abundance; prm.shard_index = 0; prm.shard_count = 1; prm.seed = 0;
+    tpc_session* s = nullptr;
+    if (int rc = tpc_session_create(&prm, nullptr, &s)) return rc;
+
+    {   // log header, same lines as vertexenumerator.h:137-147
+        std::ostringstream ss;
+        ss << "Threads = " << threads << "\nVertex length = " << k << "\nHash functions = " << q
+           << "\nFilter size = " << (1ull << filter_bits) << "\nCapacity = " << (k + 4 + 31) / 32 << "\nFiles: \n";
+        for (size_t i = 0; i < n_files; ++i) ss << fasta_paths[i] << "\n";
+        L(ss.str());
+    }
+
+    char** recs = nullptr; uint64_t* lens = nullptr; uint64_t nrec = 0;
+    int rc = 0;
+    for (size_t i = 0; i < n_files && rc == 0; ++i) rc = tpc_read_fasta(fasta_paths[i], &recs, &lens, &nrec);
+    uint64_t *codes = nullptr, *nmask = nullptr;
+    std::vector<uint64_t> start(nrec);
+    uint64_t npos = 0;
+    if (rc == 0) {
+        for (uint64_t i = 0; i < nrec && rc == 0; ++i)
+            if (lens[i] >> 32) rc = set_error("sequence %llu is longer than 2^32 bp", (unsigned long long)i);
+    }
+    if (rc == 0) {
+        npos = tpc_positions_for(lens, nrec);
+        if (cudaMallocHost((void**)&codes, tpc_code_words(npos) * 8) != cudaSuccess ||
+            cudaMallocHost((void**)&nmask, tpc_mask_words(npos) * 8) != cudaSuccess)
+            rc = set_error("out of (pinned) host memory");
+    }
+    if (rc == 0) rc = tpc_pack_records(recs, lens, nrec, threads ? threads : 1, codes, nmask, start.data());
+    tpc_genome g{};
+    if (rc == 0) {
+        g.codes = codes; g.n_mask = nmask; g.n_positions = npos;
+        g.rec_start = start.data(); g.rec_len = lens; g.n_records = nrec;
+        rc = tpc_session_set_genome_host(s, &g);
+    }
+    uint64_t bytes = 0;
+    if (rc == 0) rc = tpc_session_run_to_count(s, &bytes);
+    uint8_t* image = nullptr;
+    if (rc == 0 && cudaMallocHost((void**)&image, std::max<uint64_t>(bytes, 16)) != cudaSuccess)
+        rc = set_error("out of (pinned) host memory");
+    if (rc == 0) rc = tpc_session_write_host(s, image, bytes);
+    tpc_stats st{};
+    if (rc == 0) rc = tpc_session_stats(s, &st);
+    if (rc == 0) {
+        // JunctionPositionWriter (junctionapi.h:110-116): creates / truncates the output file
+        FILE* f = fopen(outfile, "wb");
+        if (!f) rc = set_error("Can't create the output file");
+        else {
+            if (bytes && fwrite(image, 1, bytes, f) != bytes) rc = set_error("Can't write to the output file");
+            fclose(f);
+        }
+    }
+    if (rc == 0) {
+        std::ostringstream ss;
+        ss << std::string(80, '-') << "\n"
+           << "Round 0, 0:" << (1ull << filter_bits) << "\nPass\tFilling\tFiltering\n"
+           << "1\t" << (int)(st.ms_fill / 1000) << "\t" << (int)(st.ms_query / 1000) << "\t\n"
+           << "2\t" << (int)(st.ms_insert / 1000) << "\t" << (int)(st.ms_classify / 1000) << "\n"
+           << "True junctions count = " << st.junctions << "\n"
+           << "False junctions count = " << (st.candidate_kmers - st.junctions) << "\n"
+           << "Hash table size = " << st.candidate_kmers << "\n"
+           << "Candidate marks count = " << st.candidate_marks << "\n"
+           << std::string(80, '-') << "\n"
+           << "Reallocating bifurcations time: " << (int)(st.ms_index / 1000) << "\n"
+           << "True marks count: " << st.occurrences << "\n"
+           << "Edges construction time: " << (int)(st.ms_emit / 1000) << "\n"
+           << std::string(80, '-') << "\n";
+        L(ss.str());
+    }
+    if (image) cudaFreeHost(image);
+    if (codes) cudaFreeHost(codes);
+    if (nmask) cudaFreeHost(nmask);
+    tpc_free_records(recs, lens, nrec);
+    if (rc != 0) { tpc_session_destroy(s); return rc; }
+    tpc_handle* h = new (std::nothrow) tpc_handle();
+    if (!h) { tpc_session_destroy(s); return set_error("out of memory"); }
+    h->session = s; h->stats = st; h->junctions = st.junctions;
+    *out = h;
+    return 0;
+}
+
+uint64_t tpc_vertices(const tpc_handle* h) { return h ? h->junctions : 0; }
+
+int64_t tpc_get_id(const tpc_handle* h, const char* kmer) {
+    int64_t id = TPC_INVALID_VERTEX;
+    if (!h || !h->session) return id;
+    if (tpc_session_get_id(h->session, kmer, &id) != 0) return TPC_INVALID_VERTEX;
+    return id;
+}
+
+int tpc_handle_stats(const tpc_handle* h, tpc_stats* out) {
+    if (!h || !out) return set_error("null argument");
+    *out = h->stats;
+    return 0;
+}
+
+void tpc_free(tpc_handle* h) {
+    if (!h) return;
+    tpc_session_destroy(h->session);
+    delete h;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// tpc_kernels_common.cuh -- kernels that do not depend on the k-mer word count
+// (included by tpc_session.cu only).
+#pragma once
+#include "tpc_kernels.cuh"
+
+namespace tpc {
+
+__device__ __forceinline__ bool meta_is_junction(unsigned long long meta) {
+    int indeg = __popc((uint32_t)meta & 0xFu) + ((meta & kMetaInN2) ? 2 : (meta & kMetaInN1) ? 1 : 0);
+    int outdeg = __popc((uint32_t)(meta >> 4) & 0xFu) + ((meta & kMetaOutN2) ? 2 : (meta & kMetaOutN1) ? 1 : 0);
+    return indeg > 1 || outdeg > 1;
+}
+
+// TrueBifurcations (h:1228-1256): junction && Count <= abundance -> append its word
+__global__ void __launch_bounds__(256)
+k_classify(TableView T, uint64_t abundance, uint32_t use_abundance, unsigned long long* __restrict__ out,
+           uint64_t out_cap, Counters* ctr) {
+    uint64_t cap = 1ull << T.log2cap;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2 v = *reinterpret_cast<const ulonglong2*>(T.slots + i);
+        bool j = v.x != 0 && meta_is_junction(v.y);
+        bool drop = j && use_abundance && (v.y >> kMetaCountShift) > abundance;
+        if (drop) atomicAdd(&ctr->dropped, 1ull);
+        bool take = j && !drop;
+        // warp-aggregated append
+        unsigned ballot = __ballot_sync(__activemask(), take);
+        if (take) {
+            unsigned act = __activemask();
+            int lane = threadIdx.x & 31;
+            int leader = __ffs(ballot) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(&ctr->junctions, (unsigned long long)__popc(ballot));
+            base = __shfl_sync(act, base, leader);
+            unsigned long long at = base + __popc(ballot & ((1u << lane) - 1));
+            if (at < out_cap) out[at] = v.x & kPosMask;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// exclusive prefix sum over 64-bit counters (tile counts): 2048 items per CTA
+// ------------------------------------------------------------------------------------------
+constexpr int kScanItems = 8;
+constexpr int kScanBlock = 256 * kScanItems;
+
+__global__ void __launch_bounds__(256)
+k_scan_reduce(const unsigned long long* __restrict__ in, uint64_t n, unsigned long long* __restrict__ block_sums) {
+    __shared__ unsigned long long red[8];
+    uint64_t base = (uint64_t)blockIdx.x * kScanBlock;
+    unsigned long long s = 0;
+    for (int j = 0; j < kScanItems; ++j) {
+        uint64_t i = base + (uint64_t)j * 256 + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    unsigned long long t = block_sum(s, red);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
+}
+
+// in-place exclusive scan of one CTA-sized chunk, offset by block_prefix[blockIdx.x]
+__global__ void __launch_bounds__(256)
+k_scan_apply(unsigned long long* __restrict__ data, uint64_t n, const unsigned long long* __restrict__ block_prefix) {
+    __shared__ unsigned long long warp_tot[8];
+    uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanItems;
+    unsigned long long v[kScanItems];
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) { v[j] = (base + j < n) ? data[base + j] : 0ull; sum += v[j]; }
+    unsigned long long incl = sum;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    unsigned long long run = block_prefix ? block_prefix[blockIdx.x] : 0ull;
+    for (int j = 0; j < wid; ++j) run += warp_tot[j];
+    run += incl - sum;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        if (base + j < n) data[base + j] = run;
+        run += v[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// random-access roofline probe: uniform random sector touches
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_probe(uint32_t* __restrict__ table, uint32_t sector_bits, uint32_t mode, uint64_t per_thread, unsigned long long* sink) {
+    uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t x = fmix64(tid + 0x1234567ull);
+    uint32_t acc = 0;
+    for (uint64_t i = 0; i < per_thread; ++i) {
+        x = x * 6364136223846793005ull + 1442695040888963407ull;
+        uint64_t h = fmix64(x);
+        uint32_t* sec = table + ((h >> (64 - sector_bits)) << 3);
+        if (mode == 0) {
+            uint4 a = ld_nc_v4(sec), b = ld_nc_v4(sec + 4);
+            acc += a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w;
+        } else if (mode == 1) {
+            atomicOr(sec + (h & 7), 1u << ((h >> 3) & 31));
+        } else {
+            uint32_t m = 1u << ((h >> 3) & 31);
+            uint32_t cur = __ldcg(sec + (h & 7));
+            if ((cur & m) != m) atomicOr(sec + (h & 7), m);
+            acc += cur;
+        }
+    }
+    if (acc == 0x9e3779b9u) atomicAdd(sink, 1ull);
+}
+
+}  // namespace tpc

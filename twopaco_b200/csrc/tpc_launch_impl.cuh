@@ -1,0 +1,117 @@
+// tpc_launch_impl.cuh -- included by tpc_w<W>.cu; defines Launch<W>.
+#pragma once
+#include "tpc_kernels.cuh"
+#include "tpc_launch.cuh"
+
+namespace tpc {
+
+// persistent grid: one wave of resident CTAs (148 SMs x occupancy), capped by the work
+template <typename Kern>
+static int persistent_grid(Kern kern, int threads, int sm_count, uint64_t work_items) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
+    if (per_sm < 1) per_sm = 1;
+    uint64_t g = (uint64_t)per_sm * (uint64_t)sm_count;
+    if (g > work_items) g = work_items;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+#define TPC_Q_SWITCH(q, ...)                                   \
+    switch (q) {                                               \
+        case 1: { constexpr int Q = 1; __VA_ARGS__; } break;   \
+        case 2: { constexpr int Q = 2; __VA_ARGS__; } break;   \
+        case 3: { constexpr int Q = 3; __VA_ARGS__; } break;   \
+        case 4: { constexpr int Q = 4; __VA_ARGS__; } break;   \
+        case 5: { constexpr int Q = 5; __VA_ARGS__; } break;   \
+        case 6: { constexpr int Q = 6; __VA_ARGS__; } break;   \
+        case 7: { constexpr int Q = 7; __VA_ARGS__; } break;   \
+        default: { constexpr int Q = 8; __VA_ARGS__; } break;  \
+    }
+
+template <int W>
+cudaError_t Launch<W>::fill(const LaunchCtx& c, GenomeView g, uint32_t* filter, KParams kp, uint64_t ntiles, Counters* ctr) {
+    TPC_Q_SWITCH(kp.q, {
+        int grid = persistent_grid(k_fill<W, Q>, kTileThreads, c.sm_count, ntiles);
+        k_fill<W, Q><<<grid, kTileThreads, 0, c.stream>>>(g, filter, kp, ntiles, ctr);
+    });
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+template <int W>
+cudaError_t Launch<W>::query(const LaunchCtx& c, GenomeView g, const uint32_t* filter, KParams kp, uint64_t ntiles,
+                             uint32_t* mask, int accumulate, Counters* ctr) {
+    TPC_Q_SWITCH(kp.q, {
+        int grid = persistent_grid(k_query<W, Q>, kTileThreads, c.sm_count, ntiles);
+        k_query<W, Q><<<grid, kTileThreads, 0, c.stream>>>(g, filter, kp, ntiles, mask, accumulate, ctr);
+    });
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+template <int W>
+cudaError_t Launch<W>::insert(const LaunchCtx& c, GenomeView g, const uint32_t* mask, KParams kp, uint64_t ntiles, TableView T,
+                              Counters* ctr) {
+    int grid = persistent_grid(k_insert<W>, kTileThreads, c.sm_count, ntiles);
+    k_insert<W><<<grid, kTileThreads, 0, c.stream>>>(g, mask, kp, ntiles, T, ctr);
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+template <int W>
+cudaError_t Launch<W>::build_index(const LaunchCtx& c, GenomeView g, const unsigned long long* sorted, uint64_t n, KParams kp,
+                                   TableView J) {
+    if (n == 0) return cudaSuccess;
+    int grid = persistent_grid(k_build_index<W>, 256, c.sm_count, (n + 255) / 256);
+    k_build_index<W><<<grid, 256, 0, c.stream>>>(g, sorted, n, kp, J);
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+template <int W>
+cudaError_t Launch<W>::ends(const LaunchCtx& c, GenomeView g, const RecordTable& rt, KParams kp, TableView J, uint32_t* stubmask,
+                            uint64_t pos_begin, uint64_t pos_end) {
+    if (rt.n == 0) return cudaSuccess;
+    int grid = persistent_grid(k_ends<W>, 256, c.sm_count, (rt.n + 255) / 256);
+    k_ends<W><<<grid, 256, 0, c.stream>>>(g, rt, kp, J, stubmask, pos_begin, pos_end);
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+template <int W>
+cudaError_t Launch<W>::emit_count(const LaunchCtx& c, GenomeView g, uint32_t* mask, const uint32_t* stubmask, KParams kp,
+                                  TableView J, uint64_t tile_begin, uint64_t tile_end, unsigned long long* tile_records,
+                                  unsigned long long* tile_stubs) {
+    if (tile_end <= tile_begin) return cudaSuccess;
+    int grid = persistent_grid(k_emit_count<W>, kTileThreads, c.sm_count, tile_end - tile_begin);
+    k_emit_count<W><<<grid, kTileThreads, 0, c.stream>>>(g, mask, stubmask, kp, J, tile_begin, tile_end, tile_records, tile_stubs);
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+template <int W>
+cudaError_t Launch<W>::emit_write(const LaunchCtx& c, GenomeView g, const uint32_t* mask, const uint32_t* stubmask, KParams kp,
+                                  TableView J, const RecordTable& rt, uint64_t tile_begin, uint64_t tile_end,
+                                  const unsigned long long* tile_rec_prefix, const unsigned long long* tile_stub_prefix,
+                                  uint64_t records_before, uint64_t stubs_before, uint64_t unit_base, uint64_t first_stub_id,
+                                  uint32_t* out, uint64_t out_units) {
+    if (tile_end <= tile_begin) return cudaSuccess;
+    int grid = persistent_grid(k_emit_write<W>, kTileThreads, c.sm_count, tile_end - tile_begin);
+    k_emit_write<W><<<grid, kTileThreads, 0, c.stream>>>(g, mask, stubmask, kp, J, rt, tile_begin, tile_end, tile_rec_prefix,
+                                                        tile_stub_prefix, records_before, stubs_before, unit_base,
+                                                        first_stub_id, out, out_units);
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+template <int W>
+cudaError_t Launch<W>::get_id(const LaunchCtx& c, GenomeView g, TableView J, KParams kp, const uint64_t* words, long long* d_out) {
+    Kmer<W> x;
+    for (int j = 0; j < W; ++j) x.w[j] = words[j];
+    k_get_id<W><<<1, 1, 0, c.stream>>>(g, J, kp, x, d_out);
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+}  // namespace tpc

@@ -1,0 +1,601 @@
+// tpc_session.cu -- sessions (C ABI level 3), the packed-genome entry point (level 2) and the
+// W-independent kernels.  One session = one GPU = one hash-range shard.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../../include/twopaco_b200.h"
+#include "tpc_internal.h"
+#include "tpc_kernels_common.cuh"
+#include "tpc_launch.cuh"
+
+namespace tpc {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: nothing throws across the C ABI
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_error;
+
+int set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return 1;
+}
+const char* last_error() { return g_error.c_str(); }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return tpc::set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                                  cudaGetErrorString(e_));                                         \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// W-independent launchers
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_classify(const LaunchCtx& c, TableView T, uint64_t abundance, uint32_t use_abundance,
+                            unsigned long long* out, uint64_t out_cap, Counters* ctr) {
+    uint64_t cap = 1ull << T.log2cap;
+    uint64_t blocks = std::min<uint64_t>((cap + 255) / 256, (uint64_t)c.sm_count * 8);
+    k_classify<<<(int)blocks, 256, 0, c.stream>>>(T, abundance, use_abundance, out, out_cap, ctr);
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+uint64_t scan_scratch_items(uint64_t n) {
+    uint64_t total = 0;
+    while (n > (uint64_t)kScanBlock) {
+        n = (n + kScanBlock - 1) / kScanBlock;
+        total += n;
+    }
+    return total + 1;
+}
+
+// in-place exclusive scan; scratch holds scan_scratch_items(n) words
+cudaError_t launch_scan_exclusive(const LaunchCtx& c, unsigned long long* data, uint64_t n, unsigned long long* scratch) {
+    if (n == 0) return cudaSuccess;
+    uint64_t nb = (n + kScanBlock - 1) / kScanBlock;
+    if (nb == 1) {
+        k_scan_apply<<<1, 256, 0, c.stream>>>(data, n, nullptr);
+        ++*c.launches;
+        return cudaGetLastError();
+    }
+    k_scan_reduce<<<(unsigned)nb, 256, 0, c.stream>>>(data, n, scratch);
+    ++*c.launches;
+    cudaError_t e = launch_scan_exclusive(c, scratch, nb, scratch + nb);
+    if (e != cudaSuccess) return e;
+    k_scan_apply<<<(unsigned)nb, 256, 0, c.stream>>>(data, n, scratch);
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+}  // namespace tpc
+
+using namespace tpc;
+
+// ---------------------------------------------------------------------------------------------
+// session
+// ---------------------------------------------------------------------------------------------
+struct tpc_session {
+    tpc_params prm{};
+    cudaStream_t stream = nullptr;
+    int device = 0;
+    int sm_count = 148;
+    int W = 1;
+    uint32_t filter_bits_eff = 0;
+
+    // genome
+    GenomeView g{};
+    uint64_t* d_codes = nullptr;   // owned copies (set_genome_host) or null
+    uint64_t* d_nmask = nullptr;
+    std::vector<uint64_t> rec_start, rec_len;
+    std::vector<uint32_t> sep_before;
+    std::vector<uint64_t> emit_prev;  // index of the last emitting record before record i (or 0)
+    uint64_t* d_rec_start = nullptr;
+    uint64_t* d_rec_len = nullptr;
+    uint32_t* d_sep_before = nullptr;
+    uint64_t ntiles = 0;
+
+    // working set
+    uint32_t* d_filter = nullptr;
+    uint32_t* d_mask = nullptr;
+    uint32_t* d_stubmask = nullptr;
+    Slot* d_T = nullptr;
+    uint64_t T_bytes = 0;
+    uint32_t T_log2 = 0;
+    Slot* d_J = nullptr;
+    uint32_t J_log2 = 0;
+    unsigned long long* d_local = nullptr;  // this shard's junction words
+    uint64_t local_cap = 0, local_count = 0;
+    unsigned long long* d_sorted = nullptr;  // all junction words, sorted by position
+    uint64_t J_count = 0;
+    void* d_sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    Counters* d_ctr = nullptr;
+    long long* d_id = nullptr;
+
+    // emit slice state
+    unsigned long long* d_tile_rec = nullptr;
+    unsigned long long* d_tile_stub = nullptr;
+    unsigned long long* d_scan_scratch = nullptr;
+    uint64_t tile_cap = 0;
+    uint64_t slice_tile_begin = 0, slice_tile_end = 0, slice_pos_begin = 0, slice_pos_end = 0;
+    uint64_t slice_records = 0, slice_stubs = 0;
+    bool have_candidates = false, have_index = false, have_count = false;
+
+    tpc_stats st{};
+    cudaEvent_t ev[10]{};
+    uint32_t launches = 0;
+
+    LaunchCtx lctx() { return LaunchCtx{stream, sm_count, &launches}; }
+    KParams kparams(uint32_t part) const {
+        KParams kp{};
+        kp.k = prm.k;
+        kp.q = std::min<uint32_t>(std::max<uint32_t>(prm.q, 1u), 8u);
+        kp.sector_shift = 64 - (filter_bits_eff - 8);
+        kp.nparts = prm.rounds * prm.shard_count;
+        kp.part = part;
+        kp.count_occurrences = prm.abundance != ~0ull;
+        kp.seed = prm.seed;
+        return kp;
+    }
+    RecordTable rtable() const { return RecordTable{d_rec_start, d_rec_len, d_sep_before, (uint64_t)rec_start.size()}; }
+};
+
+#define W_DISPATCH(s, EXPR)                          \
+    ((s)->W == 1 ? Launch<1>::EXPR : (s)->W == 2 ? Launch<2>::EXPR : (s)->W == 3 ? Launch<3>::EXPR : Launch<4>::EXPR)
+
+static uint32_t ceil_log2(uint64_t x) {
+    uint32_t l = 0;
+    while ((1ull << l) < x) ++l;
+    return l;
+}
+
+extern "C" {
+
+const char* tpc_last_error(void) { return tpc::last_error(); }
+uint32_t tpc_abi_version(void) { return TPC_ABI_VERSION; }
+
+uint64_t tpc_code_words(uint64_t n_positions) {
+    uint64_t tiles = (n_positions + kTilePos - 1) / kTilePos;
+    return tiles * kTileThreads + 8;
+}
+uint64_t tpc_mask_words(uint64_t n_positions) {
+    uint64_t tiles = (n_positions + kTilePos - 1) / kTilePos;
+    return tiles * (kTileThreads / 2) + 8;
+}
+uint64_t tpc_positions_for(const uint64_t* rec_len, uint64_t n_records) {
+    uint64_t p = 1;
+    for (uint64_t i = 0; i < n_records; ++i) p += rec_len[i] + 1;
+    return p;
+}
+
+int tpc_session_create(const tpc_params* params, void* stream, tpc_session** out) {
+    if (!params || !out) return set_error("null argument");
+    if (params->k == 0 || params->k % 2 == 0) return set_error("value of K must be odd");
+    if (params->k > TPC_MAX_K)
+        return set_error("The value of K is too big. Please refer to documentaion how to increase the max supported value of K.");
+    if (params->filter_bits > 40 || params->filter_bits == 0) return set_error("filter size must be in 1..40 bits");
+    if (params->rounds == 0 || params->shard_count == 0 || params->shard_index >= params->shard_count)
+        return set_error("bad rounds / shard parameters");
+    if (params->q == 0) return set_error("the number of hash functions must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_error("no CUDA device: twopaco_b200 has no CPU fallback (%s)", cudaGetErrorString(e));
+    tpc_session* s = new (std::nothrow) tpc_session();
+    if (!s) return set_error("out of memory");
+    s->prm = *params;
+    s->stream = (cudaStream_t)stream;
+    s->W = (int)((params->k + 31) / 32);
+    s->filter_bits_eff = std::max<uint32_t>(params->filter_bits, 9u);
+    cudaGetDevice(&s->device);
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
+    for (auto& ev : s->ev) cudaEventCreate(&ev);
+    if (cudaMalloc(&s->d_ctr, sizeof(Counters)) != cudaSuccess || cudaMalloc(&s->d_id, sizeof(long long)) != cudaSuccess) {
+        tpc_session_destroy(s);
+        return set_error("cudaMalloc failed");
+    }
+    cudaMemsetAsync(s->d_ctr, 0, sizeof(Counters), s->stream);
+    *out = s;
+    return 0;
+}
+
+void tpc_session_destroy(tpc_session* s) {
+    if (!s) return;
+    cudaStreamSynchronize(s->stream);
+    void* ptrs[] = {s->d_codes, s->d_nmask, s->d_rec_start, s->d_rec_len, s->d_sep_before, s->d_filter, s->d_mask,
+                    s->d_stubmask, s->d_T, s->d_J, s->d_local, s->d_sorted, s->d_sort_tmp, s->d_ctr, s->d_id,
+                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (auto& ev : s->ev)
+        if (ev) cudaEventDestroy(ev);
+    delete s;
+}
+
+static int adopt_records(tpc_session* s, const tpc_genome* g) {
+    if (g->n_positions >= (1ull << kPosBits)) return set_error("genome too large: %llu positions", (unsigned long long)g->n_positions);
+    s->rec_start.assign(g->rec_start, g->rec_start + g->n_records);
+    s->rec_len.assign(g->rec_len, g->rec_len + g->n_records);
+    s->sep_before.assign(g->n_records, 0);
+    s->emit_prev.assign(g->n_records + 1, 0);
+    uint64_t prev = 0;  // JunctionPositionWriter::nowChr_ (junctionapi.h:109,120-123)
+    for (uint64_t i = 0; i < g->n_records; ++i) {
+        if (g->rec_len[i] >> 32) return set_error("record %llu is longer than 2^32 bp", (unsigned long long)i);
+        s->emit_prev[i] = prev;
+        if (g->rec_len[i] >= s->prm.k) {
+            s->sep_before[i] = (uint32_t)(i - prev);
+            prev = i;
+        }
+    }
+    s->emit_prev[g->n_records] = prev;
+    s->ntiles = (g->n_positions + kTilePos - 1) / kTilePos;
+    size_t nr = std::max<uint64_t>(g->n_records, 1);
+    CK(cudaMalloc(&s->d_rec_start, nr * 8));
+    CK(cudaMalloc(&s->d_rec_len, nr * 8));
+    CK(cudaMalloc(&s->d_sep_before, nr * 4));
+    if (g->n_records) {
+        CK(cudaMemcpyAsync(s->d_rec_start, s->rec_start.data(), g->n_records * 8, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->d_rec_len, s->rec_len.data(), g->n_records * 8, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->d_sep_before, s->sep_before.data(), g->n_records * 4, cudaMemcpyHostToDevice, s->stream));
+    }
+    return 0;
+}
+
+int tpc_session_set_genome_host(tpc_session* s, const tpc_genome* g) {
+    if (!s || !g) return set_error("null argument");
+    if (s->g.codes) return set_error("genome already set");
+    uint64_t cw = tpc_code_words(g->n_positions), mw = tpc_mask_words(g->n_positions);
+    CK(cudaMalloc(&s->d_codes, cw * 8));
+    CK(cudaMalloc(&s->d_nmask, mw * 8));
+    CK(cudaMemcpyAsync(s->d_codes, g->codes, cw * 8, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->d_nmask, g->n_mask, mw * 8, cudaMemcpyHostToDevice, s->stream));
+    s->g = GenomeView{s->d_codes, s->d_nmask, g->n_positions};
+    return adopt_records(s, g);
+}
+
+int tpc_session_set_genome_device(tpc_session* s, const tpc_genome* g) {
+    if (!s || !g) return set_error("null argument");
+    if (s->g.codes) return set_error("genome already set");
+    s->g = GenomeView{g->codes, g->n_mask, g->n_positions};
+    return adopt_records(s, g);
+}
+
+int tpc_session_find_candidates(tpc_session* s) {
+    if (!s || !s->g.codes) return set_error("no genome set");
+    LaunchCtx lc = s->lctx();
+    const uint64_t mask_words = s->ntiles * kTileThreads;
+    const uint64_t filter_bytes = (1ull << s->filter_bits_eff) / 8;
+    if (!s->d_filter) CK(cudaMalloc(&s->d_filter, filter_bytes));
+    if (!s->d_mask) {
+        CK(cudaMalloc(&s->d_mask, std::max<uint64_t>(mask_words, 1) * 4));
+        CK(cudaMalloc(&s->d_stubmask, std::max<uint64_t>(mask_words, 1) * 4));
+    }
+    CK(cudaMemsetAsync(s->d_mask, 0, std::max<uint64_t>(mask_words, 1) * 4, s->stream));
+    CK(cudaMemsetAsync(s->d_ctr, 0, sizeof(Counters), s->stream));
+    s->local_count = 0;
+    s->st = tpc_stats{};
+    s->st.positions = s->g.npos;
+    float ms_fill = 0, ms_query = 0, ms_insert = 0, ms_classify = 0;
+    Counters prev{}, cur{};
+    for (uint32_t r = 0; r < s->prm.rounds; ++r) {
+        KParams kp = s->kparams(s->prm.shard_index * s->prm.rounds + r);
+        CK(cudaEventRecord(s->ev[0], s->stream));
+        CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));  // h:257: zero-filled each round
+        CK(W_DISPATCH(s, fill(lc, s->g, s->d_filter, kp, s->ntiles, s->d_ctr)));
+        CK(cudaEventRecord(s->ev[1], s->stream));
+        CK(W_DISPATCH(s, query(lc, s->g, s->d_filter, kp, s->ntiles, s->d_mask, r > 0, s->d_ctr)));
+        CK(cudaEventRecord(s->ev[2], s->stream));
+        CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        uint64_t marks_r = cur.marks - prev.marks;
+
+        // exact set of this round's candidates, sized from the number of marks
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        uint64_t avail = free_b + s->T_bytes;
+        uint32_t lg = std::max<uint32_t>(ceil_log2(marks_r * 2 + 16), 10);
+        while (lg > 10 && (sizeof(Slot) << lg) > avail * 6 / 10) --lg;
+        uint64_t need = sizeof(Slot) << lg;
+        if (need > s->T_bytes) {
+            if (s->d_T) CK(cudaFree(s->d_T));
+            s->d_T = nullptr; s->T_bytes = 0;
+            CK(cudaMalloc(&s->d_T, need));
+            s->T_bytes = need;
+        }
+        s->T_log2 = lg;
+        TableView T{s->d_T, lg};
+        CK(cudaMemsetAsync(s->d_T, 0, need, s->stream));
+        CK(W_DISPATCH(s, insert(lc, s->g, s->d_mask, kp, s->ntiles, T, s->d_ctr)));
+        CK(cudaEventRecord(s->ev[3], s->stream));
+        CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        if (cur.overflow) return set_error("candidate table overflow (%llu marks, 2^%u slots): not enough device memory",
+                                           (unsigned long long)marks_r, lg);
+        uint64_t distinct_r = cur.distinct - prev.distinct;
+        if (s->local_count + distinct_r > s->local_cap) {
+            uint64_t ncap = std::max<uint64_t>(s->local_count + distinct_r, 1024);
+            unsigned long long* nl = nullptr;
+            CK(cudaMalloc(&nl, ncap * 8));
+            if (s->local_count) CK(cudaMemcpyAsync(nl, s->d_local, s->local_count * 8, cudaMemcpyDeviceToDevice, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+            if (s->d_local) CK(cudaFree(s->d_local));
+            s->d_local = nl; s->local_cap = ncap;
+        }
+        CK(launch_classify(lc, T, s->prm.abundance, kp.count_occurrences, s->d_local, s->local_cap, s->d_ctr));
+        CK(cudaEventRecord(s->ev[4], s->stream));
+        CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        s->local_count = cur.junctions;
+        float t;
+        cudaEventElapsedTime(&t, s->ev[0], s->ev[1]); ms_fill += t;
+        cudaEventElapsedTime(&t, s->ev[1], s->ev[2]); ms_query += t;
+        cudaEventElapsedTime(&t, s->ev[2], s->ev[3]); ms_insert += t;
+        cudaEventElapsedTime(&t, s->ev[3], s->ev[4]); ms_classify += t;
+        prev = cur;
+    }
+    // the table is only needed inside a round (h:337-338: per-round OccurenceSet)
+    if (s->d_T) { CK(cudaFree(s->d_T)); s->d_T = nullptr; s->T_bytes = 0; }
+    s->st.candidate_marks = cur.marks;
+    s->st.candidate_kmers = cur.distinct;
+    s->st.filter_edges_set = cur.filter_new;
+    s->st.ms_fill = ms_fill; s->st.ms_query = ms_query; s->st.ms_insert = ms_insert; s->st.ms_classify = ms_classify;
+    s->have_candidates = true;
+    s->have_index = false;
+    return 0;
+}
+
+int tpc_session_local_junctions(tpc_session* s, const uint64_t** dev_words, uint64_t* count) {
+    if (!s || !s->have_candidates) return set_error("find_candidates has not run");
+    if (dev_words) *dev_words = (const uint64_t*)s->d_local;
+    if (count) *count = s->local_count;
+    return 0;
+}
+
+int tpc_session_set_junctions(tpc_session* s, const uint64_t* dev_words_all, uint64_t n) {
+    if (!s || !s->g.codes) return set_error("no genome set");
+    LaunchCtx lc = s->lctx();
+    CK(cudaEventRecord(s->ev[5], s->stream));
+    if (s->d_sorted) { CK(cudaFree(s->d_sorted)); s->d_sorted = nullptr; }
+    if (s->d_J) { CK(cudaFree(s->d_J)); s->d_J = nullptr; }
+    CK(cudaMalloc(&s->d_sorted, std::max<uint64_t>(n, 1) * 8));
+    if (n) {
+        // ids = rank of the first occurrence position: plain library radix sort of <= J 40-bit keys
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, (const unsigned long long*)dev_words_all, s->d_sorted, n, 0, kPosBits, s->stream));
+        if (tmp > s->sort_tmp_bytes) {
+            if (s->d_sort_tmp) CK(cudaFree(s->d_sort_tmp));
+            CK(cudaMalloc(&s->d_sort_tmp, tmp));
+            s->sort_tmp_bytes = tmp;
+        }
+        CK(cub::DeviceRadixSort::SortKeys(s->d_sort_tmp, tmp, (const unsigned long long*)dev_words_all, s->d_sorted, n, 0, kPosBits, s->stream));
+    }
+    s->J_log2 = std::max<uint32_t>(ceil_log2(n * 2 + 16), 6);
+    CK(cudaMalloc(&s->d_J, sizeof(Slot) << s->J_log2));
+    CK(cudaMemsetAsync(s->d_J, 0, sizeof(Slot) << s->J_log2, s->stream));
+    CK(W_DISPATCH(s, build_index(lc, s->g, s->d_sorted, n, s->kparams(0), TableView{s->d_J, s->J_log2})));
+    CK(cudaEventRecord(s->ev[6], s->stream));
+    s->J_count = n;
+    s->st.junctions = n;
+    s->have_index = true;
+    s->have_count = false;
+    return 0;
+}
+
+int tpc_session_candidate_mask(tpc_session* s, uint32_t** dev_mask, uint64_t* n_words) {
+    if (!s || !s->d_mask) return set_error("find_candidates has not run");
+    if (dev_mask) *dev_mask = s->d_mask;
+    if (n_words) *n_words = s->ntiles * kTileThreads;
+    return 0;
+}
+
+int tpc_session_emit_count(tpc_session* s, uint64_t pos_begin, uint64_t pos_end, uint64_t* n_records, uint64_t* n_stubs) {
+    if (!s || !s->have_index || !s->d_mask) return set_error("set_junctions has not run");
+    if (pos_end > s->g.npos) pos_end = s->g.npos;
+    if (pos_begin > pos_end) pos_begin = pos_end;
+    if (pos_begin % kTilePos) return set_error("emit slice must start at a multiple of %d", kTilePos);
+    if (pos_end % kTilePos && pos_end != s->g.npos) return set_error("emit slice must end at a multiple of %d", kTilePos);
+    LaunchCtx lc = s->lctx();
+    uint64_t tb = pos_begin / kTilePos, te = (pos_end + kTilePos - 1) / kTilePos;
+    uint64_t nt = te - tb;
+    if (nt + 1 > s->tile_cap) {
+        for (void* p : {(void*)s->d_tile_rec, (void*)s->d_tile_stub, (void*)s->d_scan_scratch})
+            if (p) CK(cudaFree(p));
+        s->d_tile_rec = s->d_tile_stub = s->d_scan_scratch = nullptr;
+        CK(cudaMalloc(&s->d_tile_rec, (nt + 1) * 8));
+        CK(cudaMalloc(&s->d_tile_stub, (nt + 1) * 8));
+        CK(cudaMalloc(&s->d_scan_scratch, scan_scratch_items(nt + 1) * 8));
+        s->tile_cap = nt + 1;
+    }
+    CK(cudaEventRecord(s->ev[7], s->stream));
+    CK(cudaMemsetAsync(s->d_stubmask, 0, std::max<uint64_t>(s->ntiles * kTileThreads, 1) * 4, s->stream));
+    CK(cudaMemsetAsync(s->d_tile_rec + nt, 0, 8, s->stream));
+    CK(cudaMemsetAsync(s->d_tile_stub + nt, 0, 8, s->stream));
+    KParams kp = s->kparams(0);
+    TableView J{s->d_J, s->J_log2};
+    CK(W_DISPATCH(s, ends(lc, s->g, s->rtable(), kp, J, s->d_stubmask, pos_begin, pos_end)));
+    CK(W_DISPATCH(s, emit_count(lc, s->g, s->d_mask, s->d_stubmask, kp, J, tb, te, s->d_tile_rec, s->d_tile_stub)));
+    CK(launch_scan_exclusive(lc, s->d_tile_rec, nt + 1, s->d_scan_scratch));
+    CK(launch_scan_exclusive(lc, s->d_tile_stub, nt + 1, s->d_scan_scratch));
+    unsigned long long tot[2];
+    CK(cudaMemcpyAsync(&tot[0], s->d_tile_rec + nt, 8, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(&tot[1], s->d_tile_stub + nt, 8, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->slice_tile_begin = tb; s->slice_tile_end = te;
+    s->slice_pos_begin = pos_begin; s->slice_pos_end = pos_end;
+    s->slice_records = tot[0]; s->slice_stubs = tot[1];
+    s->have_count = true;
+    if (n_records) *n_records = tot[0];
+    if (n_stubs) *n_stubs = tot[1];
+    return 0;
+}
+
+// index of the last emitting record (len >= k) whose first position is < pos, or 0
+static uint64_t emit_prev_at(const tpc_session* s, uint64_t pos) {
+    uint64_t i = std::lower_bound(s->rec_start.begin(), s->rec_start.end(), pos) - s->rec_start.begin();
+    return s->emit_prev[i];
+}
+
+int tpc_session_emit_write(tpc_session* s, uint64_t records_before, uint64_t stubs_before, uint8_t* dev_out,
+                           uint64_t out_capacity, uint64_t* image_offset, uint64_t* image_bytes) {
+    if (!s || !s->have_count) return set_error("emit_count has not run");
+    LaunchCtx lc = s->lctx();
+    uint64_t unit_base = records_before + emit_prev_at(s, s->slice_pos_begin);
+    uint64_t units = s->slice_records + emit_prev_at(s, s->slice_pos_end) - emit_prev_at(s, s->slice_pos_begin);
+    if (image_offset) *image_offset = unit_base * 12;
+    if (image_bytes) *image_bytes = units * 12;
+    if (units * 12 > out_capacity) {
+        set_error("output buffer too small: need %llu bytes", (unsigned long long)(units * 12));
+        return 2;
+    }
+    if (((uintptr_t)dev_out) & 3) return set_error("output buffer must be 4-byte aligned");
+    KParams kp = s->kparams(0);
+    TableView J{s->d_J, s->J_log2};
+    CK(W_DISPATCH(s, emit_write(lc, s->g, s->d_mask, s->d_stubmask, kp, J, s->rtable(), s->slice_tile_begin, s->slice_tile_end,
+                                s->d_tile_rec, s->d_tile_stub, records_before, stubs_before, unit_base,
+                                s->J_count + TPC_STUB_ID_OFFSET, (uint32_t*)dev_out, units)));
+    CK(cudaEventRecord(s->ev[8], s->stream));
+    s->st.occurrences = s->slice_records;
+    s->st.stubs = s->slice_stubs;
+    s->st.out_bytes = units * 12;
+    return 0;
+}
+
+int tpc_session_get_id(tpc_session* s, const char* kmer, int64_t* id) {
+    if (!s || !s->have_index || !kmer || !id) return set_error("bad argument");
+    uint32_t k = s->prm.k;
+    *id = TPC_INVALID_VERTEX;
+    if (strlen(kmer) != k) return 0;
+    uint64_t words[4] = {0, 0, 0, 0};
+    for (uint32_t j = 0; j < k; ++j) {
+        uint64_t c;
+        switch (kmer[j]) {
+            case 'A': case 'a': c = 0; break;
+            case 'C': case 'c': c = 1; break;
+            case 'G': case 'g': c = 2; break;
+            case 'T': case 't': c = 3; break;
+            default: return 0;  // not a definite k-mer: never a junction
+        }
+        words[j / 32] |= c << (2 * (j % 32));
+    }
+    LaunchCtx lc = s->lctx();
+    CK(W_DISPATCH(s, get_id(lc, s->g, TableView{s->d_J, s->J_log2}, s->kparams(0), words, s->d_id)));
+    long long v = 0;
+    CK(cudaMemcpyAsync(&v, s->d_id, 8, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    *id = v ? (int64_t)v : TPC_INVALID_VERTEX;
+    return 0;
+}
+
+int tpc_session_stats(tpc_session* s, tpc_stats* out) {
+    if (!s || !out) return set_error("null argument");
+    CK(cudaStreamSynchronize(s->stream));
+    float t = 0;
+    if (s->have_index && cudaEventElapsedTime(&t, s->ev[5], s->ev[6]) == cudaSuccess) s->st.ms_index = t;
+    if (s->st.out_bytes && cudaEventElapsedTime(&t, s->ev[7], s->ev[8]) == cudaSuccess) s->st.ms_emit = t;
+    s->st.ms_total = s->st.ms_fill + s->st.ms_query + s->st.ms_insert + s->st.ms_classify + s->st.ms_index + s->st.ms_emit;
+    s->st.kernel_launches = s->launches;
+    *out = s->st;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// level 2: packed genome in host memory -> image in host memory (single GPU, unsharded)
+// ---------------------------------------------------------------------------------------------
+int tpc_session_run_to_count(tpc_session* s, uint64_t* image_bytes) {
+    if (int rc = tpc_session_find_candidates(s)) return rc;
+    const uint64_t* words = nullptr;
+    uint64_t n = 0;
+    if (int rc = tpc_session_local_junctions(s, &words, &n)) return rc;
+    if (int rc = tpc_session_set_junctions(s, words, n)) return rc;
+    uint64_t nrec = 0, nstub = 0;
+    if (int rc = tpc_session_emit_count(s, 0, s->g.npos, &nrec, &nstub)) return rc;
+    if (image_bytes) *image_bytes = (nrec + s->emit_prev[s->rec_start.size()]) * 12;
+    return 0;
+}
+
+int tpc_session_write_host(tpc_session* s, uint8_t* out_image, uint64_t image_bytes) {
+    uint8_t* d_out = nullptr;
+    CK(cudaMalloc(&d_out, std::max<uint64_t>(image_bytes, 16)));
+    uint64_t off = 0, bytes = 0;
+    int rc = tpc_session_emit_write(s, 0, 0, d_out, image_bytes, &off, &bytes);
+    if (rc == 0 && bytes) {
+        cudaError_t e = cudaMemcpyAsync(out_image, d_out, bytes, cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) rc = set_error("CUDA error %s copying the image", cudaGetErrorName(e));
+    } else if (rc == 0) {
+        cudaStreamSynchronize(s->stream);
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+int tpc_junctions_host(const tpc_params* params, const tpc_genome* host_genome, uint8_t* out_image, uint64_t out_capacity,
+                       uint64_t* out_bytes, tpc_stats* stats) {
+    if (!params || !host_genome) return set_error("null argument");
+    tpc_params p = *params;
+    p.shard_index = 0;
+    p.shard_count = 1;
+    tpc_session* s = nullptr;
+    if (int rc = tpc_session_create(&p, nullptr, &s)) return rc;
+    int rc = tpc_session_set_genome_host(s, host_genome);
+    uint64_t bytes = 0;
+    if (rc == 0) rc = tpc_session_run_to_count(s, &bytes);
+    if (out_bytes) *out_bytes = bytes;
+    if (rc == 0 && bytes > out_capacity) {
+        set_error("output buffer too small: need %llu bytes", (unsigned long long)bytes);
+        rc = 2;
+    }
+    if (rc == 0) rc = tpc_session_write_host(s, out_image, bytes);
+    if (stats) tpc_session_stats(s, stats);
+    tpc_session_destroy(s);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// random-access roofline probe
+// ---------------------------------------------------------------------------------------------
+int tpc_random_access_probe(uint32_t filter_bits, uint32_t mode, uint64_t touches, double* touches_per_s) {
+    if (filter_bits < 9 || filter_bits > 40 || mode > 2) return set_error("bad probe arguments");
+    uint32_t* table = nullptr;
+    unsigned long long* sink = nullptr;
+    uint64_t bytes = (1ull << filter_bits) / 8;
+    CK(cudaMalloc(&table, bytes));
+    CK(cudaMalloc(&sink, 8));
+    CK(cudaMemset(table, 0, bytes));
+    CK(cudaMemset(sink, 0, 8));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int blocks = sms * 8;
+    uint64_t threads = (uint64_t)blocks * 256;
+    uint64_t per_thread = std::max<uint64_t>(touches / threads, 1);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    k_probe<<<blocks, 256>>>(table, filter_bits - 8, mode, std::max<uint64_t>(per_thread / 8, 1), sink);  // warm-up
+    cudaEventRecord(a);
+    k_probe<<<blocks, 256>>>(table, filter_bits - 8, mode, per_thread, sink);
+    cudaEventRecord(b);
+    cudaError_t e = cudaDeviceSynchronize();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(table); cudaFree(sink);
+    if (e != cudaSuccess) return set_error("probe failed: %s", cudaGetErrorString(e));
+    if (touches_per_s) *touches_per_s = (double)(per_thread * threads) / (ms * 1e-3);
+    return 0;
+}
+
+}  // extern "C"
