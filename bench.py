@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- input Gbp/s to the exact junction set (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|dev] [--impl reference]
+
+One "step" = one full pass of the junction-finding hot path (filter fill, candidate query,
+exact pass, id index, ordered emit) over one synthetic genome set.
+
+* value      : whole-job throughput, packed genome already resident in HBM, image left in HBM.
+* e2e        : same metric through the C-ABI call with HOST buffers (tpc_junctions_host):
+               H2D of the packed genome and D2H of the de_bruijn.bin image inside the timed region.
+* roofline   : the dominant kernel (candidate query), algorithmic bytes / CUDA-event time.
+* cpu_baseline: the UNMODIFIED reference (oracle/_ref/twopaco) on a bounded sample of the same
+               workload with all host cores; the sample's output is also compared (canonical
+               stream) with ours -- that, not the oracle, is what `parity_on_sample` reports.
+Multi-GPU (torchrun): hash-range shards, NCCL all-gather of junction lists + OR-reduce of the
+candidate masks, position-sharded emit.  Strong scaling: the genome set is fixed as N grows.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # SURVEY.md 8(d) / BASELINE.json configs[2]: 7 x 24 x 129,166,667 bp, p = 0.001, k = 25, -f 36
+    "c3": dict(name="C3: 7 synthetic human-sized genomes (7x24x129166667 bp, 0.1% divergence), k=25 -f 36 -q 5",
+               seed=0x4855, genomes=7, records=24, length=129_166_667, p=0.001, k=25, f=36, q=5, sample_bp=3_000_000),
+    # configs[1]: 62 x 5 Mbp, p = 0.01, k = 25, -f 32
+    "c2": dict(name="C2: 62 synthetic E. coli-like genomes (62x5 Mbp, 1% divergence), k=25 -f 32 -q 5",
+               seed=0xEC01, genomes=62, records=1, length=5_000_000, p=0.01, k=25, f=32, q=5, sample_bp=400_000),
+    "dev": dict(name="dev: 7x2x4 Mbp, 0.1% divergence, k=25 -f 30 -q 5",
+                seed=0xD0, genomes=7, records=2, length=4_000_000, p=0.001, k=25, f=30, q=5, sample_bp=500_000),
+}
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self) -> dict:
+        sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference on a bounded sample
+# ---------------------------------------------------------------------------------------------
+def sample_records(dg, wl) -> list[bytes]:
+    """Bounded sample of the workload: the first sample_bp bases of the first record of every genome."""
+    return [dg.record_ascii(g * wl["records"], wl["sample_bp"]) for g in range(wl["genomes"])]
+
+
+def run_reference_on(records: list[bytes], wl: dict, threads: int):
+    from oracle import oracle as O
+    with tempfile.TemporaryDirectory(prefix="tpc_bench_") as d:
+        paths = []
+        for i, r in enumerate(records):  # one FASTA per genome, as the reference is used
+            p = os.path.join(d, f"g{i}.fa")
+            O.write_fasta(p, [r], names=[f"g{i}_c0"])
+            paths.append(p)
+        t0 = time.perf_counter()
+        img, log = O.run_reference(paths, wl["k"], min(wl["f"], 32), q=wl["q"], r=1, t=threads)
+        dt = time.perf_counter() - t0
+    return img, dt
+
+
+def cpu_baseline(dg, wl: dict) -> dict:
+    from oracle import oracle as O
+    from twopaco_b200 import api
+    if not O.have_reference():
+        return {"value": None, "unit": "Gbp/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/twopaco missing"}
+    cores = os.cpu_count() or 1
+    recs = sample_records(dg, wl)
+    bp = sum(len(r) for r in recs)
+    ref_img, dt = run_reference_on(recs, wl, cores)
+    ours, _ = api.junctions_host(api.pack_records(recs), k=wl["k"], filter_bits=min(wl["f"], 32), q=wl["q"])
+    return {"value": bp / dt / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "reference",
+            "sample": f"first {wl['sample_bp']} bp of record 0 of each of the {wl['genomes']} genomes ({bp} bp), "
+                      f"-k {wl['k']} -f {min(wl['f'], 32)} -q {wl['q']} -t {cores}, wall {dt:.2f} s incl. FASTA parsing",
+            "parity_on_sample": bool(O.canon_equal(bytes(ours), ref_img))}
+
+
+# ---------------------------------------------------------------------------------------------
+# one step of our arm
+# ---------------------------------------------------------------------------------------------
+class Runner:
+    def __init__(self, wl, dg, rank, world):
+        import torch
+        from twopaco_b200 import api
+        self.torch, self.api, self.wl, self.dg, self.rank, self.world = torch, api, wl, dg, rank, world
+        self.session = None
+        self.out = None
+        self.last = {}
+
+    def step(self):
+        torch, api, wl, dg = self.torch, self.api, self.wl, self.dg
+        if self.session is not None:
+            self.session.close()
+        s = api.Session(k=wl["k"], filter_bits=wl["f"], q=wl["q"], shard_index=self.rank, shard_count=self.world)
+        self.session = s
+        dg.attach(s)
+        s.find_candidates()
+        ptr, n = s.local_junctions()
+        if self.world == 1:
+            s.set_junctions(ptr, n)
+            nrec, nstub = s.emit_count(0, dg.n_positions)
+            need = 12 * (nrec + len(dg.rec_len)) + 16
+            if self.out is None or self.out.nbytes < need:
+                self.out = api.DeviceBuffer(need)
+            off, nb = s.emit_write(0, 0, self.out.ptr, self.out.nbytes)
+            self.last = dict(junctions=n, records=nrec, stubs=nstub, image_bytes=nb)
+            return
+        import torch.distributed as dist
+        # (1) all-gather the shards' junction words (variable length)
+        local = api.as_torch(ptr, n, torch.int64)
+        counts = torch.zeros(self.world, dtype=torch.int64, device="cuda")
+        counts[self.rank] = n
+        dist.all_reduce(counts)
+        counts_h = counts.tolist()
+        mx = max(max(counts_h), 1)
+        padded = torch.zeros(mx, dtype=torch.int64, device="cuda")
+        padded[:n] = local
+        gathered = torch.empty(self.world * mx, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(gathered, padded)
+        allj = torch.cat([gathered[r * mx: r * mx + counts_h[r]] for r in range(self.world)])
+        s.set_junctions(allj.data_ptr(), allj.numel())
+        # (2) OR-reduce the disjoint candidate masks (sum == or)
+        mptr, mw = s.candidate_mask()
+        dist.all_reduce(api.as_torch(mptr, mw, torch.int32))
+        # (3) position-sharded ordered emit
+        tiles = (dg.n_positions + api.TILE_POSITIONS - 1) // api.TILE_POSITIONS
+        cut = [min(dg.n_positions, (tiles * r // self.world) * api.TILE_POSITIONS) for r in range(self.world)] + [dg.n_positions]
+        nrec, nstub = s.emit_count(cut[self.rank], cut[self.rank + 1])
+        cnt = torch.zeros(self.world, 2, dtype=torch.int64, device="cuda")
+        cnt[self.rank, 0], cnt[self.rank, 1] = nrec, nstub
+        dist.all_reduce(cnt)
+        cnt_h = cnt.tolist()
+        rb = sum(c[0] for c in cnt_h[:self.rank])
+        sb = sum(c[1] for c in cnt_h[:self.rank])
+        need = 12 * (nrec + len(dg.rec_len)) + 16
+        if self.out is None or self.out.nbytes < need:
+            self.out = api.DeviceBuffer(need)
+        off, nb = s.emit_write(rb, sb, self.out.ptr, self.out.nbytes)
+        self.last = dict(junctions=allj.numel(), records=sum(c[0] for c in cnt_h), stubs=sum(c[1] for c in cnt_h),
+                         image_bytes=None, slice_offset=off, slice_bytes=nb)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("TPC_BENCH_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank == 0:  # the other ranks exit without work
+            reference_arm(args, wl, world)
+        return
+
+    import torch
+    from twopaco_b200 import api
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    total_bp = wl["genomes"] * wl["records"] * wl["length"]
+    dg = api.synth_family_device(wl["seed"], wl["genomes"], wl["records"], wl["length"], wl["p"], keep_ascii=(rank == 0))
+    total_bp = dg.total_bp
+
+    runner = Runner(wl, dg, rank, world)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        runner.step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = {k: 0.0 for k in ("ms_fill", "ms_query", "ms_insert", "ms_classify", "ms_index", "ms_emit")}
+    launches = 0
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            runner.step()
+            st = runner.session.stats()
+            for k in stage_ms:
+                stage_ms[k] += getattr(st, k)
+            launches += st.kernel_launches
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    st = runner.session.stats()
+
+    # ---- roofline of the dominant kernel (algorithmic bytes per position) ----------
+    # query: one 32-byte filter sector per owned definite k-mer + the packed stream (0.375 B/bp read)
+    # + 1 bit/bp of candidate mask written.
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    positions = st.positions
+    q_ms = stage_ms["ms_query"] / args.steps
+    f_ms = stage_ms["ms_fill"] / args.steps
+    alg_query = 32.0 * total_bp / world + 0.375 * positions + positions / 8.0
+    alg_fill = 32.0 * total_bp / world + 0.375 * positions
+    dom = "query" if q_ms >= f_ms else "fill"
+    dom_ms, dom_bytes = (q_ms, alg_query) if dom == "query" else (f_ms, alg_fill)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "peak_source": "measured" if peaks else "fallback",
+                "traffic": None, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": round(dom_ms, 3),
+                "random_sector_touches_per_s": round(total_bp / world / (dom_ms * 1e-3) / 1e9, 2) if dom_ms > 0 else None,
+                "other": {"k_fill": {"ms": round(f_ms, 3), "GBps": round(alg_fill / (f_ms * 1e-3) / 1e9, 1) if f_ms > 0 else None}}}
+
+    result = {
+        "metric": "input Gbp/s to exact junction set", "value": round(total_bp / (ms_per_step * 1e-3) / 1e9, 4), "unit": "Gbp/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": wl["name"], "total_bp": total_bp, "k": wl["k"], "filter_bits": wl["f"], "q": wl["q"],
+                   "parallelism": f"hash-range shards x{world}" if world > 1 else "single GPU",
+                   "l2_hygiene": "inputs (packed genome + 2^f-bit filter) are far larger than the 126 MB L2"},
+        "stages_ms": {k: round(v / args.steps, 3) for k, v in stage_ms.items()},
+        "result": {**runner.last, "candidate_marks": st.candidate_marks, "candidate_kmers": st.candidate_kmers},
+        "gpu_launches": launches, "roofline": roofline,
+    }
+    if rank == 0:
+        result["clocks"] = clocks.summary()
+
+    # ---- end-to-end through the C ABI with host buffers (N = 1) ---------------------------------
+    if not args.no_e2e and world == 1:
+        runner.session.close()
+        host = dg.to_host()
+        codes = torch.from_numpy(host.codes.view(np.int64)).pin_memory()
+        nmask = torch.from_numpy(host.n_mask.view(np.int64)).pin_memory()
+        pinned = api.PackedGenome(codes.numpy().view(np.uint64), nmask.numpy().view(np.uint64), host.n_positions,
+                                  host.rec_start, host.rec_len)
+        out = torch.empty(runner.last["image_bytes"] + 4096, dtype=torch.uint8).pin_memory()
+        out_np = out.numpy()
+        times = []
+        for i in range(1 + max(1, min(args.steps, 3))):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            img, st2 = api.junctions_host(pinned, k=wl["k"], filter_bits=wl["f"], q=wl["q"], out=out_np)
+            torch.cuda.synchronize()
+            if i:
+                times.append(time.perf_counter() - t0)
+        e2e_s = float(np.mean(times))
+        result["e2e"] = {"value": round(total_bp / e2e_s / 1e9, 4), "unit": "Gbp/s",
+                         "h2d_bytes_per_step": int(pinned.codes.nbytes + pinned.n_mask.nbytes),
+                         "d2h_bytes_per_step": int(len(img)), "ms_per_step": round(e2e_s * 1e3, 3),
+                         "api": "tpc_junctions_host (pinned host genome -> pinned host de_bruijn.bin image)"}
+    elif world > 1:
+        result["e2e"] = None
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        result["cpu_baseline"] = cpu_baseline(dg, wl)
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def reference_arm(args, wl, world) -> None:
+    """--impl reference: the unmodified reference CPU implementation on a bounded sample of the
+    same workload (rank 0 only), all host cores."""
+    from oracle import oracle as O
+    from twopaco_b200 import api
+    if not O.have_reference():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/twopaco was not built (no /root/reference at build time)"}))
+        return
+    cores = os.cpu_count() or 1
+    dg = api.synth_family_device(wl["seed"], wl["genomes"], wl["records"], min(wl["length"], wl["sample_bp"] * 2), wl["p"])
+    recs = sample_records(dg, wl)
+    bp = sum(len(r) for r in recs)
+    times = []
+    for i in range(args.warmup + args.steps):
+        _, dt = run_reference_on(recs, wl, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = float(np.mean(times)) * 1e3
+    v = bp / (ms * 1e-3) / 1e9
+    sample = (f"first {wl['sample_bp']} bp of record 0 of each of the {wl['genomes']} genomes ({bp} bp), "
+              f"-t {cores}, wall incl. FASTA parsing")
+    print(json.dumps({
+        "impl": "reference", "metric": "input Gbp/s to exact junction set", "value": round(v, 6), "unit": "Gbp/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": wl["name"], "k": wl["k"], "filter_bits": min(wl["f"], 32), "q": wl["q"]},
+        "cpu_baseline": {"value": round(v, 6), "unit": "Gbp/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": round(v, 6), "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+if __name__ == "__main__":
+    main()

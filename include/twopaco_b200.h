@@ -188,6 +188,29 @@ int tpc_session_stats(tpc_session *s, tpc_stats *out);   /* synchronises the str
  * 2 = load + conditional atomicOr (the fill pattern).  Returns sector touches per second. */
 int tpc_random_access_probe(uint32_t filter_bits, uint32_t mode, uint64_t touches, double *touches_per_s);
 
+/* ------------------------------------------------------------------------------------------
+ * K0: ASCII -> 2-bit codes + N mask on the device.  dev_ascii holds one byte per position in
+ * the layout of tpc_genome ('N' or any non-ACGT byte at separators; case folded; the alphabet
+ * of dnachar.cpp:18-33).  The reference has no such step: it re-parses the ASCII FASTA once per
+ * stage (vertexenumerator.h:1135-1214).
+ * ---------------------------------------------------------------------------------------- */
+int tpc_pack_ascii_device(const uint8_t *dev_ascii, uint64_t n_positions, uint64_t *dev_codes,
+                          uint64_t *dev_nmask, void *stream);
+
+/* Synthetic founder-family genome set generated ON the device: genome 0 is an
+ * i.i.d. uniform founder of records_per_genome x record_len bases; every other genome mutates
+ * each founder base with probability p (80 % SNP, 10 % 1-bp insertion, 10 % 1-bp deletion).
+ * Records are ordered genome-major.  Returns a device ASCII buffer in the tpc_genome layout
+ * (release with tpc_device_free) and fills the HOST arrays rec_start / rec_len
+ * (genomes * records_per_genome entries each). */
+int tpc_synth_family_device(uint64_t seed, uint32_t genomes, uint32_t records_per_genome,
+                            uint64_t record_len, double p, uint8_t **dev_ascii,
+                            uint64_t *n_positions, uint64_t *rec_start, uint64_t *rec_len);
+int tpc_device_alloc(uint64_t bytes, void **out);
+void tpc_device_free(void *p);
+int tpc_copy_to_host(void *host_dst, const void *dev_src, uint64_t bytes);
+int tpc_copy_to_device(void *dev_dst, const void *host_src, uint64_t bytes);
+
 const char *tpc_last_error(void);
 uint32_t tpc_abi_version(void);
 

@@ -17,6 +17,7 @@ ROOT = Path(__file__).resolve().parents[1]
 
 def test_every_declared_symbol_is_exported_and_bound():
     header = (ROOT / "include" / "twopaco_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)  # declarations only
     declared = set(re.findall(r"\b(tpc_[a-z0-9_]+)\s*\(", header)) - {"tpc_log_fn"}
     L = api.lib()
     for name in sorted(declared):

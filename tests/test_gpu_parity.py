@@ -218,3 +218,46 @@ def test_full_size_properties_c2_slice():
     lens = np.array([len(r) for r in recs], dtype=np.int64)
     mirrored = sorted(zip(seq_c.tolist(), (lens[seq_c] - 25 - pos_c.astype(np.int64)).tolist()))
     assert mirrored == sorted(zip(seq.tolist(), pos.astype(np.int64).tolist()))
+
+
+def test_k0_pack_ascii_device_matches_host_packer():
+    """K0 (ASCII -> 2-bit + N mask on the device) == tpc_pack_records on the host."""
+    recs = synth.founder_family(41, 3, 2, 70_001, 0.01, n_runs=3) + [b"", b"acgtnRYKM" * 7, b"ACG"]
+    host = api.pack_records(recs)
+    layout = bytearray(b"N")
+    for r in recs:
+        layout += r + b"N"
+    assert len(layout) == host.n_positions
+    buf = api.DeviceBuffer((len(layout) + 63) // 64 * 64 + 64)
+    buf.from_host(np.frombuffer(bytes(layout), dtype=np.uint8))
+    dg = api.pack_ascii_device(buf, host.n_positions, host.rec_start, host.rec_len)
+    dev = dg.to_host()
+    assert np.array_equal(dev.codes, host.codes) and np.array_equal(dev.n_mask, host.n_mask)
+
+
+def test_synth_family_device_generator():
+    """On-device founder-family generator: deterministic, right shape, right divergence."""
+    a = api.synth_family_device(0x4855, 4, 3, 200_000, 0.01)
+    b = api.synth_family_device(0x4855, 4, 3, 200_000, 0.01)
+    assert a.n_positions == b.n_positions and np.array_equal(a.codes.to_host(), b.codes.to_host())
+    assert len(a.rec_len) == 12 and np.all(a.rec_len[:3] == 200_000)
+    assert int(a.rec_start[0]) == 1 and a.n_positions == 1 + int((a.rec_len + 1).sum())
+    founder, derived = a.record_ascii(1), a.record_ascii(4)   # record 1 of genome 0 and of genome 1
+    assert set(founder) <= set(b"ACGT") and abs(len(derived) - len(founder)) < 200
+    # SNP-dominated divergence ~ 1 %: compare a prefix before indels shift the frame too far
+    f, d = np.frombuffer(founder[:2000], np.uint8), np.frombuffer(derived[:2000], np.uint8)
+    assert (f != d).mean() < 0.5
+    # the packed form spells the same bases as the ASCII buffer
+    host = a.to_host()
+    pos = np.arange(int(a.rec_start[4]), int(a.rec_start[4]) + 1000, dtype=np.uint64)
+    code = (host.codes[pos >> np.uint64(5)] >> (np.uint64(2) * (pos & np.uint64(31)))) & np.uint64(3)
+    assert bytes(np.frombuffer(b"ACGT", np.uint8)[code.astype(np.int64)]) == derived[:1000]
+    # and the junction finder agrees with the oracle on it
+    recs = [a.record_ascii(r) for r in range(12)]
+    ref, nj, _ = O.find_junctions(recs, 25)
+    s = api.Session(k=25, filter_bits=26)
+    a.attach(s)
+    s.find_candidates()
+    ptr, n = s.local_junctions()
+    assert n == nj
+    s.close()

@@ -77,6 +77,13 @@ SIGNATURES = {
     "tpc_session_get_id": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "tpc_session_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "tpc_random_access_probe": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_double)]),
+    "tpc_pack_ascii_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tpc_synth_family_device": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_double, C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]),
+    "tpc_device_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "tpc_device_free": (None, [C.c_void_p]),
+    "tpc_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "tpc_copy_to_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "tpc_last_error": (C.c_char_p, []),
     "tpc_abi_version": (C.c_uint32, []),
 }
@@ -297,3 +304,110 @@ def random_access_probe(filter_bits: int, mode: int, touches: int = 1 << 30) -> 
     v = C.c_double()
     _check(lib().tpc_random_access_probe(filter_bits, mode, touches, C.byref(v)))
     return v.value
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident genomes (benchmark inputs; K0 pack)
+# ---------------------------------------------------------------------------------------------
+class DeviceBuffer:
+    """cudaMalloc'ed buffer owned by Python (freed on close / GC)."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        _check(lib().tpc_device_alloc(nbytes, C.byref(p)))
+        self.ptr, self.nbytes = p.value, nbytes
+
+    @classmethod
+    def adopt(cls, ptr: int, nbytes: int) -> "DeviceBuffer":
+        self = cls.__new__(cls)
+        self.ptr, self.nbytes = ptr, nbytes
+        return self
+
+    def from_host(self, data: np.ndarray, offset: int = 0) -> None:
+        data = np.ascontiguousarray(data)
+        _check(lib().tpc_copy_to_device(C.c_void_p(self.ptr + offset), data.ctypes.data, data.nbytes))
+
+    def to_host(self, nbytes: int | None = None, offset: int = 0) -> np.ndarray:
+        n = self.nbytes - offset if nbytes is None else nbytes
+        out = np.empty(n, dtype=np.uint8)
+        _check(lib().tpc_copy_to_host(out.ctypes.data, C.c_void_p(self.ptr + offset), n))
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "ptr", None):
+            lib().tpc_device_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceGenome:
+    """Packed genome resident in HBM: codes / n_mask device buffers + host record table."""
+
+    def __init__(self, codes: DeviceBuffer, n_mask: DeviceBuffer, n_positions: int, rec_start: np.ndarray,
+                 rec_len: np.ndarray, ascii_buf: DeviceBuffer | None = None):
+        self.codes, self.n_mask, self.n_positions = codes, n_mask, int(n_positions)
+        self.rec_start, self.rec_len, self.ascii = rec_start, rec_len, ascii_buf
+
+    @property
+    def total_bp(self) -> int:
+        return int(self.rec_len.sum())
+
+    def attach(self, session: "Session") -> None:
+        session.set_genome_device(self.codes.ptr, self.n_mask.ptr, self.n_positions, self.rec_start, self.rec_len, keep=self)
+
+    def to_host(self) -> PackedGenome:
+        L = lib()
+        cw, mw = L.tpc_code_words(self.n_positions), L.tpc_mask_words(self.n_positions)
+        return PackedGenome(self.codes.to_host(cw * 8).view(np.uint64), self.n_mask.to_host(mw * 8).view(np.uint64),
+                            self.n_positions, self.rec_start, self.rec_len)
+
+    def record_ascii(self, r: int, length: int | None = None) -> bytes:
+        """Bases of record r (prefix of `length`) copied back from the device ASCII buffer."""
+        n = int(self.rec_len[r]) if length is None else min(int(length), int(self.rec_len[r]))
+        return self.ascii.to_host(n, int(self.rec_start[r])).tobytes()
+
+
+def pack_ascii_device(ascii_buf: DeviceBuffer, n_positions: int, rec_start: np.ndarray, rec_len: np.ndarray,
+                      keep_ascii: bool = True) -> DeviceGenome:
+    """K0 on the device: ASCII (tpc_genome layout) -> 2-bit codes + N mask."""
+    L = lib()
+    codes = DeviceBuffer(L.tpc_code_words(n_positions) * 8)
+    n_mask = DeviceBuffer(L.tpc_mask_words(n_positions) * 8)
+    _check(L.tpc_pack_ascii_device(C.c_void_p(ascii_buf.ptr), n_positions, C.c_void_p(codes.ptr), C.c_void_p(n_mask.ptr), None))
+    g = DeviceGenome(codes, n_mask, n_positions, rec_start, rec_len, ascii_buf if keep_ascii else None)
+    if not keep_ascii:
+        ascii_buf.close()
+    return g
+
+
+def synth_family_device(seed: int, genomes: int, records_per_genome: int, record_len: int, p: float,
+                        keep_ascii: bool = True) -> DeviceGenome:
+    """Founder-family genome set generated and packed on the device."""
+    L = lib()
+    n = genomes * records_per_genome
+    rec_start = np.empty(n, dtype=np.uint64)
+    rec_len = np.empty(n, dtype=np.uint64)
+    ptr, npos = C.c_void_p(), C.c_uint64()
+    _check(L.tpc_synth_family_device(seed, genomes, records_per_genome, record_len, p, C.byref(ptr), C.byref(npos),
+                                     rec_start.ctypes.data, rec_len.ctypes.data))
+    buf = DeviceBuffer.adopt(ptr.value, (npos.value + 63) // 64 * 64 + 64)
+    return pack_ascii_device(buf, npos.value, rec_start, rec_len, keep_ascii=keep_ascii)
+
+
+class _DevArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def as_torch(ptr: int, n: int, dtype):
+    """Zero-copy torch view of a device pointer owned by the library (for torch.distributed)."""
+    import torch
+    typestr = {torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=dtype, device="cuda")
+    return torch.as_tensor(_DevArray(ptr, n, typestr), device="cuda")
