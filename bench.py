@@ -228,7 +228,7 @@ def main() -> None:
         runner.step()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms = {k: 0.0 for k in ("ms_fill", "ms_query", "ms_insert", "ms_classify", "ms_index", "ms_emit")}
+    stage_ms = {k: 0.0 for k in ("ms_bin", "ms_fill", "ms_query", "ms_insert", "ms_classify", "ms_index", "ms_emit")}
     launches = 0
     with ClockSampler(local_rank) as clocks:
         ev0.record()

@@ -60,7 +60,8 @@ typedef struct tpc_stats {
     uint64_t stubs;              /* records that are end-of-sequence stubs                    */
     uint64_t out_bytes;          /* size of the de_bruijn.bin image                           */
     uint64_t filter_edges_set;   /* fill: (vertex, edge-slot) items that set a new bit        */
-    float ms_fill, ms_query, ms_insert, ms_classify, ms_index, ms_emit, ms_total; /* CUDA events */
+    float ms_bin, ms_fill, ms_query, ms_insert, ms_classify, ms_index, ms_emit, ms_total; /* CUDA events;
+                                    ms_bin = partition of filter records by slice (binned path only) */
     uint32_t kernel_launches;    /* kernels of this library launched by the call              */
     uint32_t reserved;
 } tpc_stats;

@@ -320,3 +320,40 @@ def test_cli_selftest_mode(tmp_path):
                        timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stderr.count("PASSED") == 10 and "FAILED" not in r.stderr
+
+
+# ---- binned filter passes (tpc_bin.cuh): forced on small inputs via the debug environment knobs --------
+@pytest.mark.parametrize("slice_log2,buffer_mb", [(13, 0), (12, 1), (16, 1), (10, 0)])
+@pytest.mark.parametrize("name", ["family_k25", "family_k63", "family_k127", "selftest_s3_k9", "edge_mixed_k5", "family_seam_k25"])
+def test_binned_filter_passes_match_golden(name, slice_log2, buffer_mb, golden, monkeypatch):
+    """Partition-by-filter-slice path: single wave (records shared by fill and query), several
+    waves (re-binned per pass, tiny buffer), many / few slices, overflow of skewed slices."""
+    spec, g = CASES[name], golden[name]
+    f = spec.get("f", 24)
+    if not 1 <= f - 3 - slice_log2 <= 8:
+        f = slice_log2 + 3 + 6
+    monkeypatch.setenv("TPC_FILTER_MODE", "binned")
+    monkeypatch.setenv("TPC_SLICE_LOG2", str(slice_log2))
+    if buffer_mb:
+        monkeypatch.setenv("TPC_BIN_BUFFER_MB", str(buffer_mb))
+    with case_files(spec) as (paths, _, _):
+        recs = api.read_fasta(paths)
+    img, st = api.junctions_host(api.pack_records(recs), k=spec["k"], filter_bits=f, q=spec.get("q", 5))
+    assert st.ms_bin > 0, "binned path was not taken"
+    assert canon_md5(bytes(img)) == g["canon_md5"]
+    assert st.junctions == g["distinct_junctions"]
+
+
+def test_binned_rounds_and_shards(monkeypatch, golden):
+    monkeypatch.setenv("TPC_FILTER_MODE", "binned")
+    monkeypatch.setenv("TPC_SLICE_LOG2", "12")
+    spec, g = CASES["family_k25"], golden["family_k25"]
+    with case_files(spec) as (paths, _, _):
+        recs = api.read_fasta(paths)
+    img, st = api.junctions_host(api.pack_records(recs), k=25, filter_bits=20, q=3, rounds=3)
+    assert st.ms_bin > 0 and canon_md5(bytes(img)) == g["canon_md5"]
+    # skew: a genome that is one k-mer repeated sends every record to a single slice (overflow path)
+    rep = [b"ACGTTGCA" * 40_000, b"ACGTTGCA" * 30_000 + b"T"]
+    ref, nj, _ = O.find_junctions(rep, 25)
+    img, st = api.junctions_host(api.pack_records(rep), k=25, filter_bits=22, q=5)
+    assert bytes(img) == ref   # (falls back to the direct kernels when the overflow area is exceeded)

@@ -34,7 +34,7 @@ class Stats(C.Structure):
     _fields_ = [("positions", C.c_uint64), ("candidate_marks", C.c_uint64), ("candidate_kmers", C.c_uint64),
                 ("junctions", C.c_uint64), ("occurrences", C.c_uint64), ("stubs", C.c_uint64),
                 ("out_bytes", C.c_uint64), ("filter_edges_set", C.c_uint64),
-                ("ms_fill", C.c_float), ("ms_query", C.c_float), ("ms_insert", C.c_float), ("ms_classify", C.c_float),
+                ("ms_bin", C.c_float), ("ms_fill", C.c_float), ("ms_query", C.c_float), ("ms_insert", C.c_float), ("ms_classify", C.c_float),
                 ("ms_index", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float),
                 ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
 

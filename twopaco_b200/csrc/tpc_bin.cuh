@@ -1,0 +1,144 @@
+// tpc_bin.cuh -- "binned" filter passes: make the random filter traffic L2-resident.
+//
+// Measured on B200 (profiles/): uniform random 32-byte sector touches into a 2^36-bit table run
+// at ~18.6 G/s (each L2 miss moves a whole 128-byte line from HBM), but at >100 G/s when the
+// touched range fits the 126 MB L2.  So instead of touching the filter in genome order
+// (k_fill / k_query), the binned path
+//   1. k_bin: streams the genome ONCE, computes per owned definite k-mer a 12-byte record
+//      {Bloom mask, sector-in-slice | neighbour code, position} and radix-partitions the records
+//      by filter slice (slice = 2^slice_log2 bytes, default 64 MiB): CTA-level counting sort in
+//      shared memory, coalesced bulk writes per slice (sequential HBM traffic);
+//   2. k_apply_fill / k_apply_query: one launch per slice over that slice's records; the slice is
+//      fetched from HBM once and every further touch is an L2 hit.
+// When one wave of records fits in free HBM the same records serve both passes.
+#pragma once
+#include "tpc_kernels.cuh"
+
+namespace tpc {
+
+constexpr int kBinHalf = 16;                       // positions per thread per staging round
+constexpr int kBinStage = kTileThreads * kBinHalf;  // 4096 records staged per round
+constexpr int kBinMaxBuckets = 256;
+constexpr int kBinNbShift = 26;                    // record word 1: sector-in-slice | nb << 26
+constexpr size_t kBinSmemBytes = kBinMaxBuckets * 8 + kBinMaxBuckets * 4 * 2 + 8 * 4 + kBinStage * 4 * 3;
+
+struct BinView {
+    uint32_t* rec;                 // [bucket][3][cap] : mask | word1 | relative position
+    unsigned long long* count;     // [buckets] records reserved (may exceed cap)
+    uint32_t* ov;                  // overflow records {mask, word1, relpos, bucket}
+    unsigned long long* ov_count;
+    uint64_t cap, ov_cap;
+    uint32_t bucket_bits;          // log2(#slices)
+    uint32_t sib_bits;             // log2(sectors per slice)
+};
+
+__device__ __forceinline__ uint32_t encode_neigh(const Neigh& nb) {
+    return nb.a | (nb.a_n ? 4u : 0u) | (nb.b << 3) | (nb.b_n ? 32u : 0u);
+}
+__device__ __forceinline__ Neigh decode_neigh(uint32_t c) {
+    Neigh nb;
+    nb.a = c & 3u; nb.a_n = (c & 4u) != 0; nb.b = (c >> 3) & 3u; nb.b_n = (c & 32u) != 0;
+    return nb;
+}
+
+template <int W, int Q>
+__global__ void __launch_bounds__(kTileThreads, 2)
+k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_end, uint64_t wave_base) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* gbase = reinterpret_cast<unsigned long long*>(smem_raw);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(gbase + kBinMaxBuckets);
+    uint32_t* pref = hist + kBinMaxBuckets;
+    uint32_t* warp_tot = pref + kBinMaxBuckets;
+    uint32_t* st_a = warp_tot + 8;
+    uint32_t* st_b = st_a + kBinStage;
+    uint32_t* st_c = st_b + kBinStage;
+    const uint32_t nbuckets = 1u << bin.bucket_bits;
+    const uint32_t sib_mask = (1u << bin.sib_bits) - 1u;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    for (uint64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+        uint64_t w = tile * kTileThreads + tid;
+        Window<W> win;
+        win.valid = 0; win.prev_n = 0; win.next_n = 0; win.next_feed = 0; win.prev_feed = 0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) { win.X.w[j] = 0; win.Y.w[j] = 0; }
+        if (w * 32 < g.npos) win.load(g, w, kp.k);
+        uint64_t nf = win.next_feed, pf = win.prev_feed;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            hist[tid] = 0;
+            __syncthreads();
+            uint32_t rm[kBinHalf], rw[kBinHalf], rk[kBinHalf];
+#pragma unroll
+            for (int j = 0; j < kBinHalf; ++j) {
+                int i = half * kBinHalf + j;
+                uint32_t nxt = (uint32_t)nf & 3u, prv = (uint32_t)pf & 3u;
+                nf >>= 2; pf >>= 2;
+                rk[j] = ~0u; rm[j] = 0; rw[j] = 0;
+                if ((win.valid >> i) & 1u) {
+                    bool fwd = kmer_less<W>(win.X, win.Y);
+                    uint64_t h = kmer_hash<W>(fwd ? win.X : win.Y, kp.seed);
+                    if (kp.nparts == 1 || hash_part(h, kp.nparts) == kp.part) {
+                        Neigh nb = orient(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
+                        uint64_t s = hash_sector(h, kp.sector_shift);
+                        uint32_t bucket = (uint32_t)(s >> bin.sib_bits);
+                        rm[j] = vertex_mask<Q>(h);
+                        rw[j] = ((uint32_t)s & sib_mask) | (encode_neigh(nb) << kBinNbShift);
+                        rk[j] = (bucket << 16) | atomicAdd(&hist[bucket], 1u);
+                    }
+                }
+                roll<W>(win.X, win.Y, nxt, kp.k);
+            }
+            __syncthreads();
+            // exclusive scan of the histogram + global reservation per slice
+            uint32_t cnt = hist[tid], incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) warp_tot[wid] = incl;
+            __syncthreads();
+            uint32_t base = 0;
+            for (int j = 0; j < wid; ++j) base += warp_tot[j];
+            pref[tid] = base + incl - cnt;
+            if (cnt) gbase[tid] = atomicAdd(&bin.count[tid], (unsigned long long)cnt);
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < kBinHalf; ++j) {
+                if (rk[j] != ~0u) {
+                    uint32_t idx = pref[rk[j] >> 16] + (rk[j] & 0xFFFFu);
+                    st_a[idx] = rm[j];
+                    st_b[idx] = rw[j];
+                    st_c[idx] = (uint32_t)(w * 32 + half * kBinHalf + j - wave_base);
+                }
+            }
+            __syncthreads();
+            // bulk copy-out, one warp per slice: coalesced runs in the slice's record arrays
+            for (uint32_t b = wid; b < nbuckets; b += kTileThreads / 32) {
+                uint32_t n = hist[b];
+                if (!n) continue;
+                uint32_t s0 = pref[b];
+                unsigned long long gb = gbase[b];
+                uint32_t* ra = bin.rec + (uint64_t)b * 3 * bin.cap;
+                for (uint32_t j = lane; j < n; j += 32) {
+                    unsigned long long dst = gb + j;
+                    if (dst < bin.cap) {
+                        __stcs(ra + dst, st_a[s0 + j]);
+                        __stcs(ra + bin.cap + dst, st_b[s0 + j]);
+                        __stcs(ra + 2 * bin.cap + dst, st_c[s0 + j]);
+                    } else {
+                        unsigned long long o = atomicAdd(bin.ov_count, 1ull);
+                        if (o < bin.ov_cap) {
+                            uint4 r = make_uint4(st_a[s0 + j], st_b[s0 + j], st_c[s0 + j], b);
+                            reinterpret_cast<uint4*>(bin.ov)[o] = r;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace tpc

@@ -203,11 +203,13 @@ __device__ __forceinline__ uint64_t hash_slot(uint64_t h, uint32_t log2cap) {
     return (h * 0x9E3779B97F4A7C15ull) >> (64 - log2cap);
 }
 
-// Bloom bits of edge slot `slot` (0..3 in-edge by base, 4..7 out-edge by base, canonical
-// orientation) inside that slot's 32-bit word of the vertex's sector: Q bit positions.
+// Bloom bits of a vertex: Q bit positions inside a 32-bit word.  The SAME mask is used in each
+// of the 8 edge-slot words of the vertex's sector (word c = in-edge with base c, word 4+c =
+// out-edge with base c, canonical orientation): each word is an independent Bloom filter over
+// the vertices that have that edge, so sharing the mask between words costs nothing.
 template <int Q>
-__device__ __forceinline__ uint32_t slot_bits(uint64_t h, uint32_t slot) {
-    uint32_t g = fmix32((uint32_t)h + slot * 0x9E3779B9u + (uint32_t)(h >> 32) * 0x85EBCA77u);
+__device__ __forceinline__ uint32_t vertex_mask(uint64_t h) {
+    uint32_t g = fmix32((uint32_t)h ^ ((uint32_t)(h >> 32) * 0x85EBCA77u));
     uint32_t m = 0;
 #pragma unroll
     for (int t = 0; t < Q; ++t) {

@@ -44,6 +44,34 @@ __device__ __forceinline__ uint32_t filter_set(uint32_t* word, uint32_t m) {
     return 0;
 }
 
+// Record the in-edge and the out-edge of one occurrence in the vertex's sector.  An 'N'
+// neighbour is unique: make every occurrence of this k-mer a candidate by recording two
+// distinct dummy edges (h:1044-1058).
+__device__ __forceinline__ uint32_t fill_vertex(uint32_t* sec, uint32_t m, const Neigh& nb) {
+    uint32_t fresh = 0;
+    if (!nb.a_n) fresh += filter_set(sec + nb.a, m);
+    else { fresh += filter_set(sec + 0, m); fresh += filter_set(sec + 3, m); }
+    if (!nb.b_n) fresh += filter_set(sec + 4 + nb.b, m);
+    else { fresh += filter_set(sec + 4, m); fresh += filter_set(sec + 7, m); }
+    return fresh;
+}
+
+// All 8 edge queries of one k-mer from its sector (h:640-660): the edge actually present at
+// this occurrence counts once; any other edge recorded in the filter counts too.
+__device__ __forceinline__ bool query_vertex(const uint32_t* sec, uint32_t m, const Neigh& nb) {
+    uint4 sin = ld_nc_v4(sec);
+    uint4 sout = ld_nc_v4(sec + 4);
+    uint32_t si[4] = {sin.x, sin.y, sin.z, sin.w};
+    uint32_t so[4] = {sout.x, sout.y, sout.z, sout.w};
+    uint32_t in_cnt = nb.a_n ? 2u : 0u, out_cnt = nb.b_n ? 2u : 0u;
+#pragma unroll
+    for (uint32_t c = 0; c < 4; ++c) {
+        in_cnt += (c == nb.a || (si[c] & m) == m) ? 1u : 0u;
+        out_cnt += (c == nb.b || (so[c] & m) == m) ? 1u : 0u;
+    }
+    return in_cnt > 1 || out_cnt > 1;
+}
+
 template <int W, int Q>
 __global__ void __launch_bounds__(kTileThreads)
 k_fill(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t ntiles, Counters* ctr) {
@@ -66,12 +94,7 @@ k_fill(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t ntiles,
                 if (kp.nparts == 1 || hash_part(h, kp.nparts) == kp.part) {
                     Neigh nb = orient(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
                     uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
-                    // An 'N' neighbour is unique: make every occurrence of this k-mer a
-                    // candidate by recording two distinct dummy edges (h:1044-1058).
-                    if (!nb.a_n) fresh += filter_set(sec + nb.a, slot_bits<Q>(h, nb.a));
-                    else { fresh += filter_set(sec + 0, slot_bits<Q>(h, 0)); fresh += filter_set(sec + 3, slot_bits<Q>(h, 3)); }
-                    if (!nb.b_n) fresh += filter_set(sec + 4 + nb.b, slot_bits<Q>(h, 4 + nb.b));
-                    else { fresh += filter_set(sec + 4, slot_bits<Q>(h, 4)); fresh += filter_set(sec + 7, slot_bits<Q>(h, 7)); }
+                    fresh += fill_vertex(sec, vertex_mask<Q>(h), nb);
                 }
             }
             roll<W>(win.X, win.Y, nxt, kp.k);
@@ -108,20 +131,7 @@ k_query(GenomeView g, const uint32_t* __restrict__ filter, KParams kp, uint64_t 
                     if (kp.nparts == 1 || hash_part(h, kp.nparts) == kp.part) {
                         Neigh nb = orient(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
                         const uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
-                        uint4 sin = ld_nc_v4(sec);
-                        uint4 sout = ld_nc_v4(sec + 4);
-                        uint32_t si[4] = {sin.x, sin.y, sin.z, sin.w};
-                        uint32_t so[4] = {sout.x, sout.y, sout.z, sout.w};
-                        // h:640-654: the edge actually present at this occurrence counts
-                        // once; any other edge recorded in the filter counts too.
-                        uint32_t in_cnt = nb.a_n ? 2u : 0u, out_cnt = nb.b_n ? 2u : 0u;
-#pragma unroll
-                        for (uint32_t c = 0; c < 4; ++c) {
-                            uint32_t mi = slot_bits<Q>(h, c), mo = slot_bits<Q>(h, 4 + c);
-                            in_cnt += (c == nb.a || (si[c] & mi) == mi) ? 1u : 0u;
-                            out_cnt += (c == nb.b || (so[c] & mo) == mo) ? 1u : 0u;
-                        }
-                        if (in_cnt > 1 || out_cnt > 1) out |= 1u << i;
+                        if (query_vertex(sec, vertex_mask<Q>(h), nb)) out |= 1u << i;
                     }
                 }
                 roll<W>(win.X, win.Y, nxt, kp.k);

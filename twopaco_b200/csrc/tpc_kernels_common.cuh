@@ -1,6 +1,7 @@
 // tpc_kernels_common.cuh -- kernels that do not depend on the k-mer word count
 // (included by tpc_session.cu only).
 #pragma once
+#include "tpc_bin.cuh"
 #include "tpc_kernels.cuh"
 
 namespace tpc {
@@ -109,6 +110,68 @@ k_probe(uint32_t* __restrict__ table, uint32_t sector_bits, uint32_t mode, uint6
         }
     }
     if (acc == 0x9e3779b9u) atomicAdd(sink, 1ull);
+}
+
+// ---- apply: one launch per slice; the slice stays in L2 ------------------------------------------
+__global__ void __launch_bounds__(256)
+k_apply_fill(uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, const unsigned long long* __restrict__ count,
+             uint64_t cap, uint32_t sib_mask, Counters* ctr) {
+    __shared__ unsigned long long red[8];
+    unsigned long long n = *count;
+    if (n > cap) n = cap;
+    unsigned long long fresh = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t m = __ldcs(rec + i), w1 = __ldcs(rec + cap + i);
+        fresh += fill_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), m, decode_neigh(w1 >> kBinNbShift));
+    }
+    unsigned long long t = block_sum(fresh, red);
+    if (threadIdx.x == 0 && t) atomicAdd(&ctr->filter_new, t);
+}
+
+__global__ void __launch_bounds__(256)
+k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, const unsigned long long* __restrict__ count,
+              uint64_t cap, uint32_t sib_mask, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr) {
+    __shared__ unsigned long long red[8];
+    unsigned long long n = *count;
+    if (n > cap) n = cap;
+    unsigned long long marks = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t m = __ldcs(rec + i), w1 = __ldcs(rec + cap + i);
+        if (query_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), m, decode_neigh(w1 >> kBinNbShift))) {
+            uint64_t p = wave_base + __ldcs(rec + 2 * cap + i);
+            atomicOr(mask + (p >> 5), 1u << (p & 31));
+            ++marks;
+        }
+    }
+    unsigned long long t = block_sum(marks, red);
+    if (threadIdx.x == 0 && t) atomicAdd(&ctr->marks, t);
+}
+
+// records that did not fit their slice's array (skewed inputs): direct random access
+__global__ void __launch_bounds__(256)
+k_apply_overflow(uint32_t* __restrict__ filter, const uint32_t* __restrict__ ov, const unsigned long long* __restrict__ ov_count,
+                 uint64_t ov_cap, uint32_t sib_bits, int do_query, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr) {
+    __shared__ unsigned long long red[8];
+    unsigned long long n = *ov_count;
+    if (n > ov_cap) n = ov_cap;
+    unsigned long long acc = 0;
+    const uint32_t sib_mask = (1u << sib_bits) - 1u;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint4 r = reinterpret_cast<const uint4*>(ov)[i];
+        uint32_t* sec = filter + ((((uint64_t)r.w << sib_bits) | (r.y & sib_mask)) << 3);
+        Neigh nb = decode_neigh(r.y >> kBinNbShift);
+        if (!do_query) acc += fill_vertex(sec, r.x, nb);
+        else if (query_vertex(sec, r.x, nb)) {
+            uint64_t p = wave_base + r.z;
+            atomicOr(mask + (p >> 5), 1u << (p & 31));
+            ++acc;
+        }
+    }
+    unsigned long long t = block_sum(acc, red);
+    if (threadIdx.x == 0 && t) atomicAdd(do_query ? &ctr->marks : &ctr->filter_new, t);
 }
 
 }  // namespace tpc

@@ -1,5 +1,6 @@
 // tpc_launch_impl.cuh -- included by tpc_w<W>.cu; defines Launch<W>.
 #pragma once
+#include "tpc_bin.cuh"
 #include "tpc_kernels.cuh"
 #include "tpc_launch.cuh"
 
@@ -45,6 +46,26 @@ cudaError_t Launch<W>::query(const LaunchCtx& c, GenomeView g, const uint32_t* f
     TPC_Q_SWITCH(kp.q, {
         int grid = persistent_grid(k_query<W, Q>, kTileThreads, c.sm_count, ntiles);
         k_query<W, Q><<<grid, kTileThreads, 0, c.stream>>>(g, filter, kp, ntiles, mask, accumulate, ctr);
+    });
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+template <int W>
+cudaError_t Launch<W>::bin(const LaunchCtx& c, GenomeView g, KParams kp, const BinView& bv, uint64_t tile_begin, uint64_t tile_end,
+                           uint64_t wave_base) {
+    if (tile_end <= tile_begin) return cudaSuccess;
+    TPC_Q_SWITCH(kp.q, {
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k_bin<W, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinSmemBytes);
+            configured = true;
+        }
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin<W, Q>, kTileThreads, kBinSmemBytes);
+        uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count;
+        if (grid > tile_end - tile_begin) grid = tile_end - tile_begin;
+        k_bin<W, Q><<<(int)grid, kTileThreads, kBinSmemBytes, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base);
     });
     ++*c.launches;
     return cudaGetLastError();

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -42,6 +43,37 @@ const char* last_error() { return g_error.c_str(); }
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// device memory: stream-ordered allocations from the device's default pool, which is told to keep
+// freed memory (release threshold = max) so that repeated runs do not pay cudaMalloc/cudaFree.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t dev_alloc(T** p, size_t bytes, cudaStream_t st) {
+    return cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 16, st);
+}
+static cudaError_t dev_free(void* p, cudaStream_t st) { return p ? cudaFreeAsync(p, st) : cudaSuccess; }
+
+static void configure_pool(int device) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+}
+
+// memory a new allocation can use: free device memory + what the pool holds but does not use
+static uint64_t available_bytes(int device) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    cudaMemPool_t pool;
+    uint64_t reserved = 0, used = 0;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    }
+    return (uint64_t)free_b + (reserved > used ? reserved - used : 0);
+}
+
+// ---------------------------------------------------------------------------------------------
 // W-independent launchers
 // ---------------------------------------------------------------------------------------------
 cudaError_t launch_classify(const LaunchCtx& c, TableView T, uint64_t abundance, uint32_t use_abundance,
@@ -76,6 +108,33 @@ cudaError_t launch_scan_exclusive(const LaunchCtx& c, unsigned long long* data, 
     cudaError_t e = launch_scan_exclusive(c, scratch, nb, scratch + nb);
     if (e != cudaSuccess) return e;
     k_scan_apply<<<(unsigned)nb, 256, 0, c.stream>>>(data, n, scratch);
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+static int apply_grid(const LaunchCtx& c) { return c.sm_count * 8; }
+
+cudaError_t launch_apply_fill(const LaunchCtx& c, uint32_t* filter, const BinView& bv, uint32_t bucket, Counters* ctr) {
+    uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
+    k_apply_fill<<<apply_grid(c), 256, 0, c.stream>>>(slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap,
+                                                      (1u << bv.sib_bits) - 1u, ctr);
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_apply_query(const LaunchCtx& c, const uint32_t* filter, const BinView& bv, uint32_t bucket, uint32_t* mask,
+                               uint64_t wave_base, Counters* ctr) {
+    const uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
+    k_apply_query<<<apply_grid(c), 256, 0, c.stream>>>(slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap,
+                                                       (1u << bv.sib_bits) - 1u, mask, wave_base, ctr);
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_apply_overflow(const LaunchCtx& c, uint32_t* filter, const BinView& bv, int do_query, uint32_t* mask,
+                                  uint64_t wave_base, Counters* ctr) {
+    k_apply_overflow<<<c.sm_count, 256, 0, c.stream>>>(filter, bv.ov, bv.ov_count, bv.ov_cap, bv.sib_bits, do_query, mask,
+                                                       wave_base, ctr);
     ++*c.launches;
     return cudaGetLastError();
 }
@@ -133,6 +192,15 @@ struct tpc_session {
     uint64_t slice_tile_begin = 0, slice_tile_end = 0, slice_pos_begin = 0, slice_pos_end = 0;
     uint64_t slice_records = 0, slice_stubs = 0;
     bool have_candidates = false, have_index = false, have_count = false;
+
+    // binned filter passes (tpc_bin.cuh)
+    int filter_mode = 0;           // 0 auto, 1 direct, 2 binned (env TPC_FILTER_MODE)
+    uint32_t slice_log2 = 26;      // filter slice kept L2-resident by the apply kernels (env TPC_SLICE_LOG2)
+    uint64_t bin_budget_bytes = 0; // 0 = 70 % of free HBM (env TPC_BIN_BUFFER_MB)
+    uint32_t* d_bin_rec = nullptr;
+    unsigned long long* d_bin_count = nullptr;
+    uint32_t* d_bin_ov = nullptr;
+    bool used_binned = false;
 
     tpc_stats st{};
     cudaEvent_t ev[10]{};
@@ -200,10 +268,14 @@ int tpc_session_create(const tpc_params* params, void* stream, tpc_session** out
     s->stream = (cudaStream_t)stream;
     s->W = (int)((params->k + 31) / 32);
     s->filter_bits_eff = std::max<uint32_t>(params->filter_bits, 9u);
+    if (const char* e = getenv("TPC_FILTER_MODE")) s->filter_mode = !strcmp(e, "direct") ? 1 : !strcmp(e, "binned") ? 2 : 0;
+    if (const char* e = getenv("TPC_SLICE_LOG2")) s->slice_log2 = std::min(31, std::max(8, atoi(e)));
+    if (const char* e = getenv("TPC_BIN_BUFFER_MB")) s->bin_budget_bytes = (uint64_t)atoll(e) << 20;
     cudaGetDevice(&s->device);
+    configure_pool(s->device);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
     for (auto& ev : s->ev) cudaEventCreate(&ev);
-    if (cudaMalloc(&s->d_ctr, sizeof(Counters)) != cudaSuccess || cudaMalloc(&s->d_id, sizeof(long long)) != cudaSuccess) {
+    if (dev_alloc(&s->d_ctr, sizeof(Counters), s->stream) != cudaSuccess || dev_alloc(&s->d_id, sizeof(long long), s->stream) != cudaSuccess) {
         tpc_session_destroy(s);
         return set_error("cudaMalloc failed");
     }
@@ -217,9 +289,10 @@ void tpc_session_destroy(tpc_session* s) {
     cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_codes, s->d_nmask, s->d_rec_start, s->d_rec_len, s->d_sep_before, s->d_filter, s->d_mask,
                     s->d_stubmask, s->d_T, s->d_J, s->d_local, s->d_sorted, s->d_sort_tmp, s->d_ctr, s->d_id,
-                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch};
+                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch, s->d_bin_rec, s->d_bin_count, s->d_bin_ov};
     for (void* p : ptrs)
-        if (p) cudaFree(p);
+        dev_free(p, s->stream);
+    cudaStreamSynchronize(s->stream);
     for (auto& ev : s->ev)
         if (ev) cudaEventDestroy(ev);
     delete s;
@@ -243,9 +316,9 @@ static int adopt_records(tpc_session* s, const tpc_genome* g) {
     s->emit_prev[g->n_records] = prev;
     s->ntiles = (g->n_positions + kTilePos - 1) / kTilePos;
     size_t nr = std::max<uint64_t>(g->n_records, 1);
-    CK(cudaMalloc(&s->d_rec_start, nr * 8));
-    CK(cudaMalloc(&s->d_rec_len, nr * 8));
-    CK(cudaMalloc(&s->d_sep_before, nr * 4));
+    CK(dev_alloc(&s->d_rec_start, nr * 8, s->stream));
+    CK(dev_alloc(&s->d_rec_len, nr * 8, s->stream));
+    CK(dev_alloc(&s->d_sep_before, nr * 4, s->stream));
     if (g->n_records) {
         CK(cudaMemcpyAsync(s->d_rec_start, s->rec_start.data(), g->n_records * 8, cudaMemcpyHostToDevice, s->stream));
         CK(cudaMemcpyAsync(s->d_rec_len, s->rec_len.data(), g->n_records * 8, cudaMemcpyHostToDevice, s->stream));
@@ -258,8 +331,8 @@ int tpc_session_set_genome_host(tpc_session* s, const tpc_genome* g) {
     if (!s || !g) return set_error("null argument");
     if (s->g.codes) return set_error("genome already set");
     uint64_t cw = tpc_code_words(g->n_positions), mw = tpc_mask_words(g->n_positions);
-    CK(cudaMalloc(&s->d_codes, cw * 8));
-    CK(cudaMalloc(&s->d_nmask, mw * 8));
+    CK(dev_alloc(&s->d_codes, cw * 8, s->stream));
+    CK(dev_alloc(&s->d_nmask, mw * 8, s->stream));
     CK(cudaMemcpyAsync(s->d_codes, g->codes, cw * 8, cudaMemcpyHostToDevice, s->stream));
     CK(cudaMemcpyAsync(s->d_nmask, g->n_mask, mw * 8, cudaMemcpyHostToDevice, s->stream));
     s->g = GenomeView{s->d_codes, s->d_nmask, g->n_positions};
@@ -273,46 +346,128 @@ int tpc_session_set_genome_device(tpc_session* s, const tpc_genome* g) {
     return adopt_records(s, g);
 }
 
+// Filter passes of one round through the binned path.  Returns -1 when the binned path does not
+// apply and -2 when a slice overflowed beyond the overflow area (then the caller uses k_fill /
+// k_query), 0 on success, >0 on error.
+static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin, float* ms_fill, float* ms_query) {
+    if (s->filter_mode == 1) return -1;
+    int bb = (int)s->filter_bits_eff - 3 - (int)s->slice_log2;
+    if (bb < 1 || bb > 8) return -1;
+    if (s->filter_mode == 0 && s->g.npos < (1ull << 22)) return -1;
+    LaunchCtx lc = s->lctx();
+    BinView bv{};
+    bv.bucket_bits = (uint32_t)bb;
+    bv.sib_bits = s->filter_bits_eff - 8 - (uint32_t)bb;
+    const uint32_t buckets = 1u << bb;
+    uint64_t budget = s->bin_budget_bytes ? s->bin_budget_bytes : (uint64_t)(available_bytes(s->device) * 0.7);
+    // records of one wave must fit the budget: 12 B per record + 8 % slack per slice
+    uint64_t max_records = budget / 14;
+    uint64_t wave_pos = std::min<uint64_t>(s->ntiles * (uint64_t)kTilePos, (1ull << 32) - kTilePos);
+    if (max_records < wave_pos / kp.nparts) wave_pos = std::max<uint64_t>(max_records * kp.nparts, kTilePos);
+    uint64_t wave_tiles = std::max<uint64_t>(wave_pos / kTilePos, 1);
+    uint64_t nwaves = (s->ntiles + wave_tiles - 1) / wave_tiles;
+    uint64_t est = wave_tiles * kTilePos / kp.nparts;
+    bv.cap = ((uint64_t)(est / buckets * 1.08) + 8192 + 31) / 32 * 32;
+    bv.ov_cap = std::max<uint64_t>(1 << 16, est / 64);
+    CK(dev_alloc(&s->d_bin_rec, (uint64_t)buckets * 3 * bv.cap * 4, s->stream));
+    CK(dev_alloc(&s->d_bin_count, (buckets + 1) * 8, s->stream));
+    CK(dev_alloc(&s->d_bin_ov, bv.ov_cap * 16, s->stream));
+    bv.rec = s->d_bin_rec; bv.count = s->d_bin_count; bv.ov_count = s->d_bin_count + buckets; bv.ov = s->d_bin_ov;
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    unsigned long long ov_total = 0, ov_now = 0;
+    auto finish_wave = [&](float* a, float* b) -> int {
+        CK(cudaMemcpyAsync(&ov_now, bv.ov_count, 8, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaEventSynchronize(e2));
+        CK(cudaStreamSynchronize(s->stream));
+        float t = 0;
+        cudaEventElapsedTime(&t, e0, e1); *a += t;
+        cudaEventElapsedTime(&t, e1, e2); *b += t;
+        ov_total = std::max(ov_total, ov_now);
+        return 0;
+    };
+    int rc = 0;
+    for (int pass = 0; pass < 2 && rc == 0; ++pass) {           // 0 = fill, 1 = query
+        for (uint64_t wv = 0; wv < nwaves && rc == 0; ++wv) {
+            uint64_t t0 = wv * wave_tiles, t1 = std::min(s->ntiles, t0 + wave_tiles);
+            uint64_t base = t0 * kTilePos;
+            bool rebin = !(pass == 1 && nwaves == 1);           // one wave: the records serve both passes
+            CK(cudaEventRecord(e0, s->stream));
+            if (rebin) {
+                CK(cudaMemsetAsync(s->d_bin_count, 0, (buckets + 1) * 8, s->stream));
+                CK(W_DISPATCH(s, bin(lc, s->g, kp, bv, t0, t1, base)));
+            }
+            CK(cudaEventRecord(e1, s->stream));
+            for (uint32_t b = 0; b < buckets; ++b) {
+                if (pass == 0) CK(launch_apply_fill(lc, s->d_filter, bv, b, s->d_ctr));
+                else CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, base, s->d_ctr));
+            }
+            CK(launch_apply_overflow(lc, s->d_filter, bv, pass, s->d_mask, base, s->d_ctr));
+            CK(cudaEventRecord(e2, s->stream));
+            rc = finish_wave(ms_bin, pass == 0 ? ms_fill : ms_query);
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    for (void** p : {(void**)&s->d_bin_rec, (void**)&s->d_bin_count, (void**)&s->d_bin_ov}) {
+        dev_free(*p, s->stream);
+        *p = nullptr;
+    }
+    if (rc) return rc;
+    if (ov_total > bv.ov_cap) return -2;  // heavily skewed input: the caller redoes the round with k_fill / k_query
+    s->used_binned = true;
+    return 0;
+}
+
 int tpc_session_find_candidates(tpc_session* s) {
     if (!s || !s->g.codes) return set_error("no genome set");
     LaunchCtx lc = s->lctx();
     const uint64_t mask_words = s->ntiles * kTileThreads;
     const uint64_t filter_bytes = (1ull << s->filter_bits_eff) / 8;
-    if (!s->d_filter) CK(cudaMalloc(&s->d_filter, filter_bytes));
+    if (!s->d_filter) CK(dev_alloc(&s->d_filter, filter_bytes, s->stream));
     if (!s->d_mask) {
-        CK(cudaMalloc(&s->d_mask, std::max<uint64_t>(mask_words, 1) * 4));
-        CK(cudaMalloc(&s->d_stubmask, std::max<uint64_t>(mask_words, 1) * 4));
+        CK(dev_alloc(&s->d_mask, std::max<uint64_t>(mask_words, 1) * 4, s->stream));
+        CK(dev_alloc(&s->d_stubmask, std::max<uint64_t>(mask_words, 1) * 4, s->stream));
     }
     CK(cudaMemsetAsync(s->d_mask, 0, std::max<uint64_t>(mask_words, 1) * 4, s->stream));
     CK(cudaMemsetAsync(s->d_ctr, 0, sizeof(Counters), s->stream));
     s->local_count = 0;
     s->st = tpc_stats{};
     s->st.positions = s->g.npos;
-    float ms_fill = 0, ms_query = 0, ms_insert = 0, ms_classify = 0;
+    float ms_bin = 0, ms_fill = 0, ms_query = 0, ms_insert = 0, ms_classify = 0;
     Counters prev{}, cur{};
     for (uint32_t r = 0; r < s->prm.rounds; ++r) {
         KParams kp = s->kparams(s->prm.shard_index * s->prm.rounds + r);
         CK(cudaEventRecord(s->ev[0], s->stream));
         CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));  // h:257: zero-filled each round
-        CK(W_DISPATCH(s, fill(lc, s->g, s->d_filter, kp, s->ntiles, s->d_ctr)));
-        CK(cudaEventRecord(s->ev[1], s->stream));
-        CK(W_DISPATCH(s, query(lc, s->g, s->d_filter, kp, s->ntiles, s->d_mask, r > 0, s->d_ctr)));
+        float b_bin = 0, b_fill = 0, b_query = 0;
+        int brc = filter_passes_binned(s, kp, &b_bin, &b_fill, &b_query);
+        if (brc > 0) return brc;
+        if (brc == -2) {  // redo this round from scratch; marks already set are true marks and may stay
+            CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));
+            CK(cudaMemcpyAsync(s->d_ctr, &prev, sizeof prev, cudaMemcpyHostToDevice, s->stream));
+            CK(cudaEventRecord(s->ev[0], s->stream));
+        }
+        if (brc < 0) {
+            CK(W_DISPATCH(s, fill(lc, s->g, s->d_filter, kp, s->ntiles, s->d_ctr)));
+            CK(cudaEventRecord(s->ev[1], s->stream));
+            CK(W_DISPATCH(s, query(lc, s->g, s->d_filter, kp, s->ntiles, s->d_mask, r > 0 || brc == -2, s->d_ctr)));
+        } else {
+            CK(cudaEventRecord(s->ev[1], s->stream));
+        }
         CK(cudaEventRecord(s->ev[2], s->stream));
         CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
         uint64_t marks_r = cur.marks - prev.marks;
 
         // exact set of this round's candidates, sized from the number of marks
-        size_t free_b = 0, total_b = 0;
-        CK(cudaMemGetInfo(&free_b, &total_b));
-        uint64_t avail = free_b + s->T_bytes;
+        uint64_t avail = available_bytes(s->device) + s->T_bytes;
         uint32_t lg = std::max<uint32_t>(ceil_log2(marks_r * 2 + 16), 10);
         while (lg > 10 && (sizeof(Slot) << lg) > avail * 6 / 10) --lg;
         uint64_t need = sizeof(Slot) << lg;
         if (need > s->T_bytes) {
-            if (s->d_T) CK(cudaFree(s->d_T));
+            if (s->d_T) CK(dev_free(s->d_T, s->stream));
             s->d_T = nullptr; s->T_bytes = 0;
-            CK(cudaMalloc(&s->d_T, need));
+            CK(dev_alloc(&s->d_T, need, s->stream));
             s->T_bytes = need;
         }
         s->T_log2 = lg;
@@ -328,10 +483,10 @@ int tpc_session_find_candidates(tpc_session* s) {
         if (s->local_count + distinct_r > s->local_cap) {
             uint64_t ncap = std::max<uint64_t>(s->local_count + distinct_r, 1024);
             unsigned long long* nl = nullptr;
-            CK(cudaMalloc(&nl, ncap * 8));
+            CK(dev_alloc(&nl, ncap * 8, s->stream));
             if (s->local_count) CK(cudaMemcpyAsync(nl, s->d_local, s->local_count * 8, cudaMemcpyDeviceToDevice, s->stream));
             CK(cudaStreamSynchronize(s->stream));
-            if (s->d_local) CK(cudaFree(s->d_local));
+            if (s->d_local) CK(dev_free(s->d_local, s->stream));
             s->d_local = nl; s->local_cap = ncap;
         }
         CK(launch_classify(lc, T, s->prm.abundance, kp.count_occurrences, s->d_local, s->local_cap, s->d_ctr));
@@ -340,18 +495,22 @@ int tpc_session_find_candidates(tpc_session* s) {
         CK(cudaStreamSynchronize(s->stream));
         s->local_count = cur.junctions;
         float t;
-        cudaEventElapsedTime(&t, s->ev[0], s->ev[1]); ms_fill += t;
-        cudaEventElapsedTime(&t, s->ev[1], s->ev[2]); ms_query += t;
+        if (brc < 0) {
+            cudaEventElapsedTime(&t, s->ev[0], s->ev[1]); ms_fill += t;
+            cudaEventElapsedTime(&t, s->ev[1], s->ev[2]); ms_query += t;
+        } else {
+            ms_bin += b_bin; ms_fill += b_fill; ms_query += b_query;
+        }
         cudaEventElapsedTime(&t, s->ev[2], s->ev[3]); ms_insert += t;
         cudaEventElapsedTime(&t, s->ev[3], s->ev[4]); ms_classify += t;
         prev = cur;
     }
     // the table is only needed inside a round (h:337-338: per-round OccurenceSet)
-    if (s->d_T) { CK(cudaFree(s->d_T)); s->d_T = nullptr; s->T_bytes = 0; }
+    if (s->d_T) { CK(dev_free(s->d_T, s->stream)); s->d_T = nullptr; s->T_bytes = 0; }
     s->st.candidate_marks = cur.marks;
     s->st.candidate_kmers = cur.distinct;
     s->st.filter_edges_set = cur.filter_new;
-    s->st.ms_fill = ms_fill; s->st.ms_query = ms_query; s->st.ms_insert = ms_insert; s->st.ms_classify = ms_classify;
+    s->st.ms_bin = ms_bin; s->st.ms_fill = ms_fill; s->st.ms_query = ms_query; s->st.ms_insert = ms_insert; s->st.ms_classify = ms_classify;
     s->have_candidates = true;
     s->have_index = false;
     return 0;
@@ -368,22 +527,22 @@ int tpc_session_set_junctions(tpc_session* s, const uint64_t* dev_words_all, uin
     if (!s || !s->g.codes) return set_error("no genome set");
     LaunchCtx lc = s->lctx();
     CK(cudaEventRecord(s->ev[5], s->stream));
-    if (s->d_sorted) { CK(cudaFree(s->d_sorted)); s->d_sorted = nullptr; }
-    if (s->d_J) { CK(cudaFree(s->d_J)); s->d_J = nullptr; }
-    CK(cudaMalloc(&s->d_sorted, std::max<uint64_t>(n, 1) * 8));
+    if (s->d_sorted) { CK(dev_free(s->d_sorted, s->stream)); s->d_sorted = nullptr; }
+    if (s->d_J) { CK(dev_free(s->d_J, s->stream)); s->d_J = nullptr; }
+    CK(dev_alloc(&s->d_sorted, std::max<uint64_t>(n, 1) * 8, s->stream));
     if (n) {
         // ids = rank of the first occurrence position: plain library radix sort of <= J 40-bit keys
         size_t tmp = 0;
         CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, (const unsigned long long*)dev_words_all, s->d_sorted, n, 0, kPosBits, s->stream));
         if (tmp > s->sort_tmp_bytes) {
-            if (s->d_sort_tmp) CK(cudaFree(s->d_sort_tmp));
-            CK(cudaMalloc(&s->d_sort_tmp, tmp));
+            if (s->d_sort_tmp) CK(dev_free(s->d_sort_tmp, s->stream));
+            CK(dev_alloc(&s->d_sort_tmp, tmp, s->stream));
             s->sort_tmp_bytes = tmp;
         }
         CK(cub::DeviceRadixSort::SortKeys(s->d_sort_tmp, tmp, (const unsigned long long*)dev_words_all, s->d_sorted, n, 0, kPosBits, s->stream));
     }
     s->J_log2 = std::max<uint32_t>(ceil_log2(n * 2 + 16), 6);
-    CK(cudaMalloc(&s->d_J, sizeof(Slot) << s->J_log2));
+    CK(dev_alloc(&s->d_J, sizeof(Slot) << s->J_log2, s->stream));
     CK(cudaMemsetAsync(s->d_J, 0, sizeof(Slot) << s->J_log2, s->stream));
     CK(W_DISPATCH(s, build_index(lc, s->g, s->d_sorted, n, s->kparams(0), TableView{s->d_J, s->J_log2})));
     CK(cudaEventRecord(s->ev[6], s->stream));
@@ -412,11 +571,11 @@ int tpc_session_emit_count(tpc_session* s, uint64_t pos_begin, uint64_t pos_end,
     uint64_t nt = te - tb;
     if (nt + 1 > s->tile_cap) {
         for (void* p : {(void*)s->d_tile_rec, (void*)s->d_tile_stub, (void*)s->d_scan_scratch})
-            if (p) CK(cudaFree(p));
+            if (p) CK(dev_free(p, s->stream));
         s->d_tile_rec = s->d_tile_stub = s->d_scan_scratch = nullptr;
-        CK(cudaMalloc(&s->d_tile_rec, (nt + 1) * 8));
-        CK(cudaMalloc(&s->d_tile_stub, (nt + 1) * 8));
-        CK(cudaMalloc(&s->d_scan_scratch, scan_scratch_items(nt + 1) * 8));
+        CK(dev_alloc(&s->d_tile_rec, (nt + 1) * 8, s->stream));
+        CK(dev_alloc(&s->d_tile_stub, (nt + 1) * 8, s->stream));
+        CK(dev_alloc(&s->d_scan_scratch, scan_scratch_items(nt + 1) * 8, s->stream));
         s->tile_cap = nt + 1;
     }
     CK(cudaEventRecord(s->ev[7], s->stream));
@@ -505,7 +664,7 @@ int tpc_session_stats(tpc_session* s, tpc_stats* out) {
     float t = 0;
     if (s->have_index && cudaEventElapsedTime(&t, s->ev[5], s->ev[6]) == cudaSuccess) s->st.ms_index = t;
     if (s->st.out_bytes && cudaEventElapsedTime(&t, s->ev[7], s->ev[8]) == cudaSuccess) s->st.ms_emit = t;
-    s->st.ms_total = s->st.ms_fill + s->st.ms_query + s->st.ms_insert + s->st.ms_classify + s->st.ms_index + s->st.ms_emit;
+    s->st.ms_total = s->st.ms_bin + s->st.ms_fill + s->st.ms_query + s->st.ms_insert + s->st.ms_classify + s->st.ms_index + s->st.ms_emit;
     s->st.kernel_launches = s->launches;
     *out = s->st;
     return 0;
@@ -528,7 +687,7 @@ int tpc_session_run_to_count(tpc_session* s, uint64_t* image_bytes) {
 
 int tpc_session_write_host(tpc_session* s, uint8_t* out_image, uint64_t image_bytes) {
     uint8_t* d_out = nullptr;
-    CK(cudaMalloc(&d_out, std::max<uint64_t>(image_bytes, 16)));
+    CK(dev_alloc(&d_out, std::max<uint64_t>(image_bytes, 16), s->stream));
     uint64_t off = 0, bytes = 0;
     int rc = tpc_session_emit_write(s, 0, 0, d_out, image_bytes, &off, &bytes);
     if (rc == 0 && bytes) {
@@ -538,7 +697,7 @@ int tpc_session_write_host(tpc_session* s, uint8_t* out_image, uint64_t image_by
     } else if (rc == 0) {
         cudaStreamSynchronize(s->stream);
     }
-    cudaFree(d_out);
+    dev_free(d_out, s->stream);
     return rc;
 }
 
@@ -569,6 +728,12 @@ int tpc_junctions_host(const tpc_params* params, const tpc_genome* host_genome, 
 // ---------------------------------------------------------------------------------------------
 int tpc_random_access_probe(uint32_t filter_bits, uint32_t mode, uint64_t touches, double* touches_per_s) {
     if (filter_bits < 9 || filter_bits > 40 || mode > 2) return set_error("bad probe arguments");
+    if (const char* gran = getenv("TPC_L2_FETCH_GRANULARITY")) {
+        cudaError_t ge = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gran));
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "[tpc] L2 fetch granularity: requested %s -> %s, now %zu\n", gran, cudaGetErrorName(ge), got);
+    }
     uint32_t* table = nullptr;
     unsigned long long* sink = nullptr;
     uint64_t bytes = (1ull << filter_bits) / 8;
