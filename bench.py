@@ -134,56 +134,14 @@ class Runner:
         self.last = {}
 
     def step(self):
-        torch, api, wl, dg = self.torch, self.api, self.wl, self.dg
+        api, wl, dg = self.api, self.wl, self.dg
+        from twopaco_b200 import dist as tdist
         if self.session is not None:
             self.session.close()
         s = api.Session(k=wl["k"], filter_bits=wl["f"], q=wl["q"], shard_index=self.rank, shard_count=self.world)
         self.session = s
         dg.attach(s)
-        s.find_candidates()
-        ptr, n = s.local_junctions()
-        if self.world == 1:
-            s.set_junctions(ptr, n)
-            nrec, nstub = s.emit_count(0, dg.n_positions)
-            need = 12 * (nrec + len(dg.rec_len)) + 16
-            if self.out is None or self.out.nbytes < need:
-                self.out = api.DeviceBuffer(need)
-            off, nb = s.emit_write(0, 0, self.out.ptr, self.out.nbytes)
-            self.last = dict(junctions=n, records=nrec, stubs=nstub, image_bytes=nb)
-            return
-        import torch.distributed as dist
-        # (1) all-gather the shards' junction words (variable length)
-        local = api.as_torch(ptr, n, torch.int64)
-        counts = torch.zeros(self.world, dtype=torch.int64, device="cuda")
-        counts[self.rank] = n
-        dist.all_reduce(counts)
-        counts_h = counts.tolist()
-        mx = max(max(counts_h), 1)
-        padded = torch.zeros(mx, dtype=torch.int64, device="cuda")
-        padded[:n] = local
-        gathered = torch.empty(self.world * mx, dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(gathered, padded)
-        allj = torch.cat([gathered[r * mx: r * mx + counts_h[r]] for r in range(self.world)])
-        s.set_junctions(allj.data_ptr(), allj.numel())
-        # (2) OR-reduce the disjoint candidate masks (sum == or)
-        mptr, mw = s.candidate_mask()
-        dist.all_reduce(api.as_torch(mptr, mw, torch.int32))
-        # (3) position-sharded ordered emit
-        tiles = (dg.n_positions + api.TILE_POSITIONS - 1) // api.TILE_POSITIONS
-        cut = [min(dg.n_positions, (tiles * r // self.world) * api.TILE_POSITIONS) for r in range(self.world)] + [dg.n_positions]
-        nrec, nstub = s.emit_count(cut[self.rank], cut[self.rank + 1])
-        cnt = torch.zeros(self.world, 2, dtype=torch.int64, device="cuda")
-        cnt[self.rank, 0], cnt[self.rank, 1] = nrec, nstub
-        dist.all_reduce(cnt)
-        cnt_h = cnt.tolist()
-        rb = sum(c[0] for c in cnt_h[:self.rank])
-        sb = sum(c[1] for c in cnt_h[:self.rank])
-        need = 12 * (nrec + len(dg.rec_len)) + 16
-        if self.out is None or self.out.nbytes < need:
-            self.out = api.DeviceBuffer(need)
-        off, nb = s.emit_write(rb, sb, self.out.ptr, self.out.nbytes)
-        self.last = dict(junctions=allj.numel(), records=sum(c[0] for c in cnt_h), stubs=sum(c[1] for c in cnt_h),
-                         image_bytes=None, slice_offset=off, slice_bytes=nb)
+        self.last, self.out = tdist.sharded_run(s, dg, self.rank, self.world, self.out)
 
 
 def main() -> None:

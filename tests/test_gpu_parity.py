@@ -357,3 +357,19 @@ def test_binned_rounds_and_shards(monkeypatch, golden):
     ref, nj, _ = O.find_junctions(rep, 25)
     img, st = api.junctions_host(api.pack_records(rep), k=25, filter_bits=22, q=5)
     assert bytes(img) == ref   # (falls back to the direct kernels when the overflow area is exceeded)
+
+
+def test_multi_gpu_torchrun():
+    """N > 1: hash-range shards over NCCL (skipped on single-GPU boxes)."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "mgpu_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("mgpu ok") == 6

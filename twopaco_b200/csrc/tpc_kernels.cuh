@@ -32,6 +32,16 @@ struct Counters {
     unsigned long long dropped;      // classify: dropped by abundance
 };
 
+// HyperLogLog sketch (4096 registers) of the candidate k-mers, updated by the query kernels; the
+// host sizes the exact candidate table from it (the reference grows std::unordered_set instead).
+constexpr int kHllBits = 12;
+__device__ __forceinline__ void hll_add(uint32_t* __restrict__ hll, uint32_t vertex_mask_bits, uint64_t sector) {
+    uint64_t hh = fmix64(((uint64_t)vertex_mask_bits << 32) ^ sector);
+    uint32_t idx = (uint32_t)hh & ((1u << kHllBits) - 1u);
+    uint32_t rho = (uint32_t)__clzll((hh >> kHllBits) << kHllBits | (1ull << (kHllBits - 1))) + 1u;
+    if (rho > __ldcg(hll + idx)) atomicMax(hll + idx, rho);
+}
+
 // ------------------------------------------------------------------------------------------
 // pass 1a: fill
 // ------------------------------------------------------------------------------------------
@@ -110,7 +120,7 @@ k_fill(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t ntiles,
 template <int W, int Q>
 __global__ void __launch_bounds__(kTileThreads)
 k_query(GenomeView g, const uint32_t* __restrict__ filter, KParams kp, uint64_t ntiles,
-        uint32_t* __restrict__ mask, int accumulate, Counters* ctr) {
+        uint32_t* __restrict__ mask, int accumulate, Counters* ctr, uint32_t* __restrict__ hll) {
     __shared__ unsigned long long red[8];
     unsigned long long marks = 0;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -131,7 +141,11 @@ k_query(GenomeView g, const uint32_t* __restrict__ filter, KParams kp, uint64_t 
                     if (kp.nparts == 1 || hash_part(h, kp.nparts) == kp.part) {
                         Neigh nb = orient(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
                         const uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
-                        if (query_vertex(sec, vertex_mask<Q>(h), nb)) out |= 1u << i;
+                        uint32_t vm = vertex_mask<Q>(h);
+                        if (query_vertex(sec, vm, nb)) {
+                            out |= 1u << i;
+                            hll_add(hll, vm, hash_sector(h, kp.sector_shift));
+                        }
                     }
                 }
                 roll<W>(win.X, win.Y, nxt, kp.k);

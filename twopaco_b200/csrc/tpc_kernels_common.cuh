@@ -131,7 +131,8 @@ k_apply_fill(uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, con
 
 __global__ void __launch_bounds__(256)
 k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, const unsigned long long* __restrict__ count,
-              uint64_t cap, uint32_t sib_mask, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr) {
+              uint64_t cap, uint32_t sib_mask, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr,
+              uint32_t* __restrict__ hll, uint64_t slice_first_sector) {
     __shared__ unsigned long long red[8];
     unsigned long long n = *count;
     if (n > cap) n = cap;
@@ -140,6 +141,7 @@ k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ r
          i += (unsigned long long)gridDim.x * blockDim.x) {
         uint32_t m = __ldcs(rec + i), w1 = __ldcs(rec + cap + i);
         if (query_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), m, decode_neigh(w1 >> kBinNbShift))) {
+            hll_add(hll, m, slice_first_sector | (w1 & sib_mask));
             uint64_t p = wave_base + __ldcs(rec + 2 * cap + i);
             atomicOr(mask + (p >> 5), 1u << (p & 31));
             ++marks;
@@ -152,7 +154,8 @@ k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ r
 // records that did not fit their slice's array (skewed inputs): direct random access
 __global__ void __launch_bounds__(256)
 k_apply_overflow(uint32_t* __restrict__ filter, const uint32_t* __restrict__ ov, const unsigned long long* __restrict__ ov_count,
-                 uint64_t ov_cap, uint32_t sib_bits, int do_query, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr) {
+                 uint64_t ov_cap, uint32_t sib_bits, int do_query, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr,
+                 uint32_t* __restrict__ hll) {
     __shared__ unsigned long long red[8];
     unsigned long long n = *ov_count;
     if (n > ov_cap) n = ov_cap;
@@ -165,6 +168,7 @@ k_apply_overflow(uint32_t* __restrict__ filter, const uint32_t* __restrict__ ov,
         Neigh nb = decode_neigh(r.y >> kBinNbShift);
         if (!do_query) acc += fill_vertex(sec, r.x, nb);
         else if (query_vertex(sec, r.x, nb)) {
+            hll_add(hll, r.x, ((uint64_t)r.w << sib_bits) | (r.y & sib_mask));
             uint64_t p = wave_base + r.z;
             atomicOr(mask + (p >> 5), 1u << (p & 31));
             ++acc;

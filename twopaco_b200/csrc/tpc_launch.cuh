@@ -19,7 +19,7 @@ template <int W>
 struct Launch {
     static cudaError_t fill(const LaunchCtx&, GenomeView, uint32_t* filter, KParams, uint64_t ntiles, Counters*);
     static cudaError_t query(const LaunchCtx&, GenomeView, const uint32_t* filter, KParams, uint64_t ntiles,
-                             uint32_t* mask, int accumulate, Counters*);
+                             uint32_t* mask, int accumulate, Counters*, uint32_t* hll);
     static cudaError_t bin(const LaunchCtx&, GenomeView, KParams, const BinView&, uint64_t tile_begin, uint64_t tile_end,
                            uint64_t wave_base);
     static cudaError_t insert(const LaunchCtx&, GenomeView, const uint32_t* mask, KParams, uint64_t ntiles, TableView T, Counters*);

@@ -42,10 +42,10 @@ cudaError_t Launch<W>::fill(const LaunchCtx& c, GenomeView g, uint32_t* filter, 
 
 template <int W>
 cudaError_t Launch<W>::query(const LaunchCtx& c, GenomeView g, const uint32_t* filter, KParams kp, uint64_t ntiles,
-                             uint32_t* mask, int accumulate, Counters* ctr) {
+                             uint32_t* mask, int accumulate, Counters* ctr, uint32_t* hll) {
     TPC_Q_SWITCH(kp.q, {
         int grid = persistent_grid(k_query<W, Q>, kTileThreads, c.sm_count, ntiles);
-        k_query<W, Q><<<grid, kTileThreads, 0, c.stream>>>(g, filter, kp, ntiles, mask, accumulate, ctr);
+        k_query<W, Q><<<grid, kTileThreads, 0, c.stream>>>(g, filter, kp, ntiles, mask, accumulate, ctr, hll);
     });
     ++*c.launches;
     return cudaGetLastError();

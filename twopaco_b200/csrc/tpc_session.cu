@@ -1,6 +1,7 @@
 // tpc_session.cu -- sessions (C ABI level 3), the packed-genome entry point (level 2) and the
 // W-independent kernels.  One session = one GPU = one hash-range shard.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -123,18 +124,18 @@ cudaError_t launch_apply_fill(const LaunchCtx& c, uint32_t* filter, const BinVie
 }
 
 cudaError_t launch_apply_query(const LaunchCtx& c, const uint32_t* filter, const BinView& bv, uint32_t bucket, uint32_t* mask,
-                               uint64_t wave_base, Counters* ctr) {
+                               uint64_t wave_base, Counters* ctr, uint32_t* hll) {
     const uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
     k_apply_query<<<apply_grid(c), 256, 0, c.stream>>>(slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap,
-                                                       (1u << bv.sib_bits) - 1u, mask, wave_base, ctr);
+                                                       (1u << bv.sib_bits) - 1u, mask, wave_base, ctr, hll, (uint64_t)bucket << bv.sib_bits);
     ++*c.launches;
     return cudaGetLastError();
 }
 
 cudaError_t launch_apply_overflow(const LaunchCtx& c, uint32_t* filter, const BinView& bv, int do_query, uint32_t* mask,
-                                  uint64_t wave_base, Counters* ctr) {
+                                  uint64_t wave_base, Counters* ctr, uint32_t* hll) {
     k_apply_overflow<<<c.sm_count, 256, 0, c.stream>>>(filter, bv.ov, bv.ov_count, bv.ov_cap, bv.sib_bits, do_query, mask,
-                                                       wave_base, ctr);
+                                                       wave_base, ctr, hll);
     ++*c.launches;
     return cudaGetLastError();
 }
@@ -182,6 +183,7 @@ struct tpc_session {
     void* d_sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
     Counters* d_ctr = nullptr;
+    uint32_t* d_hll = nullptr;     // HyperLogLog registers of the round's candidates
     long long* d_id = nullptr;
 
     // emit slice state
@@ -275,7 +277,8 @@ int tpc_session_create(const tpc_params* params, void* stream, tpc_session** out
     configure_pool(s->device);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
     for (auto& ev : s->ev) cudaEventCreate(&ev);
-    if (dev_alloc(&s->d_ctr, sizeof(Counters), s->stream) != cudaSuccess || dev_alloc(&s->d_id, sizeof(long long), s->stream) != cudaSuccess) {
+    if (dev_alloc(&s->d_ctr, sizeof(Counters), s->stream) != cudaSuccess || dev_alloc(&s->d_id, sizeof(long long), s->stream) != cudaSuccess ||
+        dev_alloc(&s->d_hll, (4u << kHllBits), s->stream) != cudaSuccess) {
         tpc_session_destroy(s);
         return set_error("cudaMalloc failed");
     }
@@ -289,7 +292,7 @@ void tpc_session_destroy(tpc_session* s) {
     cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_codes, s->d_nmask, s->d_rec_start, s->d_rec_len, s->d_sep_before, s->d_filter, s->d_mask,
                     s->d_stubmask, s->d_T, s->d_J, s->d_local, s->d_sorted, s->d_sort_tmp, s->d_ctr, s->d_id,
-                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch, s->d_bin_rec, s->d_bin_count, s->d_bin_ov};
+                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch, s->d_bin_rec, s->d_bin_count, s->d_bin_ov, s->d_hll};
     for (void* p : ptrs)
         dev_free(p, s->stream);
     cudaStreamSynchronize(s->stream);
@@ -346,6 +349,16 @@ int tpc_session_set_genome_device(tpc_session* s, const tpc_genome* g) {
     return adopt_records(s, g);
 }
 
+static double hll_estimate(const std::vector<uint32_t>& reg) {
+    const double m = (double)reg.size();
+    double sum = 0;
+    uint32_t zeros = 0;
+    for (uint32_t r : reg) { sum += std::ldexp(1.0, -(int)r); zeros += r == 0; }
+    double e = (0.7213 / (1.0 + 1.079 / m)) * m * m / sum;
+    if (e <= 2.5 * m && zeros) e = m * std::log(m / zeros);  // small-range correction (linear counting)
+    return e;
+}
+
 // Filter passes of one round through the binned path.  Returns -1 when the binned path does not
 // apply and -2 when a slice overflowed beyond the overflow area (then the caller uses k_fill /
 // k_query), 0 on success, >0 on error.
@@ -400,9 +413,9 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
             CK(cudaEventRecord(e1, s->stream));
             for (uint32_t b = 0; b < buckets; ++b) {
                 if (pass == 0) CK(launch_apply_fill(lc, s->d_filter, bv, b, s->d_ctr));
-                else CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, base, s->d_ctr));
+                else CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, base, s->d_ctr, s->d_hll));
             }
-            CK(launch_apply_overflow(lc, s->d_filter, bv, pass, s->d_mask, base, s->d_ctr));
+            CK(launch_apply_overflow(lc, s->d_filter, bv, pass, s->d_mask, base, s->d_ctr, s->d_hll));
             CK(cudaEventRecord(e2, s->stream));
             rc = finish_wave(ms_bin, pass == 0 ? ms_fill : ms_query);
         }
@@ -439,18 +452,20 @@ int tpc_session_find_candidates(tpc_session* s) {
         KParams kp = s->kparams(s->prm.shard_index * s->prm.rounds + r);
         CK(cudaEventRecord(s->ev[0], s->stream));
         CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));  // h:257: zero-filled each round
+        CK(cudaMemsetAsync(s->d_hll, 0, 4u << kHllBits, s->stream));
         float b_bin = 0, b_fill = 0, b_query = 0;
         int brc = filter_passes_binned(s, kp, &b_bin, &b_fill, &b_query);
         if (brc > 0) return brc;
         if (brc == -2) {  // redo this round from scratch; marks already set are true marks and may stay
             CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));
             CK(cudaMemcpyAsync(s->d_ctr, &prev, sizeof prev, cudaMemcpyHostToDevice, s->stream));
+            CK(cudaMemsetAsync(s->d_hll, 0, 4u << kHllBits, s->stream));
             CK(cudaEventRecord(s->ev[0], s->stream));
         }
         if (brc < 0) {
             CK(W_DISPATCH(s, fill(lc, s->g, s->d_filter, kp, s->ntiles, s->d_ctr)));
             CK(cudaEventRecord(s->ev[1], s->stream));
-            CK(W_DISPATCH(s, query(lc, s->g, s->d_filter, kp, s->ntiles, s->d_mask, r > 0 || brc == -2, s->d_ctr)));
+            CK(W_DISPATCH(s, query(lc, s->g, s->d_filter, kp, s->ntiles, s->d_mask, r > 0 || brc == -2, s->d_ctr, s->d_hll)));
         } else {
             CK(cudaEventRecord(s->ev[1], s->stream));
         }
@@ -459,26 +474,38 @@ int tpc_session_find_candidates(tpc_session* s) {
         CK(cudaStreamSynchronize(s->stream));
         uint64_t marks_r = cur.marks - prev.marks;
 
-        // exact set of this round's candidates, sized from the number of marks
-        uint64_t avail = available_bytes(s->device) + s->T_bytes;
-        uint32_t lg = std::max<uint32_t>(ceil_log2(marks_r * 2 + 16), 10);
-        while (lg > 10 && (sizeof(Slot) << lg) > avail * 6 / 10) --lg;
-        uint64_t need = sizeof(Slot) << lg;
-        if (need > s->T_bytes) {
-            if (s->d_T) CK(dev_free(s->d_T, s->stream));
-            s->d_T = nullptr; s->T_bytes = 0;
-            CK(dev_alloc(&s->d_T, need, s->stream));
-            s->T_bytes = need;
-        }
-        s->T_log2 = lg;
-        TableView T{s->d_T, lg};
-        CK(cudaMemsetAsync(s->d_T, 0, need, s->stream));
-        CK(W_DISPATCH(s, insert(lc, s->g, s->d_mask, kp, s->ntiles, T, s->d_ctr)));
-        CK(cudaEventRecord(s->ev[3], s->stream));
-        CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
+        // exact set of this round's candidates, sized from the HyperLogLog estimate of their number
+        std::vector<uint32_t> hll(1u << kHllBits);
+        CK(cudaMemcpyAsync(hll.data(), s->d_hll, 4u << kHllBits, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
-        if (cur.overflow) return set_error("candidate table overflow (%llu marks, 2^%u slots): not enough device memory",
-                                           (unsigned long long)marks_r, lg);
+        double est = hll_estimate(hll);
+        if (est > (double)marks_r) est = (double)marks_r;
+        uint32_t lg = std::max<uint32_t>(ceil_log2((uint64_t)(est * 1.15 * 2.0) + 64), 10);
+        for (;;) {
+            uint64_t avail = available_bytes(s->device) + s->T_bytes;
+            uint64_t need = sizeof(Slot) << lg;
+            if (need > avail) return set_error("candidate table of 2^%u slots does not fit in device memory", lg);
+            if (need > s->T_bytes) {
+                if (s->d_T) CK(dev_free(s->d_T, s->stream));
+                s->d_T = nullptr; s->T_bytes = 0;
+                CK(dev_alloc(&s->d_T, need, s->stream));
+                s->T_bytes = need;
+            }
+            s->T_log2 = lg;
+            CK(cudaMemsetAsync(s->d_T, 0, need, s->stream));
+            CK(W_DISPATCH(s, insert(lc, s->g, s->d_mask, kp, s->ntiles, TableView{s->d_T, lg}, s->d_ctr)));
+            CK(cudaEventRecord(s->ev[3], s->stream));
+            CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+            if (cur.overflow == prev.overflow && (cur.distinct - prev.distinct) * 10 <= (7ull << lg)) break;
+            // estimate too low (cannot happen within HLL's error bars, but stay exact): grow and redo
+            Counters redo = cur;
+            redo.distinct = prev.distinct; redo.overflow = prev.overflow;
+            CK(cudaMemcpyAsync(s->d_ctr, &redo, sizeof redo, cudaMemcpyHostToDevice, s->stream));
+            cur = redo;
+            ++lg;
+        }
+        TableView T{s->d_T, s->T_log2};
         uint64_t distinct_r = cur.distinct - prev.distinct;
         if (s->local_count + distinct_r > s->local_cap) {
             uint64_t ncap = std::max<uint64_t>(s->local_count + distinct_r, 1024);
