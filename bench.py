@@ -206,28 +206,42 @@ def main() -> None:
     ms_per_step = ms / args.steps
     st = runner.session.stats()
 
-    # ---- roofline of the dominant kernel (algorithmic bytes per position) ----------
-    # query: one 32-byte filter sector per owned definite k-mer + the packed stream (0.375 B/bp read)
-    # + 1 bit/bp of candidate mask written.
+    # ---- roofline of the dominant filter-pass kernel ---------------------------
+    # algorithmic HBM bytes, summed over the kernel's launches of one step:
+    #   direct : k_fill  = 32 B (one filter sector) x owned k-mers + 0.375 B x positions (packed stream)
+    #            k_query = the same + 1 bit/position of candidate mask
+    #   binned : k_bin         = 0.375 B x positions + 12 B x records written        (per binning pass)
+    #            k_apply_fill  = 8 B x records read + filter read once and written back once per wave
+    #            k_apply_query = 8 B x records + 8 B x marks (position word + mask word) + filter read per wave
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except OSError:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    positions = st.positions
-    q_ms = stage_ms["ms_query"] / args.steps
-    f_ms = stage_ms["ms_fill"] / args.steps
-    alg_query = 32.0 * total_bp / world + 0.375 * positions + positions / 8.0
-    alg_fill = 32.0 * total_bp / world + 0.375 * positions
-    dom = "query" if q_ms >= f_ms else "fill"
-    dom_ms, dom_bytes = (q_ms, alg_query) if dom == "query" else (f_ms, alg_fill)
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "peak_source": "measured" if peaks else "fallback",
-                "traffic": None, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": round(dom_ms, 3),
-                "random_sector_touches_per_s": round(total_bp / world / (dom_ms * 1e-3) / 1e9, 2) if dom_ms > 0 else None,
-                "other": {"k_fill": {"ms": round(f_ms, 3), "GBps": round(alg_fill / (f_ms * 1e-3) / 1e9, 1) if f_ms > 0 else None}}}
+    positions, recs, marks = st.positions, total_bp / world, st.candidate_marks
+    filter_bytes = (1 << wl["f"]) / 8
+    per = {k: v / args.steps for k, v in stage_ms.items()}
+    if st.bin_waves:
+        waves = st.bin_waves
+        passes = 1 if waves == 1 else 2
+        kernels = {"k_bin": (per["ms_bin"], passes * (0.375 * positions + 12.0 * recs)),
+                   "k_apply_fill": (per["ms_fill"], 8.0 * recs + 2.0 * filter_bytes * waves),
+                   "k_apply_query": (per["ms_query"], 8.0 * recs + 8.0 * marks + filter_bytes * waves)}
+    else:
+        kernels = {"k_fill": (per["ms_fill"], 32.0 * recs + 0.375 * positions),
+                   "k_query": (per["ms_query"], 32.0 * recs + 0.5 * positions)}
+    dom = max(kernels, key=lambda k: kernels[k][0])
+    dom_ms, dom_bytes = kernels[dom]
+    gbps = lambda ms, nbytes: round(nbytes / (ms * 1e-3) / 1e9, 1) if ms > 0 else None
+    achieved = gbps(dom_ms, dom_bytes) or 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "peak_source": "measured" if peaks else "fallback", "traffic": None,
+                "algorithmic_bytes_per_step": dom_bytes, "ms_per_step": round(dom_ms, 3),
+                "filter_path": "binned (L2-resident slices)" if st.bin_waves else "direct (random HBM sectors)",
+                "filter_touches_per_s_G": {k: round(recs / (v[0] * 1e-3) / 1e9, 2) for k, v in kernels.items()
+                                            if v[0] > 0 and k != "k_bin"},
+                "all_filter_kernels": {k: {"ms": round(v[0], 3), "GBps": gbps(*v)} for k, v in kernels.items()}}
 
     result = {
         "metric": "input Gbp/s to exact junction set", "value": round(total_bp / (ms_per_step * 1e-3) / 1e9, 4), "unit": "Gbp/s",

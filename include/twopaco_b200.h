@@ -63,7 +63,8 @@ typedef struct tpc_stats {
     float ms_bin, ms_fill, ms_query, ms_insert, ms_classify, ms_index, ms_emit, ms_total; /* CUDA events;
                                     ms_bin = partition of filter records by slice (binned path only) */
     uint32_t kernel_launches;    /* kernels of this library launched by the call              */
-    uint32_t reserved;
+    uint32_t bin_waves;          /* binned path: waves of records per pass (1 = records shared by
+                                    fill and query); 0 = direct path                             */
 } tpc_stats;
 
 /* ------------------------------------------------------------------------------------------

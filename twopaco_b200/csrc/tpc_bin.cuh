@@ -77,7 +77,7 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
                 rk[j] = ~0u; rm[j] = 0; rw[j] = 0;
                 if ((win.valid >> i) & 1u) {
                     bool fwd = kmer_less<W>(win.X, win.Y);
-                    uint64_t h = kmer_hash<W>(fwd ? win.X : win.Y, kp.seed);
+                    uint64_t h = kmer_hash<W>(kmer_select<W>(fwd, win.X, win.Y), kp.seed);
                     if (kp.nparts == 1 || hash_part(h, kp.nparts) == kp.part) {
                         Neigh nb = orient(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
                         uint64_t s = hash_sector(h, kp.sector_shift);

@@ -173,6 +173,15 @@ __device__ __forceinline__ bool kmer_less(const Kmer<W>& a, const Kmer<W>& b) {
     return a.w[0] < b.w[0];
 }
 
+// c ? a : b, word by word (a ternary on the structs would force both into local memory)
+template <int W>
+__device__ __forceinline__ Kmer<W> kmer_select(bool c, const Kmer<W>& a, const Kmer<W>& b) {
+    Kmer<W> r;
+#pragma unroll
+    for (int j = 0; j < W; ++j) r.w[j] = c ? a.w[j] : b.w[j];
+    return r;
+}
+
 template <int W>
 __device__ __forceinline__ bool kmer_eq(const Kmer<W>& a, const Kmer<W>& b) {
     bool e = true;

@@ -100,7 +100,7 @@ k_fill(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t ntiles,
             nf >>= 2; pf >>= 2;
             if ((win.valid >> i) & 1u) {
                 bool fwd = kmer_less<W>(win.X, win.Y);
-                uint64_t h = kmer_hash<W>(fwd ? win.X : win.Y, kp.seed);
+                uint64_t h = kmer_hash<W>(kmer_select<W>(fwd, win.X, win.Y), kp.seed);
                 if (kp.nparts == 1 || hash_part(h, kp.nparts) == kp.part) {
                     Neigh nb = orient(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
                     uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
@@ -137,7 +137,7 @@ k_query(GenomeView g, const uint32_t* __restrict__ filter, KParams kp, uint64_t 
                 nf >>= 2; pf >>= 2;
                 if ((win.valid >> i) & 1u) {
                     bool fwd = kmer_less<W>(win.X, win.Y);
-                    uint64_t h = kmer_hash<W>(fwd ? win.X : win.Y, kp.seed);
+                    uint64_t h = kmer_hash<W>(kmer_select<W>(fwd, win.X, win.Y), kp.seed);
                     if (kp.nparts == 1 || hash_part(h, kp.nparts) == kp.part) {
                         Neigh nb = orient(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
                         const uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
@@ -176,7 +176,7 @@ __device__ __forceinline__ Occ<W> occurrence_at(const GenomeView& g, uint64_t p,
     o.X = extract_kmer<W>(g.codes, p, kp.k);
     o.Y = revcomp<W>(o.X, kp.k);
     o.fwd = kmer_less<W>(o.X, o.Y);
-    o.h = kmer_hash<W>(o.fwd ? o.X : o.Y, kp.seed);
+    o.h = kmer_hash<W>(kmer_select<W>(o.fwd, o.X, o.Y), kp.seed);
     return o;
 }
 
@@ -422,7 +422,7 @@ __global__ void k_get_id(GenomeView g, TableView J, KParams kp, Kmer<W> x, long 
     o.X = x;
     o.Y = revcomp<W>(x, kp.k);
     o.fwd = kmer_less<W>(o.X, o.Y);
-    o.h = kmer_hash<W>(o.fwd ? o.X : o.Y, kp.seed);
+    o.h = kmer_hash<W>(kmer_select<W>(o.fwd, o.X, o.Y), kp.seed);
     *out = lookup_id<W>(g, J, o, kp.k);
 }
 

@@ -428,6 +428,7 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
     if (rc) return rc;
     if (ov_total > bv.ov_cap) return -2;  // heavily skewed input: the caller redoes the round with k_fill / k_query
     s->used_binned = true;
+    s->st.bin_waves = (uint32_t)nwaves;
     return 0;
 }
 
