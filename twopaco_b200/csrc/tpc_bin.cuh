@@ -19,26 +19,23 @@ namespace tpc {
 constexpr int kBinHalf = 16;                       // positions per thread per staging round
 constexpr int kBinStage = kTileThreads * kBinHalf;  // 4096 records staged per round
 constexpr int kBinMaxBuckets = 256;
-constexpr int kBinNbShift = 26;                    // record word 1: sector-in-slice | nb << 26
+constexpr int kBinCodeShift = 25;                  // record word 1: sector-in-slice | occurrence code << 25
 constexpr size_t kBinSmemBytes = kBinMaxBuckets * 8 + kBinMaxBuckets * 4 * 2 + 8 * 4 + kBinStage * 4 * 3;
 
 struct BinView {
-    uint32_t* rec;                 // [bucket][3][cap] : mask | word1 | relative position
+    uint32_t* rec;                 // [bucket][3][cap] : mask seed | word1 | relative position
     unsigned long long* count;     // [buckets] records reserved (may exceed cap)
-    uint32_t* ov;                  // overflow records {mask, word1, relpos, bucket}
+    uint32_t* ov;                  // overflow records {mask seed, word1, relpos, bucket}
     unsigned long long* ov_count;
     uint64_t cap, ov_cap;
     uint32_t bucket_bits;          // log2(#slices)
-    uint32_t sib_bits;             // log2(sectors per slice)
+    uint32_t sib_bits;             // log2(sectors per slice) <= 25
+    uint32_t q;                    // Bloom bits per edge (the apply kernels expand the mask seed)
 };
 
-__device__ __forceinline__ uint32_t encode_neigh(const Neigh& nb) {
-    return nb.a | (nb.a_n ? 4u : 0u) | (nb.b << 3) | (nb.b_n ? 32u : 0u);
-}
-__device__ __forceinline__ Neigh decode_neigh(uint32_t c) {
-    Neigh nb;
-    nb.a = c & 3u; nb.a_n = (c & 4u) != 0; nb.b = (c >> 3) & 3u; nb.b_n = (c & 32u) != 0;
-    return nb;
+// occurrence code (7 bits): prev base | prev is N << 2 | next base << 3 | next is N << 5 | forward strand is canonical << 6
+__device__ __forceinline__ Neigh decode_occurrence(uint32_t c) {
+    return orient((c >> 6) & 1u, c & 3u, (c >> 3) & 3u, (c >> 2) & 1u, (c >> 5) & 1u);
 }
 
 template <int W, int Q>
@@ -63,27 +60,30 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
 #pragma unroll
         for (int j = 0; j < W; ++j) { win.X.w[j] = 0; win.Y.w[j] = 0; }
         if (w * 32 < g.npos) win.load(g, w, kp.k);
-        uint64_t nf = win.next_feed, pf = win.prev_feed;
-#pragma unroll 1
+        const bool any_n = (win.prev_n | win.next_n) != 0;
+        const uint32_t relbase = (uint32_t)(w * 32 - wave_base);
+#pragma unroll
         for (int half = 0; half < 2; ++half) {
             hist[tid] = 0;
             __syncthreads();
+            const uint32_t nf32 = half ? (uint32_t)(win.next_feed >> 32) : (uint32_t)win.next_feed;
+            const uint32_t pf32 = half ? (uint32_t)(win.prev_feed >> 32) : (uint32_t)win.prev_feed;
             uint32_t rm[kBinHalf], rw[kBinHalf], rk[kBinHalf];
 #pragma unroll
             for (int j = 0; j < kBinHalf; ++j) {
-                int i = half * kBinHalf + j;
-                uint32_t nxt = (uint32_t)nf & 3u, prv = (uint32_t)pf & 3u;
-                nf >>= 2; pf >>= 2;
+                const int i = half * kBinHalf + j;
+                const uint32_t nxt = (nf32 >> (2 * j)) & 3u, prv = (pf32 >> (2 * j)) & 3u;
                 rk[j] = ~0u; rm[j] = 0; rw[j] = 0;
-                if ((win.valid >> i) & 1u) {
-                    bool fwd = kmer_less<W>(win.X, win.Y);
-                    uint64_t h = kmer_hash<W>(kmer_select<W>(fwd, win.X, win.Y), kp.seed);
+                if (win.valid & (1u << i)) {
+                    const bool fwd = kmer_less<W>(win.X, win.Y);
+                    const uint64_t h = kmer_hash<W>(kmer_select<W>(fwd, win.X, win.Y), kp.seed);
                     if (kp.nparts == 1 || hash_part(h, kp.nparts) == kp.part) {
-                        Neigh nb = orient(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
-                        uint64_t s = hash_sector(h, kp.sector_shift);
-                        uint32_t bucket = (uint32_t)(s >> bin.sib_bits);
-                        rm[j] = vertex_mask<Q>(h);
-                        rw[j] = ((uint32_t)s & sib_mask) | (encode_neigh(nb) << kBinNbShift);
+                        const uint64_t s = hash_sector(h, kp.sector_shift);
+                        uint32_t code = prv | (nxt << 3) | (fwd ? 64u : 0u);
+                        if (any_n) code |= (((win.prev_n >> i) & 1u) << 2) | (((win.next_n >> i) & 1u) << 5);
+                        rm[j] = mask_seed(h);
+                        rw[j] = ((uint32_t)s & sib_mask) | (code << kBinCodeShift);
+                        const uint32_t bucket = (uint32_t)(s >> bin.sib_bits);
                         rk[j] = (bucket << 16) | atomicAdd(&hist[bucket], 1u);
                     }
                 }
@@ -110,7 +110,7 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
                     uint32_t idx = pref[rk[j] >> 16] + (rk[j] & 0xFFFFu);
                     st_a[idx] = rm[j];
                     st_b[idx] = rw[j];
-                    st_c[idx] = (uint32_t)(w * 32 + half * kBinHalf + j - wave_base);
+                    st_c[idx] = relbase + half * kBinHalf + j;
                 }
             }
             __syncthreads();

@@ -216,9 +216,12 @@ __device__ __forceinline__ uint64_t hash_slot(uint64_t h, uint32_t log2cap) {
 // of the 8 edge-slot words of the vertex's sector (word c = in-edge with base c, word 4+c =
 // out-edge with base c, canonical orientation): each word is an independent Bloom filter over
 // the vertices that have that edge, so sharing the mask between words costs nothing.
+__device__ __forceinline__ uint32_t mask_seed(uint64_t h) {  // 32 hash bits the Bloom mask derives from
+    return (uint32_t)h ^ ((uint32_t)(h >> 32) * 0x85EBCA77u);
+}
 template <int Q>
-__device__ __forceinline__ uint32_t vertex_mask(uint64_t h) {
-    uint32_t g = fmix32((uint32_t)h ^ ((uint32_t)(h >> 32) * 0x85EBCA77u));
+__device__ __forceinline__ uint32_t mask_from_seed(uint32_t seed32) {
+    uint32_t g = fmix32(seed32);
     uint32_t m = 0;
 #pragma unroll
     for (int t = 0; t < Q; ++t) {
@@ -226,6 +229,19 @@ __device__ __forceinline__ uint32_t vertex_mask(uint64_t h) {
         m |= 1u << ((g >> (5 * (t % 6))) & 31u);
     }
     return m;
+}
+__device__ __forceinline__ uint32_t mask_from_seed_rt(uint32_t seed32, uint32_t q) {  // same bits, run-time q
+    uint32_t g = fmix32(seed32);
+    uint32_t m = 0;
+    for (uint32_t t = 0; t < q; ++t) {
+        if (t == 6) g = g * 0x9E3779B1u + 0x7F4A7C15u, g ^= g >> 15;
+        m |= 1u << ((g >> (5 * (t % 6))) & 31u);
+    }
+    return m;
+}
+template <int Q>
+__device__ __forceinline__ uint32_t vertex_mask(uint64_t h) {
+    return mask_from_seed<Q>(mask_seed(h));
 }
 
 // ---- per-thread window over 32 consecutive positions ------------------------------------
@@ -292,6 +308,32 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint32_t* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
+}
+
+// One whole 32-byte filter sector with ONE 256-bit load (sm_100: LDG.E.256): a random sector per
+// lane costs one L1 tag cycle per lane and instruction, so halving the instructions doubles the
+// rate the L2-resident apply kernels can sustain.
+struct Sector {
+    uint32_t w[8];
+};
+__device__ __forceinline__ Sector ld_sector_nc(const uint32_t* p) {  // read-only data (query pass)
+    Sector r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ Sector ld_sector_cg(const uint32_t* p) {  // data being updated by atomics (fill pass)
+    Sector r;
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p) : "memory");
+    return r;
+}
+// word c (0..3) of a half sector without dynamic register indexing
+__device__ __forceinline__ uint32_t pick4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t c) {
+    uint32_t lo = (c & 1u) ? w1 : w0, hi = (c & 1u) ? w3 : w2;
+    return (c & 2u) ? hi : lo;
 }
 
 // block-wide sum of a 64-bit value (all threads must call); result valid in thread 0

@@ -45,8 +45,7 @@ __device__ __forceinline__ void hll_add(uint32_t* __restrict__ hll, uint32_t ver
 // ------------------------------------------------------------------------------------------
 // pass 1a: fill
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t filter_set(uint32_t* word, uint32_t m) {
-    uint32_t cur = __ldcg(word);
+__device__ __forceinline__ uint32_t filter_set(uint32_t* word, uint32_t cur, uint32_t m) {
     if ((cur & m) != m) {
         atomicOr(word, m);
         return 1;
@@ -54,30 +53,28 @@ __device__ __forceinline__ uint32_t filter_set(uint32_t* word, uint32_t m) {
     return 0;
 }
 
-// Record the in-edge and the out-edge of one occurrence in the vertex's sector.  An 'N'
-// neighbour is unique: make every occurrence of this k-mer a candidate by recording two
-// distinct dummy edges (h:1044-1058).
+// Record the in-edge and the out-edge of one occurrence in the vertex's sector (one 256-bit load,
+// test, then atomicOr only on the words that miss bits).  An 'N' neighbour is unique: make every
+// occurrence of this k-mer a candidate by recording two distinct dummy edges (h:1044-1058).
 __device__ __forceinline__ uint32_t fill_vertex(uint32_t* sec, uint32_t m, const Neigh& nb) {
+    Sector s = ld_sector_cg(sec);
     uint32_t fresh = 0;
-    if (!nb.a_n) fresh += filter_set(sec + nb.a, m);
-    else { fresh += filter_set(sec + 0, m); fresh += filter_set(sec + 3, m); }
-    if (!nb.b_n) fresh += filter_set(sec + 4 + nb.b, m);
-    else { fresh += filter_set(sec + 4, m); fresh += filter_set(sec + 7, m); }
+    if (!nb.a_n) fresh += filter_set(sec + nb.a, pick4(s.w[0], s.w[1], s.w[2], s.w[3], nb.a), m);
+    else { fresh += filter_set(sec + 0, s.w[0], m); fresh += filter_set(sec + 3, s.w[3], m); }
+    if (!nb.b_n) fresh += filter_set(sec + 4 + nb.b, pick4(s.w[4], s.w[5], s.w[6], s.w[7], nb.b), m);
+    else { fresh += filter_set(sec + 4, s.w[4], m); fresh += filter_set(sec + 7, s.w[7], m); }
     return fresh;
 }
 
 // All 8 edge queries of one k-mer from its sector (h:640-660): the edge actually present at
 // this occurrence counts once; any other edge recorded in the filter counts too.
 __device__ __forceinline__ bool query_vertex(const uint32_t* sec, uint32_t m, const Neigh& nb) {
-    uint4 sin = ld_nc_v4(sec);
-    uint4 sout = ld_nc_v4(sec + 4);
-    uint32_t si[4] = {sin.x, sin.y, sin.z, sin.w};
-    uint32_t so[4] = {sout.x, sout.y, sout.z, sout.w};
+    Sector s = ld_sector_nc(sec);
     uint32_t in_cnt = nb.a_n ? 2u : 0u, out_cnt = nb.b_n ? 2u : 0u;
 #pragma unroll
     for (uint32_t c = 0; c < 4; ++c) {
-        in_cnt += (c == nb.a || (si[c] & m) == m) ? 1u : 0u;
-        out_cnt += (c == nb.b || (so[c] & m) == m) ? 1u : 0u;
+        in_cnt += (c == nb.a || (s.w[c] & m) == m) ? 1u : 0u;
+        out_cnt += (c == nb.b || (s.w[4 + c] & m) == m) ? 1u : 0u;
     }
     return in_cnt > 1 || out_cnt > 1;
 }

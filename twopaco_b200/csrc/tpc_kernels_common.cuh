@@ -98,8 +98,8 @@ k_probe(uint32_t* __restrict__ table, uint32_t sector_bits, uint32_t mode, uint6
         uint64_t h = fmix64(x);
         uint32_t* sec = table + ((h >> (64 - sector_bits)) << 3);
         if (mode == 0) {
-            uint4 a = ld_nc_v4(sec), b = ld_nc_v4(sec + 4);
-            acc += a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w;
+            Sector v = ld_sector_nc(sec);
+            acc += v.w[0] ^ v.w[1] ^ v.w[2] ^ v.w[3] ^ v.w[4] ^ v.w[5] ^ v.w[6] ^ v.w[7];
         } else if (mode == 1) {
             atomicOr(sec + (h & 7), 1u << ((h >> 3) & 31));
         } else {
@@ -115,15 +115,16 @@ k_probe(uint32_t* __restrict__ table, uint32_t sector_bits, uint32_t mode, uint6
 // ---- apply: one launch per slice; the slice stays in L2 ------------------------------------------
 __global__ void __launch_bounds__(256)
 k_apply_fill(uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, const unsigned long long* __restrict__ count,
-             uint64_t cap, uint32_t sib_mask, Counters* ctr) {
+             uint64_t cap, uint32_t sib_mask, uint32_t q, Counters* ctr) {
     __shared__ unsigned long long red[8];
-    unsigned long long n = *count;
-    if (n > cap) n = cap;
+    unsigned long long n64 = *count;
+    const uint32_t n = (uint32_t)(n64 > cap ? cap : n64);
+    const uint32_t* __restrict__ rec_b = rec + cap;
     unsigned long long fresh = 0;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        uint32_t m = __ldcs(rec + i), w1 = __ldcs(rec + cap + i);
-        fresh += fill_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), m, decode_neigh(w1 >> kBinNbShift));
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t seed = __ldcs(rec + i), w1 = __ldcs(rec_b + i);
+        fresh += fill_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), mask_from_seed_rt(seed, q),
+                             decode_occurrence(w1 >> kBinCodeShift));
     }
     unsigned long long t = block_sum(fresh, red);
     if (threadIdx.x == 0 && t) atomicAdd(&ctr->filter_new, t);
@@ -131,18 +132,20 @@ k_apply_fill(uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, con
 
 __global__ void __launch_bounds__(256)
 k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, const unsigned long long* __restrict__ count,
-              uint64_t cap, uint32_t sib_mask, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr,
+              uint64_t cap, uint32_t sib_mask, uint32_t q, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr,
               uint32_t* __restrict__ hll, uint64_t slice_first_sector) {
     __shared__ unsigned long long red[8];
-    unsigned long long n = *count;
-    if (n > cap) n = cap;
+    unsigned long long n64 = *count;
+    const uint32_t n = (uint32_t)(n64 > cap ? cap : n64);
+    const uint32_t* __restrict__ rec_b = rec + cap;
+    const uint32_t* __restrict__ rec_c = rec + 2 * cap;
     unsigned long long marks = 0;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        uint32_t m = __ldcs(rec + i), w1 = __ldcs(rec + cap + i);
-        if (query_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), m, decode_neigh(w1 >> kBinNbShift))) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t seed = __ldcs(rec + i), w1 = __ldcs(rec_b + i);
+        uint32_t m = mask_from_seed_rt(seed, q);
+        if (query_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), m, decode_occurrence(w1 >> kBinCodeShift))) {
             hll_add(hll, m, slice_first_sector | (w1 & sib_mask));
-            uint64_t p = wave_base + __ldcs(rec + 2 * cap + i);
+            uint64_t p = wave_base + __ldcs(rec_c + i);
             atomicOr(mask + (p >> 5), 1u << (p & 31));
             ++marks;
         }
@@ -154,8 +157,8 @@ k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ r
 // records that did not fit their slice's array (skewed inputs): direct random access
 __global__ void __launch_bounds__(256)
 k_apply_overflow(uint32_t* __restrict__ filter, const uint32_t* __restrict__ ov, const unsigned long long* __restrict__ ov_count,
-                 uint64_t ov_cap, uint32_t sib_bits, int do_query, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr,
-                 uint32_t* __restrict__ hll) {
+                 uint64_t ov_cap, uint32_t sib_bits, uint32_t q, int do_query, uint32_t* __restrict__ mask, uint64_t wave_base,
+                 Counters* ctr, uint32_t* __restrict__ hll) {
     __shared__ unsigned long long red[8];
     unsigned long long n = *ov_count;
     if (n > ov_cap) n = ov_cap;
@@ -165,10 +168,11 @@ k_apply_overflow(uint32_t* __restrict__ filter, const uint32_t* __restrict__ ov,
          i += (unsigned long long)gridDim.x * blockDim.x) {
         uint4 r = reinterpret_cast<const uint4*>(ov)[i];
         uint32_t* sec = filter + ((((uint64_t)r.w << sib_bits) | (r.y & sib_mask)) << 3);
-        Neigh nb = decode_neigh(r.y >> kBinNbShift);
-        if (!do_query) acc += fill_vertex(sec, r.x, nb);
-        else if (query_vertex(sec, r.x, nb)) {
-            hll_add(hll, r.x, ((uint64_t)r.w << sib_bits) | (r.y & sib_mask));
+        Neigh nb = decode_occurrence(r.y >> kBinCodeShift);
+        uint32_t m = mask_from_seed_rt(r.x, q);
+        if (!do_query) acc += fill_vertex(sec, m, nb);
+        else if (query_vertex(sec, m, nb)) {
+            hll_add(hll, m, ((uint64_t)r.w << sib_bits) | (r.y & sib_mask));
             uint64_t p = wave_base + r.z;
             atomicOr(mask + (p >> 5), 1u << (p & 31));
             ++acc;

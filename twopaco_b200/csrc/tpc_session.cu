@@ -118,7 +118,7 @@ static int apply_grid(const LaunchCtx& c) { return c.sm_count * 8; }
 cudaError_t launch_apply_fill(const LaunchCtx& c, uint32_t* filter, const BinView& bv, uint32_t bucket, Counters* ctr) {
     uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
     k_apply_fill<<<apply_grid(c), 256, 0, c.stream>>>(slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap,
-                                                      (1u << bv.sib_bits) - 1u, ctr);
+                                                      (1u << bv.sib_bits) - 1u, bv.q, ctr);
     ++*c.launches;
     return cudaGetLastError();
 }
@@ -127,14 +127,14 @@ cudaError_t launch_apply_query(const LaunchCtx& c, const uint32_t* filter, const
                                uint64_t wave_base, Counters* ctr, uint32_t* hll) {
     const uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
     k_apply_query<<<apply_grid(c), 256, 0, c.stream>>>(slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap,
-                                                       (1u << bv.sib_bits) - 1u, mask, wave_base, ctr, hll, (uint64_t)bucket << bv.sib_bits);
+                                                       (1u << bv.sib_bits) - 1u, bv.q, mask, wave_base, ctr, hll, (uint64_t)bucket << bv.sib_bits);
     ++*c.launches;
     return cudaGetLastError();
 }
 
 cudaError_t launch_apply_overflow(const LaunchCtx& c, uint32_t* filter, const BinView& bv, int do_query, uint32_t* mask,
                                   uint64_t wave_base, Counters* ctr, uint32_t* hll) {
-    k_apply_overflow<<<c.sm_count, 256, 0, c.stream>>>(filter, bv.ov, bv.ov_count, bv.ov_cap, bv.sib_bits, do_query, mask,
+    k_apply_overflow<<<c.sm_count, 256, 0, c.stream>>>(filter, bv.ov, bv.ov_count, bv.ov_cap, bv.sib_bits, bv.q, do_query, mask,
                                                        wave_base, ctr, hll);
     ++*c.launches;
     return cudaGetLastError();
@@ -371,6 +371,8 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
     BinView bv{};
     bv.bucket_bits = (uint32_t)bb;
     bv.sib_bits = s->filter_bits_eff - 8 - (uint32_t)bb;
+    if (bv.sib_bits > (uint32_t)kBinCodeShift) return -1;
+    bv.q = kp.q;
     const uint32_t buckets = 1u << bb;
     uint64_t budget = s->bin_budget_bytes ? s->bin_budget_bytes : (uint64_t)(available_bytes(s->device) * 0.7);
     // records of one wave must fit the budget: 12 B per record + 8 % slack per slice
