@@ -373,3 +373,15 @@ def test_multi_gpu_torchrun():
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("mgpu ok") == 6
+
+
+@pytest.mark.parametrize("name", ["family_k25", "selftest_s1_k9", "edge_mixed_k11", "family_k11_collisions"])
+def test_position_identified_slots_for_short_k(name, golden, monkeypatch):
+    """k <= 31 normally stores the packed k-mer inline in the table slots; the general
+    position-identified slot format (used for every k > 31) must give the same result."""
+    monkeypatch.setenv("TPC_INLINE_KEYS", "0")
+    spec, g = CASES[name], golden[name]
+    with case_files(spec) as (paths, _, _):
+        recs = api.read_fasta(paths)
+    img, st = api.junctions_host(api.pack_records(recs), k=spec["k"], filter_bits=spec.get("f", 24), q=spec.get("q", 5))
+    assert canon_md5(bytes(img)) == g["canon_md5"] and st.junctions == g["distinct_junctions"]

@@ -19,7 +19,7 @@ namespace tpc {
 constexpr int kBinHalf = 16;                       // positions per thread per staging round
 constexpr int kBinStage = kTileThreads * kBinHalf;  // 4096 records staged per round
 constexpr int kBinMaxBuckets = 256;
-constexpr int kBinCodeShift = 25;                  // record word 1: sector-in-slice | occurrence code << 25
+constexpr int kBinCodeShift = 25;                  // record word 1: sector-in-slice | position bits 32.. | occurrence code << 25
 constexpr size_t kBinSmemBytes = kBinMaxBuckets * 8 + kBinMaxBuckets * 4 * 2 + 8 * 4 + kBinStage * 4 * 3;
 
 struct BinView {
@@ -61,7 +61,9 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
         for (int j = 0; j < W; ++j) { win.X.w[j] = 0; win.Y.w[j] = 0; }
         if (w * 32 < g.npos) win.load(g, w, kp.k);
         const bool any_n = (win.prev_n | win.next_n) != 0;
-        const uint32_t relbase = (uint32_t)(w * 32 - wave_base);
+        const uint64_t rel64 = w * 32 - wave_base;  // position relative to the wave: low 32 bits in word 2,
+        const uint32_t relbase = (uint32_t)rel64;   // the bits above in the spare bits of word 1
+        const uint32_t relhigh = (uint32_t)(rel64 >> 32) << bin.sib_bits;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             hist[tid] = 0;
@@ -82,7 +84,7 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
                         uint32_t code = prv | (nxt << 3) | (fwd ? 64u : 0u);
                         if (any_n) code |= (((win.prev_n >> i) & 1u) << 2) | (((win.next_n >> i) & 1u) << 5);
                         rm[j] = mask_seed(h);
-                        rw[j] = ((uint32_t)s & sib_mask) | (code << kBinCodeShift);
+                        rw[j] = ((uint32_t)s & sib_mask) | relhigh | (code << kBinCodeShift);
                         const uint32_t bucket = (uint32_t)(s >> bin.sib_bits);
                         rk[j] = (bucket << 16) | atomicAdd(&hist[bucket], 1u);
                     }

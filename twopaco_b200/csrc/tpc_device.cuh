@@ -47,7 +47,12 @@ struct Slot {  // candidate table T and junction index J
 struct TableView {
     Slot* slots;
     uint32_t log2cap;
+    // Inline keys (k <= 31 only): the canonical k-mer (< 2^62) fits the slot, so lookups never
+    // touch the genome.  T slot = {key + 1, flags(0..11) | first position << 24}
+    //                    J slot = {key + 1 | first occurrence is on the canonical strand << 63, id}
+    uint32_t inline_keys;
 };
+constexpr int kInlinePosShift = 24;
 
 struct KParams {
     uint32_t k;

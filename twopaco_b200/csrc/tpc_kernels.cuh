@@ -204,34 +204,58 @@ k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t n
             if (kp.nparts > 1 && hash_part(o.h, kp.nparts) != kp.part) continue;  // marked in another round
             bool pn = load_n(g.nmask, p - 1), nn = load_n(g.nmask, p + kp.k);
             Neigh nb = orient(o.fwd, load_base(g.codes, p - 1), load_base(g.codes, p + kp.k), pn, nn);
-            unsigned long long mine = hash_tag(o.h) | p;
-            uint64_t idx = hash_slot(o.h, T.log2cap);
-            Slot* s = nullptr;
-            unsigned long long meta = 0;
-            for (uint64_t probe = 0; probe <= capmask; ++probe, idx = (idx + 1) & capmask) {
-                Slot* cand = T.slots + idx;
-                ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(cand));
-                unsigned long long rep = v.x;
-                if (rep == 0) {
-                    rep = atomicCAS(&cand->rep, 0ull, mine);
-                    if (rep == 0) { s = cand; ++claimed; break; }
-                    v.y = 0;
-                }
-                if ((rep >> kPosBits) == (mine >> kPosBits) && match_rep<W>(g, rep, o, kp.k)) {
-                    s = cand; meta = v.y;
-                    if (mine < rep) atomicMin(&cand->rep, mine);  // keep the first occurrence
-                    break;
-                }
-            }
-            if (!s) { atomicAdd(&ctr->overflow, 1ull); continue; }
             // neighbour sets in canonical orientation (candidateoccurence.h:25-50; h:778-796)
             unsigned long long want = 0;
             if (!nb.a_n) want |= 1ull << nb.a;
             if (!nb.b_n) want |= 16ull << nb.b;
-            if ((meta & want) != want) atomicOr(&s->meta, want);
+            uint64_t idx = hash_slot(o.h, T.log2cap);
+            Slot* s = nullptr;
+            unsigned long long meta = 0;
+            if (W == 1 && T.inline_keys) {
+                const unsigned long long key1 = (o.fwd ? o.X.w[0] : o.Y.w[0]) + 1ull;
+                const unsigned long long fresh_meta = want | ((unsigned long long)p << kInlinePosShift);
+                for (uint64_t probe = 0; probe <= capmask; ++probe, idx = (idx + 1) & capmask) {
+                    Slot* cand = T.slots + idx;
+                    ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(cand));
+                    if (v.x == 0) {
+                        v.x = atomicCAS(&cand->rep, 0ull, key1);
+                        if (v.x == 0) { s = cand; ++claimed; v.x = key1; v.y = 0; }
+                    }
+                    if (v.x == key1) { s = cand; meta = v.y; break; }
+                }
+                if (!s) { atomicAdd(&ctr->overflow, 1ull); continue; }
+                // flags by OR, first position by a CAS-min on the high bits (0 = not yet set)
+                if ((meta & want) != want) meta = atomicOr(&s->meta, want) | want;
+                while ((meta >> kInlinePosShift) == 0 || (meta >> kInlinePosShift) > p) {
+                    unsigned long long neu = (meta & ((1ull << kInlinePosShift) - 1)) | ((unsigned long long)p << kInlinePosShift);
+                    unsigned long long old = atomicCAS(&s->meta, meta, neu);
+                    if (old == meta) break;
+                    meta = old;
+                }
+                (void)fresh_meta;
+            } else {
+                unsigned long long mine = hash_tag(o.h) | p;
+                for (uint64_t probe = 0; probe <= capmask; ++probe, idx = (idx + 1) & capmask) {
+                    Slot* cand = T.slots + idx;
+                    ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(cand));
+                    unsigned long long rep = v.x;
+                    if (rep == 0) {
+                        rep = atomicCAS(&cand->rep, 0ull, mine);
+                        if (rep == 0) { s = cand; ++claimed; break; }
+                        v.y = 0;
+                    }
+                    if ((rep >> kPosBits) == (mine >> kPosBits) && match_rep<W>(g, rep, o, kp.k)) {
+                        s = cand; meta = v.y;
+                        if (mine < rep) atomicMin(&cand->rep, mine);  // keep the first occurrence
+                        break;
+                    }
+                }
+                if (!s) { atomicAdd(&ctr->overflow, 1ull); continue; }
+                if ((meta & want) != want) atomicOr(&s->meta, want);
+                if (kp.count_occurrences) atomicAdd(&s->meta, 1ull << kMetaCountShift);
+            }
             if (nb.a_n) { if (atomicOr(&s->meta, kMetaInN1) & kMetaInN1) atomicOr(&s->meta, kMetaInN2); }
             if (nb.b_n) { if (atomicOr(&s->meta, kMetaOutN1) & kMetaOutN1) atomicOr(&s->meta, kMetaOutN2); }
-            if (kp.count_occurrences) atomicAdd(&s->meta, 1ull << kMetaCountShift);
         }
     }
     if (claimed) atomicAdd(&ctr->distinct, claimed);
@@ -248,6 +272,7 @@ k_build_index(GenomeView g, const unsigned long long* __restrict__ sorted_pos, u
         uint64_t p = sorted_pos[i] & kPosMask;
         Occ<W> o = occurrence_at<W>(g, p, kp);
         unsigned long long mine = hash_tag(o.h) | p;
+        if (W == 1 && J.inline_keys) mine = ((o.fwd ? o.X.w[0] : o.Y.w[0]) + 1ull) | (o.fwd ? (1ull << 63) : 0ull);
         uint64_t idx = hash_slot(o.h, J.log2cap);
         for (;; idx = (idx + 1) & capmask) {
             if (atomicCAS(&J.slots[idx].rep, 0ull, mine) == 0ull) {
@@ -263,6 +288,14 @@ k_build_index(GenomeView g, const unsigned long long* __restrict__ sorted_pos, u
 template <int W>
 __device__ __forceinline__ long long lookup_id(const GenomeView& g, const TableView& J, const Occ<W>& o, uint32_t k) {
     const uint64_t capmask = (1ull << J.log2cap) - 1;
+    if (W == 1 && J.inline_keys) {
+        const unsigned long long key1 = (o.fwd ? o.X.w[0] : o.Y.w[0]) + 1ull;
+        for (uint64_t idx = hash_slot(o.h, J.log2cap);; idx = (idx + 1) & capmask) {
+            ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(J.slots + idx));
+            if (v.x == 0) return 0;
+            if ((v.x & ~(1ull << 63)) == key1) return ((v.x >> 63) != 0) == o.fwd ? (long long)v.y : -(long long)v.y;
+        }
+    }
     unsigned long long tag = hash_tag(o.h) >> kPosBits;
     for (uint64_t idx = hash_slot(o.h, J.log2cap);; idx = (idx + 1) & capmask) {
         ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(J.slots + idx));

@@ -33,7 +33,7 @@ k_classify(TableView T, uint64_t abundance, uint32_t use_abundance, unsigned lon
             if (lane == leader) base = atomicAdd(&ctr->junctions, (unsigned long long)__popc(ballot));
             base = __shfl_sync(act, base, leader);
             unsigned long long at = base + __popc(ballot & ((1u << lane) - 1));
-            if (at < out_cap) out[at] = v.x & kPosMask;
+            if (at < out_cap) out[at] = T.inline_keys ? (v.y >> kInlinePosShift) : (v.x & kPosMask);
         }
     }
 }
@@ -132,20 +132,21 @@ k_apply_fill(uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, con
 
 __global__ void __launch_bounds__(256)
 k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, const unsigned long long* __restrict__ count,
-              uint64_t cap, uint32_t sib_mask, uint32_t q, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr,
+              uint64_t cap, uint32_t sib_bits, uint32_t q, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr,
               uint32_t* __restrict__ hll, uint64_t slice_first_sector) {
     __shared__ unsigned long long red[8];
     unsigned long long n64 = *count;
     const uint32_t n = (uint32_t)(n64 > cap ? cap : n64);
     const uint32_t* __restrict__ rec_b = rec + cap;
     const uint32_t* __restrict__ rec_c = rec + 2 * cap;
+    const uint32_t sib_mask = (1u << sib_bits) - 1u;
     unsigned long long marks = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t seed = __ldcs(rec + i), w1 = __ldcs(rec_b + i);
         uint32_t m = mask_from_seed_rt(seed, q);
         if (query_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), m, decode_occurrence(w1 >> kBinCodeShift))) {
             hll_add(hll, m, slice_first_sector | (w1 & sib_mask));
-            uint64_t p = wave_base + __ldcs(rec_c + i);
+            uint64_t p = wave_base + (((uint64_t)((w1 & ((1u << kBinCodeShift) - 1u)) >> sib_bits)) << 32) + __ldcs(rec_c + i);
             atomicOr(mask + (p >> 5), 1u << (p & 31));
             ++marks;
         }
@@ -173,7 +174,7 @@ k_apply_overflow(uint32_t* __restrict__ filter, const uint32_t* __restrict__ ov,
         if (!do_query) acc += fill_vertex(sec, m, nb);
         else if (query_vertex(sec, m, nb)) {
             hll_add(hll, m, ((uint64_t)r.w << sib_bits) | (r.y & sib_mask));
-            uint64_t p = wave_base + r.z;
+            uint64_t p = wave_base + (((uint64_t)((r.y & ((1u << kBinCodeShift) - 1u)) >> sib_bits)) << 32) + r.z;
             atomicOr(mask + (p >> 5), 1u << (p & 31));
             ++acc;
         }

@@ -127,7 +127,7 @@ cudaError_t launch_apply_query(const LaunchCtx& c, const uint32_t* filter, const
                                uint64_t wave_base, Counters* ctr, uint32_t* hll) {
     const uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
     k_apply_query<<<apply_grid(c), 256, 0, c.stream>>>(slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap,
-                                                       (1u << bv.sib_bits) - 1u, bv.q, mask, wave_base, ctr, hll, (uint64_t)bucket << bv.sib_bits);
+                                                       bv.sib_bits, bv.q, mask, wave_base, ctr, hll, (uint64_t)bucket << bv.sib_bits);
     ++*c.launches;
     return cudaGetLastError();
 }
@@ -208,6 +208,8 @@ struct tpc_session {
     cudaEvent_t ev[10]{};
     uint32_t launches = 0;
 
+    bool allow_inline = true;      // env TPC_INLINE_KEYS=0 forces position-identified slots for every k
+    uint32_t inline_keys() const { return (allow_inline && W == 1 && prm.abundance == ~0ull) ? 1u : 0u; }
     LaunchCtx lctx() { return LaunchCtx{stream, sm_count, &launches}; }
     KParams kparams(uint32_t part) const {
         KParams kp{};
@@ -271,6 +273,7 @@ int tpc_session_create(const tpc_params* params, void* stream, tpc_session** out
     s->W = (int)((params->k + 31) / 32);
     s->filter_bits_eff = std::max<uint32_t>(params->filter_bits, 9u);
     if (const char* e = getenv("TPC_FILTER_MODE")) s->filter_mode = !strcmp(e, "direct") ? 1 : !strcmp(e, "binned") ? 2 : 0;
+    if (const char* e = getenv("TPC_INLINE_KEYS")) s->allow_inline = atoi(e) != 0;
     if (const char* e = getenv("TPC_SLICE_LOG2")) s->slice_log2 = std::min(31, std::max(8, atoi(e)));
     if (const char* e = getenv("TPC_BIN_BUFFER_MB")) s->bin_budget_bytes = (uint64_t)atoll(e) << 20;
     cudaGetDevice(&s->device);
@@ -377,7 +380,8 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
     uint64_t budget = s->bin_budget_bytes ? s->bin_budget_bytes : (uint64_t)(available_bytes(s->device) * 0.7);
     // records of one wave must fit the budget: 12 B per record + 8 % slack per slice
     uint64_t max_records = budget / 14;
-    uint64_t wave_pos = std::min<uint64_t>(s->ntiles * (uint64_t)kTilePos, (1ull << 32) - kTilePos);
+    // positions inside a wave are 32 + (25 - sib_bits) bits wide (tpc_bin.cuh record layout)
+    uint64_t wave_pos = std::min<uint64_t>(s->ntiles * (uint64_t)kTilePos, (1ull << (32 + kBinCodeShift - bv.sib_bits)) - kTilePos);
     if (max_records < wave_pos / kp.nparts) wave_pos = std::max<uint64_t>(max_records * kp.nparts, kTilePos);
     uint64_t wave_tiles = std::max<uint64_t>(wave_pos / kTilePos, 1);
     uint64_t nwaves = (s->ntiles + wave_tiles - 1) / wave_tiles;
@@ -496,7 +500,7 @@ int tpc_session_find_candidates(tpc_session* s) {
             }
             s->T_log2 = lg;
             CK(cudaMemsetAsync(s->d_T, 0, need, s->stream));
-            CK(W_DISPATCH(s, insert(lc, s->g, s->d_mask, kp, s->ntiles, TableView{s->d_T, lg}, s->d_ctr)));
+            CK(W_DISPATCH(s, insert(lc, s->g, s->d_mask, kp, s->ntiles, TableView{s->d_T, lg, s->inline_keys()}, s->d_ctr)));
             CK(cudaEventRecord(s->ev[3], s->stream));
             CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
             CK(cudaStreamSynchronize(s->stream));
@@ -508,7 +512,7 @@ int tpc_session_find_candidates(tpc_session* s) {
             cur = redo;
             ++lg;
         }
-        TableView T{s->d_T, s->T_log2};
+        TableView T{s->d_T, s->T_log2, s->inline_keys()};
         uint64_t distinct_r = cur.distinct - prev.distinct;
         if (s->local_count + distinct_r > s->local_cap) {
             uint64_t ncap = std::max<uint64_t>(s->local_count + distinct_r, 1024);
@@ -574,7 +578,7 @@ int tpc_session_set_junctions(tpc_session* s, const uint64_t* dev_words_all, uin
     s->J_log2 = std::max<uint32_t>(ceil_log2(n * 2 + 16), 6);
     CK(dev_alloc(&s->d_J, sizeof(Slot) << s->J_log2, s->stream));
     CK(cudaMemsetAsync(s->d_J, 0, sizeof(Slot) << s->J_log2, s->stream));
-    CK(W_DISPATCH(s, build_index(lc, s->g, s->d_sorted, n, s->kparams(0), TableView{s->d_J, s->J_log2})));
+    CK(W_DISPATCH(s, build_index(lc, s->g, s->d_sorted, n, s->kparams(0), TableView{s->d_J, s->J_log2, s->inline_keys()})));
     CK(cudaEventRecord(s->ev[6], s->stream));
     s->J_count = n;
     s->st.junctions = n;
@@ -613,7 +617,7 @@ int tpc_session_emit_count(tpc_session* s, uint64_t pos_begin, uint64_t pos_end,
     CK(cudaMemsetAsync(s->d_tile_rec + nt, 0, 8, s->stream));
     CK(cudaMemsetAsync(s->d_tile_stub + nt, 0, 8, s->stream));
     KParams kp = s->kparams(0);
-    TableView J{s->d_J, s->J_log2};
+    TableView J{s->d_J, s->J_log2, s->inline_keys()};
     CK(W_DISPATCH(s, ends(lc, s->g, s->rtable(), kp, J, s->d_stubmask, pos_begin, pos_end)));
     CK(W_DISPATCH(s, emit_count(lc, s->g, s->d_mask, s->d_stubmask, kp, J, tb, te, s->d_tile_rec, s->d_tile_stub)));
     CK(launch_scan_exclusive(lc, s->d_tile_rec, nt + 1, s->d_scan_scratch));
@@ -651,7 +655,7 @@ int tpc_session_emit_write(tpc_session* s, uint64_t records_before, uint64_t stu
     }
     if (((uintptr_t)dev_out) & 3) return set_error("output buffer must be 4-byte aligned");
     KParams kp = s->kparams(0);
-    TableView J{s->d_J, s->J_log2};
+    TableView J{s->d_J, s->J_log2, s->inline_keys()};
     CK(W_DISPATCH(s, emit_write(lc, s->g, s->d_mask, s->d_stubmask, kp, J, s->rtable(), s->slice_tile_begin, s->slice_tile_end,
                                 s->d_tile_rec, s->d_tile_stub, records_before, stubs_before, unit_base,
                                 s->J_count + TPC_STUB_ID_OFFSET, (uint32_t*)dev_out, units)));
@@ -680,7 +684,7 @@ int tpc_session_get_id(tpc_session* s, const char* kmer, int64_t* id) {
         words[j / 32] |= c << (2 * (j % 32));
     }
     LaunchCtx lc = s->lctx();
-    CK(W_DISPATCH(s, get_id(lc, s->g, TableView{s->d_J, s->J_log2}, s->kparams(0), words, s->d_id)));
+    CK(W_DISPATCH(s, get_id(lc, s->g, TableView{s->d_J, s->J_log2, s->inline_keys()}, s->kparams(0), words, s->d_id)));
     long long v = 0;
     CK(cudaMemcpyAsync(&v, s->d_id, 8, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
