@@ -40,6 +40,11 @@ WORKLOADS = {
     # configs[1]: 62 x 5 Mbp, p = 0.01, k = 25, -f 32
     "c2": dict(name="C2: 62 synthetic E. coli-like genomes (62x5 Mbp, 1% divergence), k=25 -f 32 -q 5",
                seed=0xEC01, genomes=62, records=1, length=5_000_000, p=0.01, k=25, f=32, q=5, sample_bp=400_000),
+    # configs[3]: the same 7-genome set at k = 63 / k = 127 (2 / 4 words per k-mer), -f 37
+    "c4k63": dict(name="C4: 7 synthetic human-sized genomes (7x24x129166667 bp, 0.1% divergence), k=63 -f 37 -q 5",
+                  seed=0x4855, genomes=7, records=24, length=129_166_667, p=0.001, k=63, f=37, q=5, sample_bp=3_000_000),
+    "c4k127": dict(name="C4: 7 synthetic human-sized genomes (7x24x129166667 bp, 0.1% divergence), k=127 -f 37 -q 5",
+                   seed=0x4855, genomes=7, records=24, length=129_166_667, p=0.001, k=127, f=37, q=5, sample_bp=3_000_000),
     "dev": dict(name="dev: 7x2x4 Mbp, 0.1% divergence, k=25 -f 30 -q 5",
                 seed=0xD0, genomes=7, records=2, length=4_000_000, p=0.001, k=25, f=30, q=5, sample_bp=500_000),
 }
