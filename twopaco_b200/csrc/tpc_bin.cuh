@@ -38,7 +38,7 @@ __device__ __forceinline__ Neigh decode_occurrence(uint32_t c) {
     return orient((c >> 6) & 1u, c & 3u, (c >> 3) & 3u, (c >> 2) & 1u, (c >> 5) & 1u);
 }
 
-template <int W, int Q>
+template <int W>
 __global__ void __launch_bounds__(kTileThreads, 2)
 k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_end, uint64_t wave_base) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -78,8 +78,9 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
                 rk[j] = ~0u; rm[j] = 0; rw[j] = 0;
                 if (win.valid & (1u << i)) {
                     const bool fwd = kmer_less<W>(win.X, win.Y);
-                    const uint64_t h = kmer_hash<W>(kmer_select<W>(fwd, win.X, win.Y), kp.seed);
-                    if (kp.nparts == 1 || hash_part(h, kp.nparts) == kp.part) {
+                    const Kmer<W> canon = kmer_select<W>(fwd, win.X, win.Y);
+                    if (kp.nparts == 1 || owner_part(owner_fold<W>(canon), kp.nparts) == kp.part) {
+                        const uint64_t h = kmer_hash<W>(canon, kp.seed);
                         const uint64_t s = hash_sector(h, kp.sector_shift);
                         uint32_t code = prv | (nxt << 3) | (fwd ? 64u : 0u);
                         if (any_n) code |= (((win.prev_n >> i) & 1u) << 2) | (((win.next_n >> i) & 1u) << 5);
@@ -124,6 +125,146 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
                 unsigned long long gb = gbase[b];
                 uint32_t* ra = bin.rec + (uint64_t)b * 3 * bin.cap;
                 for (uint32_t j = lane; j < n; j += 32) {
+                    unsigned long long dst = gb + j;
+                    if (dst < bin.cap) {
+                        __stcs(ra + dst, st_a[s0 + j]);
+                        __stcs(ra + bin.cap + dst, st_b[s0 + j]);
+                        __stcs(ra + 2 * bin.cap + dst, st_c[s0 + j]);
+                    } else {
+                        unsigned long long o = atomicAdd(bin.ov_count, 1ull);
+                        if (o < bin.ov_cap) {
+                            uint4 r = make_uint4(st_a[s0 + j], st_b[s0 + j], st_c[s0 + j], b);
+                            reinterpret_cast<uint4*>(bin.ov)[o] = r;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+
+// ---- sharded variant (nparts > 1): ownership is sparse (1/nparts of the positions), so the
+// per-position loop only decides ownership (cheap fold); owned positions are compacted into a
+// CTA-wide list and the expensive part (64-bit hash, record, counting sort) runs densely on it.
+constexpr int kBinListMax = kTilePos;
+constexpr size_t kBinShardedSmemBytes = kBinSmemBytes + kBinListMax * 2 + 16;
+
+template <int W>
+__global__ void __launch_bounds__(kTileThreads, 2)
+k_bin_sharded(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_end, uint64_t wave_base) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* gbase = reinterpret_cast<unsigned long long*>(smem_raw);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(gbase + kBinMaxBuckets);
+    uint32_t* pref = hist + kBinMaxBuckets;
+    uint32_t* warp_tot = pref + kBinMaxBuckets;
+    uint32_t* st_a = warp_tot + 8;
+    uint32_t* st_b = st_a + kBinStage;
+    uint32_t* st_c = st_b + kBinStage;
+    uint32_t* list_total = st_c + kBinStage;
+    uint16_t* list = reinterpret_cast<uint16_t*>(list_total + 4);
+    const uint32_t nbuckets = 1u << bin.bucket_bits;
+    const uint32_t sib_mask = (1u << bin.sib_bits) - 1u;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    for (uint64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+        // phase 1: which of my 32 positions does this shard own?
+        uint64_t w = tile * kTileThreads + tid;
+        uint32_t own = 0;
+        if (w * 32 < g.npos) {
+            Window<W> win;
+            win.load(g, w, kp.k);
+            if (win.valid) {
+                uint64_t nf = win.next_feed;
+#pragma unroll 4
+                for (int i = 0; i < 32; ++i) {
+                    uint32_t nxt = (uint32_t)nf & 3u;
+                    nf >>= 2;
+                    if ((win.valid >> i) & 1u) {
+                        bool fwd = kmer_less<W>(win.X, win.Y);
+                        uint32_t part = owner_part(owner_fold<W>(kmer_select<W>(fwd, win.X, win.Y)), kp.nparts);
+                        own |= (part == kp.part ? 1u : 0u) << i;
+                    }
+                    roll<W>(win.X, win.Y, nxt, kp.k);
+                }
+            }
+        }
+        // CTA-wide list of owned positions (tile-relative, in position order)
+        uint32_t cnt = __popc(own), incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        __syncthreads();  // previous tile's readers of list / warp_tot are done
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        uint32_t off = incl - cnt;
+        for (int j = 0; j < wid; ++j) off += warp_tot[j];
+        if (tid == kTileThreads - 1) *list_total = off + cnt;
+        while (own) {
+            int i = __ffs(own) - 1;
+            own &= own - 1;
+            list[off++] = (uint16_t)(tid * 32 + i);
+        }
+        __syncthreads();
+        const uint32_t total = *list_total;
+
+        // phase 2: dense processing of the list, kBinStage records per round
+        for (uint32_t c0 = 0; c0 < total; c0 += kBinStage) {
+            const uint32_t n = min((uint32_t)kBinStage, total - c0);
+            hist[tid] = 0;
+            __syncthreads();
+            uint32_t rm[kBinHalf], rw[kBinHalf], rk[kBinHalf];
+#pragma unroll
+            for (int j = 0; j < kBinHalf; ++j) {
+                const uint32_t e = tid + j * kTileThreads;
+                rk[j] = ~0u; rm[j] = 0; rw[j] = 0;
+                if (e < n) {
+                    const uint64_t p = tile * kTilePos + list[c0 + e];
+                    Occ<W> o = occurrence_at<W>(g, p, kp);
+                    uint32_t code = load_base(g.codes, p - 1) | (load_base(g.codes, p + kp.k) << 3) | (o.fwd ? 64u : 0u) |
+                                    (load_n(g.nmask, p - 1) << 2) | (load_n(g.nmask, p + kp.k) << 5);
+                    const uint64_t s = hash_sector(o.h, kp.sector_shift);
+                    const uint64_t rel64 = p - wave_base;
+                    rm[j] = mask_seed(o.h);
+                    rw[j] = ((uint32_t)s & sib_mask) | ((uint32_t)(rel64 >> 32) << bin.sib_bits) | (code << kBinCodeShift);
+                    const uint32_t bucket = (uint32_t)(s >> bin.sib_bits);
+                    rk[j] = (bucket << 16) | atomicAdd(&hist[bucket], 1u);
+                }
+            }
+            __syncthreads();
+            uint32_t hc = hist[tid], hincl = hc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, hincl, o);
+                if (lane >= o) hincl += v;
+            }
+            if (lane == 31) warp_tot[wid] = hincl;
+            __syncthreads();
+            uint32_t base = 0;
+            for (int j = 0; j < wid; ++j) base += warp_tot[j];
+            pref[tid] = base + hincl - hc;
+            if (hc) gbase[tid] = atomicAdd(&bin.count[tid], (unsigned long long)hc);
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < kBinHalf; ++j) {
+                if (rk[j] != ~0u) {
+                    uint32_t idx = pref[rk[j] >> 16] + (rk[j] & 0xFFFFu);
+                    st_a[idx] = rm[j];
+                    st_b[idx] = rw[j];
+                    st_c[idx] = (uint32_t)(tile * kTilePos + list[c0 + tid + j * kTileThreads] - wave_base);
+                }
+            }
+            __syncthreads();
+            for (uint32_t b = wid; b < nbuckets; b += kTileThreads / 32) {
+                uint32_t nb = hist[b];
+                if (!nb) continue;
+                uint32_t s0 = pref[b];
+                unsigned long long gb = gbase[b];
+                uint32_t* ra = bin.rec + (uint64_t)b * 3 * bin.cap;
+                for (uint32_t j = lane; j < nb; j += 32) {
                     unsigned long long dst = gb + j;
                     if (dst < bin.cap) {
                         __stcs(ra + dst, st_a[s0 + j]);

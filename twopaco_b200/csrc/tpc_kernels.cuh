@@ -97,8 +97,9 @@ k_fill(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t ntiles,
             nf >>= 2; pf >>= 2;
             if ((win.valid >> i) & 1u) {
                 bool fwd = kmer_less<W>(win.X, win.Y);
-                uint64_t h = kmer_hash<W>(kmer_select<W>(fwd, win.X, win.Y), kp.seed);
-                if (kp.nparts == 1 || hash_part(h, kp.nparts) == kp.part) {
+                Kmer<W> canon = kmer_select<W>(fwd, win.X, win.Y);
+                if (kp.nparts == 1 || owner_part(owner_fold<W>(canon), kp.nparts) == kp.part) {
+                    uint64_t h = kmer_hash<W>(canon, kp.seed);
                     Neigh nb = orient(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
                     uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
                     fresh += fill_vertex(sec, vertex_mask<Q>(h), nb);
@@ -134,8 +135,9 @@ k_query(GenomeView g, const uint32_t* __restrict__ filter, KParams kp, uint64_t 
                 nf >>= 2; pf >>= 2;
                 if ((win.valid >> i) & 1u) {
                     bool fwd = kmer_less<W>(win.X, win.Y);
-                    uint64_t h = kmer_hash<W>(kmer_select<W>(fwd, win.X, win.Y), kp.seed);
-                    if (kp.nparts == 1 || hash_part(h, kp.nparts) == kp.part) {
+                    Kmer<W> canon = kmer_select<W>(fwd, win.X, win.Y);
+                    if (kp.nparts == 1 || owner_part(owner_fold<W>(canon), kp.nparts) == kp.part) {
+                        uint64_t h = kmer_hash<W>(canon, kp.seed);
                         Neigh nb = orient(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
                         const uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
                         uint32_t vm = vertex_mask<Q>(h);
@@ -164,7 +166,8 @@ template <int W>
 struct Occ {
     Kmer<W> X, Y;
     uint64_t h;
-    bool fwd;  // X is the canonical strand
+    uint32_t fold;  // owner_fold of the canonical k-mer
+    bool fwd;       // X is the canonical strand
 };
 
 template <int W>
@@ -173,7 +176,9 @@ __device__ __forceinline__ Occ<W> occurrence_at(const GenomeView& g, uint64_t p,
     o.X = extract_kmer<W>(g.codes, p, kp.k);
     o.Y = revcomp<W>(o.X, kp.k);
     o.fwd = kmer_less<W>(o.X, o.Y);
-    o.h = kmer_hash<W>(kmer_select<W>(o.fwd, o.X, o.Y), kp.seed);
+    Kmer<W> canon = kmer_select<W>(o.fwd, o.X, o.Y);
+    o.fold = owner_fold<W>(canon);
+    o.h = kmer_hash<W>(canon, kp.seed);
     return o;
 }
 
@@ -201,7 +206,7 @@ k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t n
             m &= m - 1;
             uint64_t p = w * 32 + i;
             Occ<W> o = occurrence_at<W>(g, p, kp);
-            if (kp.nparts > 1 && hash_part(o.h, kp.nparts) != kp.part) continue;  // marked in another round
+            if (kp.nparts > 1 && owner_part(o.fold, kp.nparts) != kp.part) continue;  // marked in another round
             bool pn = load_n(g.nmask, p - 1), nn = load_n(g.nmask, p + kp.k);
             Neigh nb = orient(o.fwd, load_base(g.codes, p - 1), load_base(g.codes, p + kp.k), pn, nn);
             // neighbour sets in canonical orientation (candidateoccurence.h:25-50; h:778-796)
@@ -452,6 +457,7 @@ __global__ void k_get_id(GenomeView g, TableView J, KParams kp, Kmer<W> x, long 
     o.X = x;
     o.Y = revcomp<W>(x, kp.k);
     o.fwd = kmer_less<W>(o.X, o.Y);
+    o.fold = 0;
     o.h = kmer_hash<W>(kmer_select<W>(o.fwd, o.X, o.Y), kp.seed);
     *out = lookup_id<W>(g, J, o, kp.k);
 }

@@ -55,18 +55,21 @@ template <int W>
 cudaError_t Launch<W>::bin(const LaunchCtx& c, GenomeView g, KParams kp, const BinView& bv, uint64_t tile_begin, uint64_t tile_end,
                            uint64_t wave_base) {
     if (tile_end <= tile_begin) return cudaSuccess;
-    TPC_Q_SWITCH(kp.q, {
-        static bool configured = false;
-        if (!configured) {
-            cudaFuncSetAttribute(k_bin<W, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinSmemBytes);
-            configured = true;
-        }
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin<W, Q>, kTileThreads, kBinSmemBytes);
-        uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count;
-        if (grid > tile_end - tile_begin) grid = tile_end - tile_begin;
-        k_bin<W, Q><<<(int)grid, kTileThreads, kBinSmemBytes, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base);
-    });
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_bin<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinSmemBytes);
+        cudaFuncSetAttribute(k_bin_sharded<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinShardedSmemBytes);
+        configured = true;
+    }
+    const bool sharded = kp.nparts > 1;
+    const size_t smem = sharded ? kBinShardedSmemBytes : kBinSmemBytes;
+    int per_sm = 0;
+    if (sharded) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_sharded<W>, kTileThreads, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin<W>, kTileThreads, smem);
+    uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count;
+    if (grid > tile_end - tile_begin) grid = tile_end - tile_begin;
+    if (sharded) k_bin_sharded<W><<<(int)grid, kTileThreads, smem, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base);
+    else k_bin<W><<<(int)grid, kTileThreads, smem, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base);
     ++*c.launches;
     return cudaGetLastError();
 }
