@@ -157,6 +157,8 @@ def main() -> None:
     ap.add_argument("--workload", default=os.environ.get("TPC_BENCH_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sim-world", type=int, default=0,
+                    help="kernel tuning aid: time only pass 1+2 of shard 0 of N on ONE GPU (not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -179,6 +181,18 @@ def main() -> None:
     total_bp = wl["genomes"] * wl["records"] * wl["length"]
     dg = api.synth_family_device(wl["seed"], wl["genomes"], wl["records"], wl["length"], wl["p"], keep_ascii=(rank == 0))
     total_bp = dg.total_bp
+
+    if args.sim_world:
+        for i in range(args.warmup + args.steps):
+            s = api.Session(k=wl["k"], filter_bits=wl["f"], q=wl["q"], shard_index=0, shard_count=args.sim_world)
+            dg.attach(s)
+            s.find_candidates()
+            st = s.stats()
+            s.close()
+        print(json.dumps({"sim_world": args.sim_world, "workload": args.workload,
+                          "stages_ms": {k: round(getattr(st, k), 3) for k in ("ms_bin", "ms_fill", "ms_query", "ms_insert", "ms_classify")},
+                          "bin_waves": st.bin_waves, "marks": st.candidate_marks, "candidate_kmers": st.candidate_kmers}))
+        return
 
     runner = Runner(wl, dg, rank, world)
 

@@ -377,18 +377,31 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
     if (bv.sib_bits > (uint32_t)kBinCodeShift) return -1;
     bv.q = kp.q;
     const uint32_t buckets = 1u << bb;
-    uint64_t budget = s->bin_budget_bytes ? s->bin_budget_bytes : (uint64_t)(available_bytes(s->device) * 0.7);
-    // records of one wave must fit the budget: 12 B per record + 8 % slack per slice
-    uint64_t max_records = budget / 14;
-    // positions inside a wave are 32 + (25 - sib_bits) bits wide (tpc_bin.cuh record layout)
-    uint64_t wave_pos = std::min<uint64_t>(s->ntiles * (uint64_t)kTilePos, (1ull << (32 + kBinCodeShift - bv.sib_bits)) - kTilePos);
-    if (max_records < wave_pos / kp.nparts) wave_pos = std::max<uint64_t>(max_records * kp.nparts, kTilePos);
-    uint64_t wave_tiles = std::max<uint64_t>(wave_pos / kTilePos, 1);
-    uint64_t nwaves = (s->ntiles + wave_tiles - 1) / wave_tiles;
-    uint64_t est = wave_tiles * kTilePos / kp.nparts;
-    bv.cap = ((uint64_t)(est / buckets * 1.08) + 8192 + 31) / 32 * 32;
-    bv.ov_cap = std::max<uint64_t>(1 << 16, est / 64);
-    CK(dev_alloc(&s->d_bin_rec, (uint64_t)buckets * 3 * bv.cap * 4, s->stream));
+    uint64_t budget = s->bin_budget_bytes ? s->bin_budget_bytes : (uint64_t)(available_bytes(s->device) * 0.92);
+    uint64_t wave_tiles = 0, nwaves = 0;
+    for (int attempt = 0;; ++attempt) {
+        // records of one wave must fit the budget: 12 B per record + 8 % slack per slice + overflow area
+        uint64_t max_records = budget / 14;
+        // positions inside a wave are 32 + (25 - sib_bits) bits wide (tpc_bin.cuh record layout)
+        uint64_t wave_pos = std::min<uint64_t>(s->ntiles * (uint64_t)kTilePos, (1ull << (32 + kBinCodeShift - bv.sib_bits)) - kTilePos);
+        if (max_records < wave_pos / kp.nparts) wave_pos = std::max<uint64_t>(max_records * kp.nparts, kTilePos);
+        wave_tiles = std::max<uint64_t>(wave_pos / kTilePos, 1);
+        nwaves = (s->ntiles + wave_tiles - 1) / wave_tiles;
+        wave_tiles = (s->ntiles + nwaves - 1) / nwaves;  // equal waves
+        uint64_t est = wave_tiles * kTilePos / kp.nparts;
+        bv.cap = ((uint64_t)(est / buckets * 1.08) + 8192 + 31) / 32 * 32;
+        bv.ov_cap = std::max<uint64_t>(1 << 16, est / 64);
+        cudaError_t e = dev_alloc(&s->d_bin_rec, (uint64_t)buckets * 3 * bv.cap * 4, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e == cudaErrorMemoryAllocation && attempt < 4 && !s->bin_budget_bytes) {
+            cudaGetLastError();  // not enough contiguous memory after all: smaller waves
+            s->d_bin_rec = nullptr;
+            budget = budget * 6 / 10;
+            continue;
+        }
+        CK(e);
+        break;
+    }
     CK(dev_alloc(&s->d_bin_count, (buckets + 1) * 8, s->stream));
     CK(dev_alloc(&s->d_bin_ov, bv.ov_cap * 16, s->stream));
     bv.rec = s->d_bin_rec; bv.count = s->d_bin_count; bv.ov_count = s->d_bin_count + buckets; bv.ov = s->d_bin_ov;
