@@ -145,15 +145,80 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
 }
 
 
-// ---- sharded variant (nparts > 1): ownership is sparse (1/nparts of the positions), so the
-// per-position loop only decides ownership (cheap fold); owned positions are compacted into a
-// CTA-wide list and the expensive part (64-bit hash, record, counting sort) runs densely on it.
+// ---- sharded variant (nparts > 1): ownership is sparse (1/nparts of the positions).
+// k_own decides ownership of EVERY position with as few instructions as possible (cheap fold of
+// the canonical k-mer, high occupancy) and writes 1 bit per position; k_bin_list compacts the
+// owned positions of a tile into a CTA-wide list and runs the expensive part (64-bit hash, record,
+// counting sort by slice) densely on it.
+template <int W>
+__global__ void __launch_bounds__(kTileThreads)
+k_own(GenomeView g, KParams kp, uint64_t word_begin, uint64_t word_end, uint32_t* __restrict__ own_mask) {
+    for (uint64_t w = word_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < word_end;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t own = 0;
+        if (w * 32 < g.npos) {
+            if (W == 1) {
+                // k <= 31: every k-mer of this thread lies inside two code words; extract both strands
+                // with constant shifts (no rolling dependency chain between positions)
+                const uint64_t c0 = __ldg(g.codes + w), c1 = __ldg(g.codes + w + 1);
+                const uint32_t k2 = 2 * kp.k;
+                const uint64_t kmask = (~0ull) >> (64 - k2);
+                // reverse complement of the 128-bit window, pre-shifted so that position i's reverse
+                // complement is the low 2k bits of (r >> (64 - 2i))
+                const uint64_t rh = pairrev64(~c0), rl = pairrev64(~c1);
+                const uint32_t s0 = 64 - k2;  // 2..62
+                const uint64_t r_lo = (rl >> s0) | (rh << (64 - s0)), r_hi = rh >> s0;
+                uint32_t valid = ~0u;
+                if (w == 0 || any_n(g.nmask, w * 32, 32 + kp.k)) {
+                    valid = 0;
+                    uint32_t run = 0;
+#pragma unroll 1
+                    for (uint32_t j = 0; j + 1 < kp.k; ++j) run = load_n(g.nmask, w * 32 + j) ? 0 : run + 1;
+#pragma unroll 1
+                    for (uint32_t i = 0; i < 32; ++i) {
+                        run = load_n(g.nmask, w * 32 + i + kp.k - 1) ? 0 : run + 1;
+                        if (run >= kp.k) valid |= 1u << i;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const uint64_t x = (i ? ((c0 >> (2 * i)) | (c1 << (64 - 2 * i))) : c0) & kmask;
+                    const uint64_t y = (i ? ((r_lo >> (64 - 2 * i)) | (r_hi << (2 * i))) : r_hi) & kmask;
+                    Kmer<1> canon;
+                    canon.w[0] = x < y ? x : y;
+                    own |= (owner_part(owner_fold<1>(canon), kp.nparts) == kp.part ? 1u : 0u) << i;
+                }
+                own &= valid;
+            } else {
+                Window<W> win;
+                win.load(g, w, kp.k);
+                if (win.valid) {
+                    uint64_t nf = win.next_feed;
+#pragma unroll 4
+                    for (int i = 0; i < 32; ++i) {
+                        uint32_t nxt = (uint32_t)nf & 3u;
+                        nf >>= 2;
+                        if ((win.valid >> i) & 1u) {
+                            bool fwd = kmer_less<W>(win.X, win.Y);
+                            uint32_t part = owner_part(owner_fold<W>(kmer_select<W>(fwd, win.X, win.Y)), kp.nparts);
+                            own |= (part == kp.part ? 1u : 0u) << i;
+                        }
+                        roll<W>(win.X, win.Y, nxt, kp.k);
+                    }
+                }
+            }
+        }
+        own_mask[w] = own;
+    }
+}
+
 constexpr int kBinListMax = kTilePos;
 constexpr size_t kBinShardedSmemBytes = kBinSmemBytes + kBinListMax * 2 + 16;
 
 template <int W>
 __global__ void __launch_bounds__(kTileThreads, 2)
-k_bin_sharded(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_end, uint64_t wave_base) {
+k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_end, uint64_t wave_base,
+           const uint32_t* __restrict__ own_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* gbase = reinterpret_cast<unsigned long long*>(smem_raw);
     uint32_t* hist = reinterpret_cast<uint32_t*>(gbase + kBinMaxBuckets);
@@ -169,27 +234,7 @@ k_bin_sharded(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     for (uint64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
-        // phase 1: which of my 32 positions does this shard own?
-        uint64_t w = tile * kTileThreads + tid;
-        uint32_t own = 0;
-        if (w * 32 < g.npos) {
-            Window<W> win;
-            win.load(g, w, kp.k);
-            if (win.valid) {
-                uint64_t nf = win.next_feed;
-#pragma unroll 4
-                for (int i = 0; i < 32; ++i) {
-                    uint32_t nxt = (uint32_t)nf & 3u;
-                    nf >>= 2;
-                    if ((win.valid >> i) & 1u) {
-                        bool fwd = kmer_less<W>(win.X, win.Y);
-                        uint32_t part = owner_part(owner_fold<W>(kmer_select<W>(fwd, win.X, win.Y)), kp.nparts);
-                        own |= (part == kp.part ? 1u : 0u) << i;
-                    }
-                    roll<W>(win.X, win.Y, nxt, kp.k);
-                }
-            }
-        }
+        uint32_t own = __ldcs(own_mask + tile * kTileThreads + tid);
         // CTA-wide list of owned positions (tile-relative, in position order)
         uint32_t cnt = __popc(own), incl = cnt;
 #pragma unroll

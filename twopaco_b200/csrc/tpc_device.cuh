@@ -297,7 +297,9 @@ struct Window {
         } else {
             valid = 0; prev_n = 0; next_n = 0;
             uint32_t run = 0;
+#pragma unroll 1
             for (uint32_t j = 0; j + 1 < k; ++j) run = load_n(g.nmask, p0 + j) ? 0 : run + 1;
+#pragma unroll 1
             for (uint32_t i = 0; i < 32; ++i) {
                 run = load_n(g.nmask, p0 + i + k - 1) ? 0 : run + 1;
                 if (run >= k) valid |= 1u << i;

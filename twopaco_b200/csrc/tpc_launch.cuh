@@ -21,7 +21,7 @@ struct Launch {
     static cudaError_t query(const LaunchCtx&, GenomeView, const uint32_t* filter, KParams, uint64_t ntiles,
                              uint32_t* mask, int accumulate, Counters*, uint32_t* hll);
     static cudaError_t bin(const LaunchCtx&, GenomeView, KParams, const BinView&, uint64_t tile_begin, uint64_t tile_end,
-                           uint64_t wave_base);
+                           uint64_t wave_base, uint32_t* own_scratch);
     static cudaError_t insert(const LaunchCtx&, GenomeView, const uint32_t* mask, KParams, uint64_t ntiles, TableView T, Counters*);
     static cudaError_t build_index(const LaunchCtx&, GenomeView, const unsigned long long* sorted, uint64_t n, KParams, TableView J);
     static cudaError_t ends(const LaunchCtx&, GenomeView, const RecordTable&, KParams, TableView J, uint32_t* stubmask,

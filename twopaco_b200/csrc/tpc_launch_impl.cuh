@@ -3,6 +3,7 @@
 #include "tpc_bin.cuh"
 #include "tpc_kernels.cuh"
 #include "tpc_launch.cuh"
+#include <algorithm>
 
 namespace tpc {
 
@@ -53,23 +54,30 @@ cudaError_t Launch<W>::query(const LaunchCtx& c, GenomeView g, const uint32_t* f
 
 template <int W>
 cudaError_t Launch<W>::bin(const LaunchCtx& c, GenomeView g, KParams kp, const BinView& bv, uint64_t tile_begin, uint64_t tile_end,
-                           uint64_t wave_base) {
+                           uint64_t wave_base, uint32_t* own_scratch) {
     if (tile_end <= tile_begin) return cudaSuccess;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(k_bin<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinSmemBytes);
-        cudaFuncSetAttribute(k_bin_sharded<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinShardedSmemBytes);
+        cudaFuncSetAttribute(k_bin_list<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinShardedSmemBytes);
         configured = true;
     }
-    const bool sharded = kp.nparts > 1;
-    const size_t smem = sharded ? kBinShardedSmemBytes : kBinSmemBytes;
-    int per_sm = 0;
-    if (sharded) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_sharded<W>, kTileThreads, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin<W>, kTileThreads, smem);
-    uint64_t grid = (uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count;
-    if (grid > tile_end - tile_begin) grid = tile_end - tile_begin;
-    if (sharded) k_bin_sharded<W><<<(int)grid, kTileThreads, smem, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base);
-    else k_bin<W><<<(int)grid, kTileThreads, smem, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base);
+    const uint64_t ntiles = tile_end - tile_begin;
+    if (kp.nparts > 1) {
+        // (1) ownership bit per position, (2) dense binning of the owned positions
+        int grid_own = persistent_grid(k_own<W>, kTileThreads, c.sm_count, ntiles);
+        k_own<W><<<grid_own, kTileThreads, 0, c.stream>>>(g, kp, tile_begin * kTileThreads, tile_end * kTileThreads, own_scratch);
+        ++*c.launches;
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_list<W>, kTileThreads, kBinShardedSmemBytes);
+        uint64_t grid = std::min<uint64_t>((uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count, ntiles);
+        k_bin_list<W><<<(int)grid, kTileThreads, kBinShardedSmemBytes, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base, own_scratch);
+    } else {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin<W>, kTileThreads, kBinSmemBytes);
+        uint64_t grid = std::min<uint64_t>((uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count, ntiles);
+        k_bin<W><<<(int)grid, kTileThreads, kBinSmemBytes, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base);
+    }
     ++*c.launches;
     return cudaGetLastError();
 }

@@ -427,7 +427,7 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
             CK(cudaEventRecord(e0, s->stream));
             if (rebin) {
                 CK(cudaMemsetAsync(s->d_bin_count, 0, (buckets + 1) * 8, s->stream));
-                CK(W_DISPATCH(s, bin(lc, s->g, kp, bv, t0, t1, base)));
+                CK(W_DISPATCH(s, bin(lc, s->g, kp, bv, t0, t1, base, s->d_stubmask)));  // stub mask doubles as ownership scratch
             }
             CK(cudaEventRecord(e1, s->stream));
             for (uint32_t b = 0; b < buckets; ++b) {
