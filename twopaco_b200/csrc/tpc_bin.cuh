@@ -213,22 +213,26 @@ k_own(GenomeView g, KParams kp, uint64_t word_begin, uint64_t word_end, uint32_t
 }
 
 constexpr int kBinListMax = kTilePos;
-constexpr size_t kBinShardedSmemBytes = kBinSmemBytes + kBinListMax * 2 + 16;
+// R = records per thread per staging round (stage = 256 R records); small R = more CTAs per SM
+constexpr size_t bin_list_smem_bytes(int R) {
+    return kBinMaxBuckets * 8 + kBinMaxBuckets * 4 * 2 + 8 * 4 + 16 + (size_t)kTileThreads * R * 4 * 3 + kBinListMax * 2;
+}
 
-template <int W>
-__global__ void __launch_bounds__(kTileThreads, 2)
+template <int W, int R>
+__global__ void __launch_bounds__(kTileThreads, (R <= 8 ? 3 : 2))
 k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_end, uint64_t wave_base,
            const uint32_t* __restrict__ own_mask) {
+    constexpr uint32_t kStage = kTileThreads * R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* gbase = reinterpret_cast<unsigned long long*>(smem_raw);
     uint32_t* hist = reinterpret_cast<uint32_t*>(gbase + kBinMaxBuckets);
     uint32_t* pref = hist + kBinMaxBuckets;
     uint32_t* warp_tot = pref + kBinMaxBuckets;
-    uint32_t* st_a = warp_tot + 8;
-    uint32_t* st_b = st_a + kBinStage;
-    uint32_t* st_c = st_b + kBinStage;
-    uint32_t* list_total = st_c + kBinStage;
-    uint16_t* list = reinterpret_cast<uint16_t*>(list_total + 4);
+    uint32_t* list_total = warp_tot + 8;
+    uint32_t* st_a = list_total + 4;
+    uint32_t* st_b = st_a + kStage;
+    uint32_t* st_c = st_b + kStage;
+    uint16_t* list = reinterpret_cast<uint16_t*>(st_c + kStage);
     const uint32_t nbuckets = 1u << bin.bucket_bits;
     const uint32_t sib_mask = (1u << bin.sib_bits) - 1u;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -256,14 +260,14 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
         __syncthreads();
         const uint32_t total = *list_total;
 
-        // phase 2: dense processing of the list, kBinStage records per round
-        for (uint32_t c0 = 0; c0 < total; c0 += kBinStage) {
-            const uint32_t n = min((uint32_t)kBinStage, total - c0);
+        // dense processing of the list, kStage records per round
+        for (uint32_t c0 = 0; c0 < total; c0 += kStage) {
+            const uint32_t n = min(kStage, total - c0);
             hist[tid] = 0;
             __syncthreads();
-            uint32_t rm[kBinHalf], rw[kBinHalf], rk[kBinHalf];
+            uint32_t rm[R], rw[R], rk[R];
 #pragma unroll
-            for (int j = 0; j < kBinHalf; ++j) {
+            for (int j = 0; j < R; ++j) {
                 const uint32_t e = tid + j * kTileThreads;
                 rk[j] = ~0u; rm[j] = 0; rw[j] = 0;
                 if (e < n) {
@@ -294,7 +298,7 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
             if (hc) gbase[tid] = atomicAdd(&bin.count[tid], (unsigned long long)hc);
             __syncthreads();
 #pragma unroll
-            for (int j = 0; j < kBinHalf; ++j) {
+            for (int j = 0; j < R; ++j) {
                 if (rk[j] != ~0u) {
                     uint32_t idx = pref[rk[j] >> 16] + (rk[j] & 0xFFFFu);
                     st_a[idx] = rm[j];

@@ -52,27 +52,42 @@ cudaError_t Launch<W>::query(const LaunchCtx& c, GenomeView g, const uint32_t* f
     return cudaGetLastError();
 }
 
+template <int W, int R>
+static void launch_bin_list(const LaunchCtx& c, GenomeView g, KParams kp, const BinView& bv, uint64_t tile_begin, uint64_t tile_end,
+                            uint64_t wave_base, const uint32_t* own) {
+    constexpr size_t smem = bin_list_smem_bytes(R);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_bin_list<W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_list<W, R>, kTileThreads, smem);
+    uint64_t grid = std::min<uint64_t>((uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count, tile_end - tile_begin);
+    k_bin_list<W, R><<<(int)grid, kTileThreads, smem, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base, own);
+}
+
 template <int W>
 cudaError_t Launch<W>::bin(const LaunchCtx& c, GenomeView g, KParams kp, const BinView& bv, uint64_t tile_begin, uint64_t tile_end,
                            uint64_t wave_base, uint32_t* own_scratch) {
     if (tile_end <= tile_begin) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_bin<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinSmemBytes);
-        cudaFuncSetAttribute(k_bin_list<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinShardedSmemBytes);
-        configured = true;
-    }
     const uint64_t ntiles = tile_end - tile_begin;
     if (kp.nparts > 1) {
         // (1) ownership bit per position, (2) dense binning of the owned positions
         int grid_own = persistent_grid(k_own<W>, kTileThreads, c.sm_count, ntiles);
         k_own<W><<<grid_own, kTileThreads, 0, c.stream>>>(g, kp, tile_begin * kTileThreads, tile_end * kTileThreads, own_scratch);
         ++*c.launches;
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_list<W>, kTileThreads, kBinShardedSmemBytes);
-        uint64_t grid = std::min<uint64_t>((uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count, ntiles);
-        k_bin_list<W><<<(int)grid, kTileThreads, kBinShardedSmemBytes, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base, own_scratch);
+        // stage size >= 1.25 x the expected owned positions of a tile (more CTAs per SM when it is small)
+        const uint32_t expect = (uint32_t)(kTilePos / kp.nparts) * 5 / 4;
+        if (expect <= 4 * kTileThreads) launch_bin_list<W, 4>(c, g, kp, bv, tile_begin, tile_end, wave_base, own_scratch);
+        else if (expect <= 8 * kTileThreads) launch_bin_list<W, 8>(c, g, kp, bv, tile_begin, tile_end, wave_base, own_scratch);
+        else launch_bin_list<W, 16>(c, g, kp, bv, tile_begin, tile_end, wave_base, own_scratch);
     } else {
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k_bin<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinSmemBytes);
+            configured = true;
+        }
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin<W>, kTileThreads, kBinSmemBytes);
         uint64_t grid = std::min<uint64_t>((uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count, ntiles);
