@@ -110,13 +110,12 @@ def run_reference_on(records: list[bytes], wl: dict, threads: int):
     return img, dt
 
 
-def cpu_baseline(dg, wl: dict) -> dict:
+def cpu_baseline(recs: list[bytes], wl: dict) -> dict:
     from oracle import oracle as O
     from twopaco_b200 import api
     if not O.have_reference():
         return {"value": None, "unit": "Gbp/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/twopaco missing"}
     cores = os.cpu_count() or 1
-    recs = sample_records(dg, wl)
     bp = sum(len(r) for r in recs)
     ref_img, dt = run_reference_on(recs, wl, cores)
     ours, _ = api.junctions_host(api.pack_records(recs), k=wl["k"], filter_bits=min(wl["f"], 32), q=wl["q"])
@@ -181,6 +180,10 @@ def main() -> None:
     total_bp = wl["genomes"] * wl["records"] * wl["length"]
     dg = api.synth_family_device(wl["seed"], wl["genomes"], wl["records"], wl["length"], wl["p"], keep_ascii=(rank == 0))
     total_bp = dg.total_bp
+    sample = sample_records(dg, wl) if rank == 0 else None   # bounded sample for the reference arm / parity check
+    if dg.ascii is not None:                                  # the 1 byte/bp generator output is not an input of the path
+        dg.ascii.close()
+        dg.ascii = None
 
     if args.sim_world:
         for i in range(args.warmup + args.steps):
@@ -303,7 +306,7 @@ def main() -> None:
         result["e2e"] = None
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        result["cpu_baseline"] = cpu_baseline(dg, wl)
+        result["cpu_baseline"] = cpu_baseline(sample, wl)
     if rank == 0:
         print(json.dumps(result))
     if world > 1:
