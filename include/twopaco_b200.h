@@ -103,6 +103,14 @@ int tpc_pack_records(const char *const *records, const uint64_t *rec_len, uint64
 int tpc_read_fasta(const char *path, char ***records, uint64_t **rec_len, uint64_t *n_records);
 void tpc_free_records(char **records, uint64_t *rec_len, uint64_t n_records);
 
+/* Multi-threaded whole-input parser used by tpc_build: all records of all files, normalised, in
+ * ONE buffer in the position layout of tpc_genome (1 byte per position, 'N' separators; feed it to
+ * tpc_pack_ascii_device).  Outputs are malloc'ed by the callee; release with tpc_host_free. */
+int tpc_ingest_fasta(const char *const *paths, size_t n_files, uint32_t threads, uint8_t **ascii,
+                     uint64_t *n_positions, uint64_t **rec_start, uint64_t **rec_len,
+                     uint64_t *n_records);
+void tpc_host_free(void *p);
+
 /* ------------------------------------------------------------------------------------------
  * Level 1 -- replaces  std::unique_ptr<VertexEnumerator> TwoPaCo::CreateEnumerator(fileName,
  * vertexLength, filterSize, hashFunctions, rounds, threads, abundance, tmpDirName,

@@ -95,3 +95,40 @@ def test_parameter_validation_and_no_cpu_fallback():
         # the product path must fail loudly without a GPU
         with pytest.raises(api.TpcError, match="no CUDA device"):
             api.Session(k=25, filter_bits=20)
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+@pytest.mark.parametrize("name", ["example_k11", "edge_mixed_k11", "edge_leading_short_k5", "family_twofiles_k25", "family_seam_k25"])
+def test_multithreaded_ingest_matches_oracle_parser(name, threads):
+    """tpc_ingest_fasta (what tpc_build uses) == the oracle's restatement of StreamFastaParser."""
+    with case_files(CASES[name]) as (paths, _, _):
+        layout, npos, rec_start, rec_len = api.ingest_fasta(paths, threads=threads)
+        ref = []
+        for p in paths:
+            ref += O.parse_fasta(p)
+    assert [int(x) for x in rec_len] == [len(r) for r in ref]
+    expect = b"N" + b"".join(r + b"N" for r in ref)
+    assert npos == len(expect) and layout == expect
+    assert [int(x) for x in rec_start] == list(np.cumsum([1] + [len(r) + 1 for r in ref])[:-1])
+
+
+def test_ingest_errors_and_odd_framing(tmp_path):
+    with pytest.raises(api.TpcError, match="Can't open file"):
+        api.ingest_fasta([str(tmp_path / "missing.fa")])
+    f = tmp_path / "x.fa"
+    f.write_bytes(b">x y\nACGTJACGT\n")
+    with pytest.raises(api.TpcError, match="invalid character 'J' in sequence x"):
+        api.ingest_fasta([str(f)])
+    f.write_bytes(b"ACGT\n")
+    with pytest.raises(api.TpcError, match="should start with a '>'"):
+        api.ingest_fasta([str(f)])
+    # '>' inside a header line is header text; '>' inside sequence text starts a record; a header
+    # without newline is an empty record; empty files have no records (streamfastaparser.cpp:29-93)
+    f.write_bytes(b">a >not a record\nAC\r\nGT>b\nTT\n\n>c")
+    layout, npos, rs, rl = api.ingest_fasta([str(f)], threads=3)
+    assert layout == b"NACGTNTTNN" and list(rl) == [4, 2, 0]
+    assert O.parse_fasta(str(f)) == [b"ACGT", b"TT", b""]
+    e = tmp_path / "empty.fa"
+    e.write_bytes(b"")
+    layout, npos, rs, rl = api.ingest_fasta([str(e), str(f)])
+    assert layout == b"NACGTNTTNN"

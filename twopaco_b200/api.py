@@ -57,6 +57,9 @@ SIGNATURES = {
     "tpc_pack_records": (C.c_int, [C.POINTER(C.c_char_p), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tpc_read_fasta": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(C.c_char_p)), C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]),
     "tpc_free_records": (None, [C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint64]),
+    "tpc_ingest_fasta": (C.c_int, [C.POINTER(C.c_char_p), C.c_size_t, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "tpc_host_free": (None, [C.c_void_p]),
     "tpc_build": (C.c_int, [C.POINTER(C.c_char_p), C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                             C.c_uint64, C.c_char_p, C.c_char_p, LOG_FN, C.c_void_p, C.POINTER(C.c_void_p)]),
     "tpc_vertices": (C.c_uint64, [C.c_void_p]),
@@ -159,6 +162,25 @@ def read_fasta(paths: list[str]) -> list[bytes]:
         return [C.string_at(recs[i], lens[i]) for i in range(n.value)]
     finally:
         L.tpc_free_records(recs, lens, n.value)
+
+
+def ingest_fasta(paths: list[str], threads: int = 0):
+    """Multi-threaded parser of tpc_build -> (ascii position layout as bytes, n_positions, rec_start, rec_len)."""
+    L = lib()
+    arr = (C.c_char_p * max(len(paths), 1))(*[os.fsencode(p) for p in paths])
+    a, s, l = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    npos, nrec = C.c_uint64(), C.c_uint64()
+    _check(L.tpc_ingest_fasta(arr, len(paths), threads or os.cpu_count() or 1, C.byref(a), C.byref(npos), C.byref(s), C.byref(l),
+                              C.byref(nrec)))
+    try:
+        n = nrec.value
+        layout = C.string_at(a, npos.value)
+        rec_start = np.frombuffer(C.string_at(s, n * 8), dtype=np.uint64).copy()
+        rec_len = np.frombuffer(C.string_at(l, n * 8), dtype=np.uint64).copy()
+    finally:
+        for p in (a, s, l):
+            L.tpc_host_free(p)
+    return layout, npos.value, rec_start, rec_len
 
 
 # ---------------------------------------------------------------------------------------------

@@ -61,6 +61,16 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
         for (int j = 0; j < W; ++j) { win.X.w[j] = 0; win.Y.w[j] = 0; }
         if (w * 32 < g.npos) win.load(g, w, kp.k);
         const bool any_n = (win.prev_n | win.next_n) != 0;
+        // k <= 31: both strands of every position by constant shifts out of two code words (and their
+        // reverse complement) instead of the rolling dependency chain
+        uint64_t c0 = 0, c1 = 0, r_lo = 0, r_hi = 0, kmask = 0;
+        if (W == 1 && w * 32 < g.npos) {
+            c0 = __ldg(g.codes + w); c1 = __ldg(g.codes + w + 1);
+            const uint32_t k2 = 2 * kp.k, s0 = 64 - k2;
+            kmask = (~0ull) >> (64 - k2);
+            const uint64_t rh = pairrev64(~c0), rl = pairrev64(~c1);
+            r_lo = (rl >> s0) | (rh << (64 - s0)); r_hi = rh >> s0;
+        }
         const uint64_t rel64 = w * 32 - wave_base;  // position relative to the wave: low 32 bits in word 2,
         const uint32_t relbase = (uint32_t)rel64;   // the bits above in the spare bits of word 1
         const uint32_t relhigh = (uint32_t)(rel64 >> 32) << bin.sib_bits;
@@ -76,10 +86,14 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
                 const int i = half * kBinHalf + j;
                 const uint32_t nxt = (nf32 >> (2 * j)) & 3u, prv = (pf32 >> (2 * j)) & 3u;
                 rk[j] = ~0u; rm[j] = 0; rw[j] = 0;
+                if (W == 1) {
+                    win.X.w[0] = (i ? ((c0 >> (2 * i)) | (c1 << (64 - 2 * i))) : c0) & kmask;
+                    win.Y.w[0] = (i ? ((r_lo >> (64 - 2 * i)) | (r_hi << (2 * i))) : r_hi) & kmask;
+                }
                 if (win.valid & (1u << i)) {
                     const bool fwd = kmer_less<W>(win.X, win.Y);
                     const Kmer<W> canon = kmer_select<W>(fwd, win.X, win.Y);
-                    if (kp.nparts == 1 || owner_part(owner_fold<W>(canon), kp.nparts) == kp.part) {
+                    {   // (k_bin runs unsharded rounds only: every definite k-mer is owned)
                         const uint64_t h = kmer_hash<W>(canon, kp.seed);
                         const uint64_t s = hash_sector(h, kp.sector_shift);
                         uint32_t code = prv | (nxt << 3) | (fwd ? 64u : 0u);
@@ -90,7 +104,7 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
                         rk[j] = (bucket << 16) | atomicAdd(&hist[bucket], 1u);
                     }
                 }
-                roll<W>(win.X, win.Y, nxt, kp.k);
+                if (W > 1) roll<W>(win.X, win.Y, nxt, kp.k);
             }
             __syncthreads();
             // exclusive scan of the histogram + global reservation per slice

@@ -16,6 +16,7 @@
 
 #include <cuda_runtime_api.h>
 
+#include "tpc_ingest.h"
 #include "tpc_internal.h"
 
 using tpc::set_error;
@@ -180,6 +181,7 @@ int tpc_pack_records(const char* const* records, const uint64_t* rec_len, uint64
 // ---------------------------------------------------------------------------------------------
 struct tpc_handle {
     tpc_session* session = nullptr;
+    void *d_codes = nullptr, *d_nmask = nullptr;
     tpc_stats stats{};
     uint64_t junctions = 0;
 };
@@ -214,28 +216,23 @@ int tpc_build(const char* const* fasta_paths, size_t n_files, uint32_t k, uint32
         L(ss.str());
     }
 
-    char** recs = nullptr; uint64_t* lens = nullptr; uint64_t nrec = 0;
-    int rc = 0;
-    for (size_t i = 0; i < n_files && rc == 0; ++i) rc = tpc_read_fasta(fasta_paths[i], &recs, &lens, &nrec);
-    uint64_t *codes = nullptr, *nmask = nullptr;
-    std::vector<uint64_t> start(nrec);
-    uint64_t npos = 0;
-    if (rc == 0) {
-        for (uint64_t i = 0; i < nrec && rc == 0; ++i)
-            if (lens[i] >> 32) rc = set_error("sequence %llu is longer than 2^32 bp", (unsigned long long)i);
-    }
-    if (rc == 0) {
-        npos = tpc_positions_for(lens, nrec);
-        if (cudaMallocHost((void**)&codes, tpc_code_words(npos) * 8) != cudaSuccess ||
-            cudaMallocHost((void**)&nmask, tpc_mask_words(npos) * 8) != cudaSuccess)
-            rc = set_error("out of (pinned) host memory");
-    }
-    if (rc == 0) rc = tpc_pack_records(recs, lens, nrec, threads ? threads : 1, codes, nmask, start.data());
+    // FASTA -> one pinned ASCII buffer in the position layout (all host threads, parsed once),
+    // -> device, packed to 2 bits + N mask by K0 on the GPU
+    tpc::IngestResult ing;
+    int rc = tpc::ingest_fasta(fasta_paths, n_files, threads ? threads : 1, &ing);
+    void *d_ascii = nullptr, *d_codes = nullptr, *d_nmask = nullptr;
     tpc_genome g{};
+    if (rc == 0) rc = tpc_device_alloc(ing.ascii_bytes, &d_ascii);
+    if (rc == 0) rc = tpc_device_alloc(tpc_code_words(ing.n_positions) * 8, &d_codes);
+    if (rc == 0) rc = tpc_device_alloc(tpc_mask_words(ing.n_positions) * 8, &d_nmask);
+    if (rc == 0) rc = tpc_copy_to_device(d_ascii, ing.ascii, ing.ascii_bytes);
+    if (rc == 0) rc = tpc_pack_ascii_device((const uint8_t*)d_ascii, ing.n_positions, (uint64_t*)d_codes, (uint64_t*)d_nmask, nullptr);
+    if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) rc = set_error("K0 pack failed");
+    tpc_device_free(d_ascii);
     if (rc == 0) {
-        g.codes = codes; g.n_mask = nmask; g.n_positions = npos;
-        g.rec_start = start.data(); g.rec_len = lens; g.n_records = nrec;
-        rc = tpc_session_set_genome_host(s, &g);
+        g.codes = (const uint64_t*)d_codes; g.n_mask = (const uint64_t*)d_nmask; g.n_positions = ing.n_positions;
+        g.rec_start = ing.rec_start.data(); g.rec_len = ing.rec_len.data(); g.n_records = ing.rec_start.size();
+        rc = tpc_session_set_genome_device(s, &g);
     }
     uint64_t bytes = 0;
     if (rc == 0) rc = tpc_session_run_to_count(s, &bytes);
@@ -272,13 +269,15 @@ int tpc_build(const char* const* fasta_paths, size_t n_files, uint32_t k, uint32
         L(ss.str());
     }
     if (image) cudaFreeHost(image);
-    if (codes) cudaFreeHost(codes);
-    if (nmask) cudaFreeHost(nmask);
-    tpc_free_records(recs, lens, nrec);
-    if (rc != 0) { tpc_session_destroy(s); return rc; }
-    tpc_handle* h = new (std::nothrow) tpc_handle();
-    if (!h) { tpc_session_destroy(s); return set_error("out of memory"); }
+    tpc_handle* h = rc == 0 ? new (std::nothrow) tpc_handle() : nullptr;
+    if (!h) {
+        tpc_session_destroy(s);
+        tpc_device_free(d_codes);
+        tpc_device_free(d_nmask);
+        return rc ? rc : set_error("out of memory");
+    }
     h->session = s; h->stats = st; h->junctions = st.junctions;
+    h->d_codes = d_codes; h->d_nmask = d_nmask;  // the session reads k-mers back from the genome (GetId)
     *out = h;
     return 0;
 }
@@ -301,6 +300,8 @@ int tpc_handle_stats(const tpc_handle* h, tpc_stats* out) {
 void tpc_free(tpc_handle* h) {
     if (!h) return;
     tpc_session_destroy(h->session);
+    tpc_device_free(h->d_codes);
+    tpc_device_free(h->d_nmask);
     delete h;
 }
 

@@ -1,0 +1,235 @@
+// tpc_ingest.cpp -- multi-threaded FASTA ingest for tpc_build.
+//
+// The reference parses its input single-threaded, one character per call, and does so again for
+// every stage (StreamFastaParser::GetChar, streamfastaparser.cpp:61-93; DistributeTasks,
+// vertexenumerator.h:1108-1226): that caps it at ~10-20 Mbp/s whatever the core count.  Here the
+// files are parsed ONCE, by all host threads:
+//   1. mmap the file; threads collect the positions of every '>' (memchr);
+//   2. one cheap sequential walk over those candidates frames the records (a '>' inside a header
+//      line belongs to the header; anywhere else it starts a record -- GetChar's rule, cpp:74-77);
+//   3. threads count the bases of 4 MiB pieces (whitespace skipped, alphabet validated);
+//   4. threads write the normalised bases into ONE pinned buffer in the tpc_genome position layout
+//      (1 byte per position, 'N' separators), which is copied to the GPU and packed there by K0
+//      (k_pack_ascii).  No per-record strings, no host-side bit packing.
+#include <algorithm>
+#include <atomic>
+#include <cctype>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cuda_runtime_api.h>
+
+#include "tpc_ingest.h"
+#include "tpc_internal.h"
+
+using tpc::set_error;
+
+namespace {
+
+struct Tables {
+    uint8_t cls[256];   // 0..3 ACGT, 4 other valid (-> N), 5 whitespace, 6 invalid
+    char norm[256];     // normalised letter
+    Tables() {
+        for (int i = 0; i < 256; ++i) { cls[i] = isspace(i) ? 5 : 6; norm[i] = 'N'; }
+        for (const char* p = "ACGTURYKMSWBDHWNXV"; *p; ++p) {   // dnachar.cpp:11
+            cls[(unsigned char)*p] = 4;
+            cls[(unsigned char)tolower(*p)] = 4;                // GetChar upper-cases (cpp:79-88)
+        }
+        const char* acgt = "ACGT";
+        for (int i = 0; i < 4; ++i) {
+            cls[(unsigned char)acgt[i]] = (uint8_t)i; cls[(unsigned char)tolower(acgt[i])] = (uint8_t)i;
+            norm[(unsigned char)acgt[i]] = acgt[i]; norm[(unsigned char)tolower(acgt[i])] = acgt[i];
+        }
+    }
+};
+const Tables kT;
+
+struct Mapped {
+    const unsigned char* p = nullptr;
+    size_t n = 0;
+    ~Mapped() { if (p && n) munmap((void*)p, n); }
+};
+
+struct Piece {      // a byte range of one record's sequence region
+    uint32_t file;
+    uint64_t rec;   // global record index
+    size_t lo, hi;
+    uint64_t bases = 0, base_off = 0;
+};
+
+template <typename F>
+void parallel_for(size_t n, uint32_t threads, F&& f) {
+    std::atomic<size_t> next{0};
+    auto run = [&]() { for (size_t i; (i = next.fetch_add(1)) < n;) f(i); };
+    std::vector<std::thread> pool;
+    for (uint32_t t = 1; t < threads && t < n; ++t) pool.emplace_back(run);
+    run();
+    for (auto& t : pool) t.join();
+}
+
+}  // namespace
+
+namespace tpc {
+
+IngestResult::~IngestResult() {
+    if (ascii && pinned) cudaFreeHost(ascii);
+    else free(ascii);
+}
+
+int ingest_fasta(const char* const* paths, size_t n_files, uint32_t threads, IngestResult* out) {
+    threads = std::max<uint32_t>(1, std::min<uint32_t>(threads, 256));
+    std::vector<Mapped> files(n_files);
+    std::vector<Piece> pieces;
+    struct Rec { uint32_t file; size_t hdr; };   // header start (for error messages)
+    std::vector<Rec> recs;
+    const size_t kPiece = 4u << 20;
+
+    for (size_t fi = 0; fi < n_files; ++fi) {
+        int fd = open(paths[fi], O_RDONLY);
+        if (fd < 0) return set_error("Can't open file %s", paths[fi]);
+        struct stat st;
+        if (fstat(fd, &st) != 0) { close(fd); return set_error("Can't open file %s", paths[fi]); }
+        Mapped& m = files[fi];
+        m.n = (size_t)st.st_size;
+        if (m.n) {
+            void* p = mmap(nullptr, m.n, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (p == MAP_FAILED) { close(fd); m.n = 0; return set_error("Can't map file %s", paths[fi]); }
+            madvise(p, m.n, MADV_SEQUENTIAL);
+            m.p = (const unsigned char*)p;
+        }
+        close(fd);
+        if (!m.n) continue;
+        if (m.p[0] != '>') return set_error("The FASTA header should start with a '>', started with '%c'", m.p[0]);
+        // 1. candidates: every '>' of the file, found by all threads
+        const size_t nchunks = std::max<size_t>(1, std::min<size_t>(threads * 4, m.n / (1 << 20) + 1));
+        std::vector<std::vector<size_t>> found(nchunks);
+        parallel_for(nchunks, threads, [&](size_t c) {
+            size_t lo = m.n * c / nchunks, hi = m.n * (c + 1) / nchunks;
+            const unsigned char* q = m.p + lo;
+            while (q < m.p + hi) {
+                q = (const unsigned char*)memchr(q, '>', (size_t)(m.p + hi - q));
+                if (!q) break;
+                found[c].push_back((size_t)(q - m.p));
+                ++q;
+            }
+        });
+        // 2. framing: a candidate inside a header line is header text
+        size_t header_end = 0;   // first byte after the newline of the current header
+        size_t prev_seq_lo = 0;
+        bool open_rec = false;
+        auto close_record = [&](size_t seq_hi) {
+            uint64_t r = recs.size() - 1;
+            for (size_t lo = prev_seq_lo; lo < seq_hi || lo == prev_seq_lo; lo += kPiece) {
+                pieces.push_back(Piece{(uint32_t)fi, r, lo, std::min(seq_hi, lo + kPiece)});
+                if (lo + kPiece >= seq_hi) break;
+            }
+        };
+        for (auto& v : found) {
+            for (size_t pos : v) {
+                if (pos < header_end) continue;          // '>' inside a header line
+                if (open_rec) close_record(pos);
+                recs.push_back(Rec{(uint32_t)fi, pos});
+                const unsigned char* nl = (const unsigned char*)memchr(m.p + pos, '\n', m.n - pos);
+                header_end = nl ? (size_t)(nl - m.p) + 1 : m.n;
+                prev_seq_lo = header_end;
+                open_rec = true;
+            }
+        }
+        if (open_rec) close_record(m.n);
+    }
+
+    // 3. bases per piece (+ alphabet check)
+    std::atomic<long long> bad_piece{-1};
+    parallel_for(pieces.size(), threads, [&](size_t i) {
+        Piece& pc = pieces[i];
+        const unsigned char* p = files[pc.file].p;
+        uint64_t n = 0;
+        bool bad = false;
+        for (size_t b = pc.lo; b < pc.hi; ++b) {
+            uint8_t c = kT.cls[p[b]];
+            n += c <= 4;
+            bad |= c == 6;
+        }
+        pc.bases = n;
+        if (bad) {
+            long long expect = -1;
+            long long mine = (long long)i;
+            while (!bad_piece.compare_exchange_weak(expect, mine) && (expect < 0 || expect > mine)) {}
+        }
+    });
+    if (bad_piece.load() >= 0) {
+        const Piece& pc = pieces[(size_t)bad_piece.load()];
+        const unsigned char* p = files[pc.file].p;
+        for (size_t b = pc.lo; b < pc.hi; ++b) {
+            if (kT.cls[p[b]] == 6) {
+                const Rec& r = recs[pc.rec];
+                size_t h0 = r.hdr + 1, h1 = h0;
+                while (h1 < files[r.file].n && !isspace(files[r.file].p[h1])) ++h1;
+                std::string name((const char*)files[r.file].p + h0, h1 - h0);
+                return set_error("Found an invalid character '%c' in sequence %s", p[b], name.c_str());
+            }
+        }
+    }
+    out->rec_len.assign(recs.size(), 0);
+    for (Piece& pc : pieces) { pc.base_off = out->rec_len[pc.rec]; out->rec_len[pc.rec] += pc.bases; }
+    out->rec_start.resize(recs.size());
+    uint64_t pos = 1;
+    for (size_t r = 0; r < recs.size(); ++r) {
+        if (out->rec_len[r] >> 32) return set_error("sequence %zu is longer than 2^32 bp", r);
+        out->rec_start[r] = pos;
+        pos += out->rec_len[r] + 1;
+    }
+    out->n_positions = pos;
+    out->ascii_bytes = (pos + 63) / 64 * 64 + 64;
+    out->pinned = cudaMallocHost((void**)&out->ascii, out->ascii_bytes) == cudaSuccess;
+    if (!out->pinned) {   // no driver (host-only use of the parser) or pinning refused: pageable memory
+        cudaGetLastError();
+        out->ascii = (uint8_t*)malloc(out->ascii_bytes);
+        if (!out->ascii) return set_error("out of host memory: %llu bytes", (unsigned long long)out->ascii_bytes);
+    }
+    // 4. normalised bases into the position layout; separators and padding are 'N'
+    out->ascii[0] = 'N';
+    for (size_t r = 0; r < recs.size(); ++r) out->ascii[out->rec_start[r] + out->rec_len[r]] = 'N';
+    memset(out->ascii + pos, 'N', out->ascii_bytes - pos);
+    parallel_for(pieces.size(), threads, [&](size_t i) {
+        const Piece& pc = pieces[i];
+        const unsigned char* p = files[pc.file].p;
+        uint8_t* dst = out->ascii + out->rec_start[pc.rec] + pc.base_off;
+        for (size_t b = pc.lo; b < pc.hi; ++b) {
+            unsigned char ch = p[b];
+            if (kT.cls[ch] <= 4) *dst++ = (uint8_t)kT.norm[ch];
+        }
+    });
+    return 0;
+}
+
+}  // namespace tpc
+
+extern "C" {
+
+int tpc_ingest_fasta(const char* const* paths, size_t n_files, uint32_t threads, uint8_t** ascii, uint64_t* n_positions,
+                     uint64_t** rec_start, uint64_t** rec_len, uint64_t* n_records) {
+    if (!paths || !ascii || !n_positions || !rec_start || !rec_len || !n_records) return set_error("null argument");
+    tpc::IngestResult r;
+    if (int rc = tpc::ingest_fasta(paths, n_files, threads, &r)) return rc;
+    size_t n = r.rec_len.size();
+    uint8_t* a = (uint8_t*)malloc(r.ascii_bytes);
+    uint64_t* s = (uint64_t*)malloc(std::max<size_t>(n, 1) * 8);
+    uint64_t* l = (uint64_t*)malloc(std::max<size_t>(n, 1) * 8);
+    if (!a || !s || !l) { free(a); free(s); free(l); return set_error("out of host memory"); }
+    memcpy(a, r.ascii, r.ascii_bytes);
+    if (n) { memcpy(s, r.rec_start.data(), n * 8); memcpy(l, r.rec_len.data(), n * 8); }
+    *ascii = a; *n_positions = r.n_positions; *rec_start = s; *rec_len = l; *n_records = n;
+    return 0;
+}
+
+void tpc_host_free(void* p) { free(p); }
+
+}  // extern "C"
