@@ -97,10 +97,15 @@ def test_parameter_validation_and_no_cpu_fallback():
             api.Session(k=25, filter_bits=20)
 
 
-@pytest.mark.parametrize("threads", [1, 4])
+@pytest.mark.parametrize("threads,piece", [(1, 0), (4, 0), (3, 7), (4, 1000)])
 @pytest.mark.parametrize("name", ["example_k11", "edge_mixed_k11", "edge_leading_short_k5", "family_twofiles_k25", "family_seam_k25"])
-def test_multithreaded_ingest_matches_oracle_parser(name, threads):
-    """tpc_ingest_fasta (what tpc_build uses) == the oracle's restatement of StreamFastaParser."""
+def test_multithreaded_ingest_matches_oracle_parser(name, threads, piece, monkeypatch):
+    """tpc_ingest_fasta (what tpc_build uses) == the oracle's restatement of StreamFastaParser.
+    Tiny work units (TPC_INGEST_PIECE) exercise the seams between pieces and between staging spans."""
+    if piece:
+        if name == "family_seam_k25" and piece < 100:
+            pytest.skip("too slow with 7-byte pieces")
+        monkeypatch.setenv("TPC_INGEST_PIECE", str(piece))
     with case_files(CASES[name]) as (paths, _, _):
         layout, npos, rec_start, rec_len = api.ingest_fasta(paths, threads=threads)
         ref = []

@@ -179,6 +179,56 @@ int tpc_pack_records(const char* const* records, const uint64_t* rec_len, uint64
 // ---------------------------------------------------------------------------------------------
 // level 1: tpc_build == CreateEnumerator
 // ---------------------------------------------------------------------------------------------
+namespace {
+
+// IngestSink that ships every span to the device: two pinned staging buffers, the copy of span i
+// overlaps the parsing of span i+1.
+class StagedUpload : public tpc::IngestSink {
+public:
+    static constexpr uint64_t kSpan = 64ull << 20;
+    explicit StagedUpload(uint8_t* device_base) : dev_(device_base) {}
+    ~StagedUpload() override {
+        for (int i = 0; i < 2; ++i) {
+            if (buf_[i]) cudaFreeHost(buf_[i]);
+            if (ev_[i]) cudaEventDestroy(ev_[i]);
+        }
+    }
+    uint8_t* acquire(uint64_t max_bytes) override {
+        int i = next_;
+        if (ev_[i] && cudaEventSynchronize(ev_[i]) != cudaSuccess) return nullptr;   // previous copy out of this buffer done
+        if (cap_[i] < max_bytes) {
+            if (buf_[i]) cudaFreeHost(buf_[i]);
+            buf_[i] = nullptr;
+            cap_[i] = std::max<uint64_t>(max_bytes, kSpan + (9u << 20));
+            if (cudaMallocHost((void**)&buf_[i], cap_[i]) != cudaSuccess) { cap_[i] = 0; return nullptr; }
+        }
+        return buf_[i];
+    }
+    int commit(uint64_t off, uint8_t* buf, uint64_t nbytes) override {
+        int i = next_;
+        if (cudaMemcpyAsync(dev_ + off, buf, nbytes, cudaMemcpyHostToDevice, nullptr) != cudaSuccess)
+            return set_error("host to device copy failed");
+        if (!ev_[i]) cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming);
+        cudaEventRecord(ev_[i], nullptr);
+        next_ ^= 1;
+        return 0;
+    }
+    int finish() { return cudaDeviceSynchronize() == cudaSuccess ? 0 : set_error("host to device copy failed"); }
+
+private:
+    uint8_t* dev_;
+    uint8_t* buf_[2] = {nullptr, nullptr};
+    uint64_t cap_[2] = {0, 0};
+    cudaEvent_t ev_[2] = {nullptr, nullptr};
+    int next_ = 0;
+};
+
+int write_chunk_to_file(void* ctx, const uint8_t* data, uint64_t nbytes) {
+    return fwrite(data, 1, nbytes, (FILE*)ctx) == nbytes ? 0 : set_error("Can't write to the output file");
+}
+
+}  // namespace
+
 struct tpc_handle {
     tpc_session* session = nullptr;
     void *d_codes = nullptr, *d_nmask = nullptr;
@@ -216,41 +266,42 @@ int tpc_build(const char* const* fasta_paths, size_t n_files, uint32_t k, uint32
         L(ss.str());
     }
 
-    // FASTA -> one pinned ASCII buffer in the position layout (all host threads, parsed once),
-    // -> device, packed to 2 bits + N mask by K0 on the GPU
-    tpc::IngestResult ing;
-    int rc = tpc::ingest_fasta(fasta_paths, n_files, threads ? threads : 1, &ing);
+    // FASTA -> position layout (all host threads, parsed once), streamed to the device through two
+    // pinned staging buffers, packed to 2 bits + N mask by K0 on the GPU
+    tpc::IngestPlan plan;
+    int rc = tpc::ingest_plan(fasta_paths, n_files, threads ? threads : 1, &plan);
     void *d_ascii = nullptr, *d_codes = nullptr, *d_nmask = nullptr;
     tpc_genome g{};
-    if (rc == 0) rc = tpc_device_alloc(ing.ascii_bytes, &d_ascii);
-    if (rc == 0) rc = tpc_device_alloc(tpc_code_words(ing.n_positions) * 8, &d_codes);
-    if (rc == 0) rc = tpc_device_alloc(tpc_mask_words(ing.n_positions) * 8, &d_nmask);
-    if (rc == 0) rc = tpc_copy_to_device(d_ascii, ing.ascii, ing.ascii_bytes);
-    if (rc == 0) rc = tpc_pack_ascii_device((const uint8_t*)d_ascii, ing.n_positions, (uint64_t*)d_codes, (uint64_t*)d_nmask, nullptr);
+    if (rc == 0) rc = tpc_device_alloc(plan.layout_bytes, &d_ascii);
+    if (rc == 0) rc = tpc_device_alloc(tpc_code_words(plan.n_positions) * 8, &d_codes);
+    if (rc == 0) rc = tpc_device_alloc(tpc_mask_words(plan.n_positions) * 8, &d_nmask);
+    if (rc == 0) {
+        StagedUpload up((uint8_t*)d_ascii);
+        rc = tpc::ingest_emit(plan, threads ? threads : 1, StagedUpload::kSpan, up);
+        if (rc == 0) rc = up.finish();
+    }
+    if (rc == 0) rc = tpc_pack_ascii_device((const uint8_t*)d_ascii, plan.n_positions, (uint64_t*)d_codes, (uint64_t*)d_nmask, nullptr);
     if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) rc = set_error("K0 pack failed");
     tpc_device_free(d_ascii);
     if (rc == 0) {
-        g.codes = (const uint64_t*)d_codes; g.n_mask = (const uint64_t*)d_nmask; g.n_positions = ing.n_positions;
-        g.rec_start = ing.rec_start.data(); g.rec_len = ing.rec_len.data(); g.n_records = ing.rec_start.size();
+        g.codes = (const uint64_t*)d_codes; g.n_mask = (const uint64_t*)d_nmask; g.n_positions = plan.n_positions;
+        g.rec_start = plan.rec_start.data(); g.rec_len = plan.rec_len.data(); g.n_records = plan.rec_start.size();
         rc = tpc_session_set_genome_device(s, &g);
     }
     uint64_t bytes = 0;
     if (rc == 0) rc = tpc_session_run_to_count(s, &bytes);
-    uint8_t* image = nullptr;
-    if (rc == 0 && cudaMallocHost((void**)&image, std::max<uint64_t>(bytes, 16)) != cudaSuccess)
-        rc = set_error("out of (pinned) host memory");
-    if (rc == 0) rc = tpc_session_write_host(s, image, bytes);
     tpc_stats st{};
-    if (rc == 0) rc = tpc_session_stats(s, &st);
     if (rc == 0) {
-        // JunctionPositionWriter (junctionapi.h:110-116): creates / truncates the output file
+        // JunctionPositionWriter (junctionapi.h:110-116): creates / truncates the output file; the image
+        // is produced on the device and streamed to the file through two pinned staging buffers
         FILE* f = fopen(outfile, "wb");
         if (!f) rc = set_error("Can't create the output file");
         else {
-            if (bytes && fwrite(image, 1, bytes, f) != bytes) rc = set_error("Can't write to the output file");
-            fclose(f);
+            rc = tpc_session_write_stream(s, bytes, write_chunk_to_file, f);
+            if (fclose(f) != 0 && rc == 0) rc = set_error("Can't write to the output file");
         }
     }
+    if (rc == 0) rc = tpc_session_stats(s, &st);
     if (rc == 0) {
         std::ostringstream ss;
         ss << std::string(80, '-') << "\n"
@@ -268,7 +319,6 @@ int tpc_build(const char* const* fasta_paths, size_t n_files, uint32_t k, uint32
            << std::string(80, '-') << "\n";
         L(ss.str());
     }
-    if (image) cudaFreeHost(image);
     tpc_handle* h = rc == 0 ? new (std::nothrow) tpc_handle() : nullptr;
     if (!h) {
         tpc_session_destroy(s);

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cctype>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -62,7 +63,15 @@ struct Piece {      // a byte range of one record's sequence region
     uint64_t rec;   // global record index
     size_t lo, hi;
     uint64_t bases = 0, base_off = 0;
+    bool last = false;   // last piece of its record: also covers the separator after the record
 };
+
+// bytes of sequence text per work unit (TPC_INGEST_PIECE shrinks it so tests can exercise seams)
+size_t piece_bytes() {
+    const char* e = getenv("TPC_INGEST_PIECE");
+    long v = e ? atol(e) : 0;
+    return v > 0 ? (size_t)v : (size_t)(4u << 20);
+}
 
 template <typename F>
 void parallel_for(size_t n, uint32_t threads, F&& f) {
@@ -78,18 +87,21 @@ void parallel_for(size_t n, uint32_t threads, F&& f) {
 
 namespace tpc {
 
-IngestResult::~IngestResult() {
-    if (ascii && pinned) cudaFreeHost(ascii);
-    else free(ascii);
-}
-
-int ingest_fasta(const char* const* paths, size_t n_files, uint32_t threads, IngestResult* out) {
-    threads = std::max<uint32_t>(1, std::min<uint32_t>(threads, 256));
-    std::vector<Mapped> files(n_files);
+struct IngestPlan::Impl {
+    std::vector<Mapped> files;
     std::vector<Piece> pieces;
+};
+IngestPlan::IngestPlan() : impl(new Impl()) {}
+IngestPlan::~IngestPlan() {}
+
+int ingest_plan(const char* const* paths, size_t n_files, uint32_t threads, IngestPlan* out) {
+    threads = std::max<uint32_t>(1, std::min<uint32_t>(threads, 256));
+    std::vector<Mapped>& files = out->impl->files;
+    std::vector<Piece>& pieces = out->impl->pieces;
+    files.resize(n_files);
     struct Rec { uint32_t file; size_t hdr; };   // header start (for error messages)
     std::vector<Rec> recs;
-    const size_t kPiece = 4u << 20;
+    const size_t kPiece = piece_bytes();
 
     for (size_t fi = 0; fi < n_files; ++fi) {
         int fd = open(paths[fi], O_RDONLY);
@@ -126,9 +138,10 @@ int ingest_fasta(const char* const* paths, size_t n_files, uint32_t threads, Ing
         bool open_rec = false;
         auto close_record = [&](size_t seq_hi) {
             uint64_t r = recs.size() - 1;
-            for (size_t lo = prev_seq_lo; lo < seq_hi || lo == prev_seq_lo; lo += kPiece) {
-                pieces.push_back(Piece{(uint32_t)fi, r, lo, std::min(seq_hi, lo + kPiece)});
-                if (lo + kPiece >= seq_hi) break;
+            for (size_t lo = prev_seq_lo;; lo += kPiece) {
+                bool last = lo + kPiece >= seq_hi;
+                pieces.push_back(Piece{(uint32_t)fi, r, lo, std::min(seq_hi, lo + kPiece), 0, 0, last});
+                if (last) break;
             }
         };
         for (auto& v : found) {
@@ -187,26 +200,55 @@ int ingest_fasta(const char* const* paths, size_t n_files, uint32_t threads, Ing
         pos += out->rec_len[r] + 1;
     }
     out->n_positions = pos;
-    out->ascii_bytes = (pos + 63) / 64 * 64 + 64;
-    out->pinned = cudaMallocHost((void**)&out->ascii, out->ascii_bytes) == cudaSuccess;
-    if (!out->pinned) {   // no driver (host-only use of the parser) or pinning refused: pageable memory
-        cudaGetLastError();
-        out->ascii = (uint8_t*)malloc(out->ascii_bytes);
-        if (!out->ascii) return set_error("out of host memory: %llu bytes", (unsigned long long)out->ascii_bytes);
-    }
-    // 4. normalised bases into the position layout; separators and padding are 'N'
-    out->ascii[0] = 'N';
-    for (size_t r = 0; r < recs.size(); ++r) out->ascii[out->rec_start[r] + out->rec_len[r]] = 'N';
-    memset(out->ascii + pos, 'N', out->ascii_bytes - pos);
-    parallel_for(pieces.size(), threads, [&](size_t i) {
-        const Piece& pc = pieces[i];
-        const unsigned char* p = files[pc.file].p;
-        uint8_t* dst = out->ascii + out->rec_start[pc.rec] + pc.base_off;
-        for (size_t b = pc.lo; b < pc.hi; ++b) {
-            unsigned char ch = p[b];
-            if (kT.cls[ch] <= 4) *dst++ = (uint8_t)kT.norm[ch];
+    out->layout_bytes = (pos + 63) / 64 * 64 + 64;
+    return 0;
+}
+
+// 4. normalised bases into the position layout, span by span; separators and padding are 'N'.
+// Consecutive pieces are contiguous in the layout: a piece covers its bases plus, when it is the
+// last piece of its record, the separator that follows the record.
+int ingest_emit(const IngestPlan& plan, uint32_t threads, uint64_t span_bytes, IngestSink& sink) {
+    threads = std::max<uint32_t>(1, std::min<uint32_t>(threads, 256));
+    const std::vector<Mapped>& files = plan.impl->files;
+    const std::vector<Piece>& pieces = plan.impl->pieces;
+    auto dest_lo = [&](const Piece& pc) { return plan.rec_start[pc.rec] + pc.base_off; };
+    auto dest_n = [&](const Piece& pc) { return pc.bases + (pc.last ? 1 : 0); };
+    const uint64_t max_piece = piece_bytes() + 1;
+    span_bytes = std::max<uint64_t>(span_bytes, 2 * max_piece);
+    size_t i = 0;
+    uint64_t span_lo = 0;   // layout offset of the current span; position 0 is the leading separator
+    while (true) {
+        size_t j = i;
+        uint64_t span_hi = i < pieces.size() ? dest_lo(pieces[i]) : plan.n_positions;
+        while (j < pieces.size() && dest_lo(pieces[j]) + dest_n(pieces[j]) - span_lo <= span_bytes) {
+            span_hi = dest_lo(pieces[j]) + dest_n(pieces[j]);
+            ++j;
         }
-    });
+        const bool final_span = j == pieces.size();
+        if (final_span) span_hi = plan.layout_bytes;        // trailing padding
+        if (span_hi - span_lo > span_bytes + 128 && !final_span) return set_error("ingest: span planning failed");
+        uint8_t* buf = sink.acquire(span_hi - span_lo);
+        if (!buf) return set_error("ingest: no staging buffer");
+        if (span_lo == 0) buf[0] = 'N';
+        if (final_span) {
+            uint64_t tail_from = std::max<uint64_t>(plan.n_positions, span_lo);
+            memset(buf + (tail_from - span_lo), 'N', span_hi - tail_from);
+        }
+        parallel_for(j - i, threads, [&](size_t t) {
+            const Piece& pc = pieces[i + t];
+            const unsigned char* p = files[pc.file].p;
+            uint8_t* dst = buf + (dest_lo(pc) - span_lo);
+            for (size_t b = pc.lo; b < pc.hi; ++b) {
+                unsigned char ch = p[b];
+                if (kT.cls[ch] <= 4) *dst++ = (uint8_t)kT.norm[ch];
+            }
+            if (pc.last) *dst = 'N';
+        });
+        if (int rc = sink.commit(span_lo, buf, span_hi - span_lo)) return rc;
+        if (final_span) break;
+        span_lo = span_hi;
+        i = j;
+    }
     return 0;
 }
 
@@ -217,16 +259,23 @@ extern "C" {
 int tpc_ingest_fasta(const char* const* paths, size_t n_files, uint32_t threads, uint8_t** ascii, uint64_t* n_positions,
                      uint64_t** rec_start, uint64_t** rec_len, uint64_t* n_records) {
     if (!paths || !ascii || !n_positions || !rec_start || !rec_len || !n_records) return set_error("null argument");
-    tpc::IngestResult r;
-    if (int rc = tpc::ingest_fasta(paths, n_files, threads, &r)) return rc;
-    size_t n = r.rec_len.size();
-    uint8_t* a = (uint8_t*)malloc(r.ascii_bytes);
+    tpc::IngestPlan plan;
+    if (int rc = tpc::ingest_plan(paths, n_files, threads, &plan)) return rc;
+    size_t n = plan.rec_len.size();
+    struct WholeBuffer : tpc::IngestSink {
+        uint8_t* base = nullptr;
+        uint64_t next = 0;
+        uint8_t* acquire(uint64_t) override { return base + next; }
+        int commit(uint64_t off, uint8_t*, uint64_t nbytes) override { next = off + nbytes; return 0; }
+    } sink;
+    sink.base = (uint8_t*)malloc(plan.layout_bytes);
     uint64_t* s = (uint64_t*)malloc(std::max<size_t>(n, 1) * 8);
     uint64_t* l = (uint64_t*)malloc(std::max<size_t>(n, 1) * 8);
-    if (!a || !s || !l) { free(a); free(s); free(l); return set_error("out of host memory"); }
-    memcpy(a, r.ascii, r.ascii_bytes);
-    if (n) { memcpy(s, r.rec_start.data(), n * 8); memcpy(l, r.rec_len.data(), n * 8); }
-    *ascii = a; *n_positions = r.n_positions; *rec_start = s; *rec_len = l; *n_records = n;
+    if (!sink.base || !s || !l) { free(sink.base); free(s); free(l); return set_error("out of host memory"); }
+    // small spans here so that the tests exercise the span logic
+    if (int rc = tpc::ingest_emit(plan, threads, 1, sink)) { free(sink.base); free(s); free(l); return rc; }
+    if (n) { memcpy(s, plan.rec_start.data(), n * 8); memcpy(l, plan.rec_len.data(), n * 8); }
+    *ascii = sink.base; *n_positions = plan.n_positions; *rec_start = s; *rec_len = l; *n_records = n;
     return 0;
 }
 

@@ -748,6 +748,41 @@ int tpc_session_write_host(tpc_session* s, uint8_t* out_image, uint64_t image_by
     return rc;
 }
 
+int tpc_session_write_stream(tpc_session* s, uint64_t image_bytes, tpc_chunk_sink sink, void* ctx) {
+    uint8_t* d_out = nullptr;
+    CK(dev_alloc(&d_out, std::max<uint64_t>(image_bytes, 16), s->stream));
+    uint64_t off = 0, bytes = 0;
+    int rc = tpc_session_emit_write(s, 0, 0, d_out, image_bytes, &off, &bytes);
+    const uint64_t kChunk = 64ull << 20;
+    uint8_t* stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (rc == 0 && bytes) {
+        for (int i = 0; i < 2 && rc == 0; ++i) {
+            if (cudaMallocHost((void**)&stage[i], std::min(kChunk, bytes)) != cudaSuccess) rc = set_error("out of (pinned) host memory");
+            else cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+        }
+        uint64_t nchunks = (bytes + kChunk - 1) / kChunk;
+        auto issue = [&](uint64_t c) {
+            uint64_t lo = c * kChunk, n = std::min(kChunk, bytes - lo);
+            cudaMemcpyAsync(stage[c & 1], d_out + lo, n, cudaMemcpyDeviceToHost, s->stream);
+            cudaEventRecord(ev[c & 1], s->stream);
+        };
+        if (rc == 0) issue(0);
+        for (uint64_t c = 0; c < nchunks && rc == 0; ++c) {
+            if (cudaEventSynchronize(ev[c & 1]) != cudaSuccess) { rc = set_error("device to host copy failed"); break; }
+            if (c + 1 < nchunks) issue(c + 1);   // overlaps the sink below
+            rc = sink(ctx, stage[c & 1], std::min(kChunk, bytes - c * kChunk));
+        }
+    }
+    cudaStreamSynchronize(s->stream);
+    for (int i = 0; i < 2; ++i) {
+        if (stage[i]) cudaFreeHost(stage[i]);
+        if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+    dev_free(d_out, s->stream);
+    return rc;
+}
+
 int tpc_junctions_host(const tpc_params* params, const tpc_genome* host_genome, uint8_t* out_image, uint64_t out_capacity,
                        uint64_t* out_bytes, tpc_stats* stats) {
     if (!params || !host_genome) return set_error("null argument");
