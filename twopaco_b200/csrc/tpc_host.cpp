@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cctype>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -199,7 +200,7 @@ public:
         if (cap_[i] < max_bytes) {
             if (buf_[i]) cudaFreeHost(buf_[i]);
             buf_[i] = nullptr;
-            cap_[i] = std::max<uint64_t>(max_bytes, kSpan + (9u << 20));
+            cap_[i] = (max_bytes + (1u << 20) - 1) >> 20 << 20;   // small inputs pin little
             if (cudaMallocHost((void**)&buf_[i], cap_[i]) != cudaSuccess) { cap_[i] = 0; return nullptr; }
         }
         return buf_[i];
@@ -268,8 +269,12 @@ int tpc_build(const char* const* fasta_paths, size_t n_files, uint32_t k, uint32
 
     // FASTA -> position layout (all host threads, parsed once), streamed to the device through two
     // pinned staging buffers, packed to 2 bits + N mask by K0 on the GPU
+    const bool verbose = getenv("TPC_VERBOSE") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
     tpc::IngestPlan plan;
     int rc = tpc::ingest_plan(fasta_paths, n_files, threads ? threads : 1, &plan);
+    double t_plan = now();
     void *d_ascii = nullptr, *d_codes = nullptr, *d_nmask = nullptr;
     tpc_genome g{};
     if (rc == 0) rc = tpc_device_alloc(plan.layout_bytes, &d_ascii);
@@ -288,8 +293,10 @@ int tpc_build(const char* const* fasta_paths, size_t n_files, uint32_t k, uint32
         g.rec_start = plan.rec_start.data(); g.rec_len = plan.rec_len.data(); g.n_records = plan.rec_start.size();
         rc = tpc_session_set_genome_device(s, &g);
     }
+    double t_upload = now();
     uint64_t bytes = 0;
     if (rc == 0) rc = tpc_session_run_to_count(s, &bytes);
+    double t_gpu = now();
     tpc_stats st{};
     if (rc == 0) {
         // JunctionPositionWriter (junctionapi.h:110-116): creates / truncates the output file; the image
@@ -302,6 +309,9 @@ int tpc_build(const char* const* fasta_paths, size_t n_files, uint32_t k, uint32
         }
     }
     if (rc == 0) rc = tpc_session_stats(s, &st);
+    if (verbose)
+        fprintf(stderr, "[tpc_build] frame+count %.3f s, normalise+upload+pack %.3f s, gpu passes %.3f s, emit+write %.3f s\n",
+                t_plan - t0, t_upload - t_plan, t_gpu - t_upload, now() - t_gpu);
     if (rc == 0) {
         std::ostringstream ss;
         ss << std::string(80, '-') << "\n"
