@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <new>
 #include <string>
 #include <vector>
@@ -204,6 +205,12 @@ struct tpc_session {
     uint32_t* d_bin_ov = nullptr;
     bool used_binned = false;
 
+    // host->device upload of the genome overlapped with the first binning pass (set_genome_host)
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> up_ev;          // upload chunk c is complete
+    std::vector<uint64_t> up_tile_begin;     // first tile of chunk c
+    size_t up_waited = 0;                    // chunks the compute stream already waits for
+
     tpc_stats st{};
     cudaEvent_t ev[10]{};
     uint32_t launches = 0;
@@ -301,6 +308,9 @@ void tpc_session_destroy(tpc_session* s) {
     cudaStreamSynchronize(s->stream);
     for (auto& ev : s->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : s->up_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
     delete s;
 }
 
@@ -333,16 +343,44 @@ static int adopt_records(tpc_session* s, const tpc_genome* g) {
     return 0;
 }
 
+// make the compute stream wait for the upload chunks that cover tiles [0, tile_end] (the kernels
+// read a few words past the end of a tile)
+static int wait_genome(tpc_session* s, uint64_t tile_end) {
+    while (s->up_waited < s->up_ev.size() && s->up_tile_begin[s->up_waited] <= tile_end) {
+        CK(cudaStreamWaitEvent(s->stream, s->up_ev[s->up_waited], 0));
+        ++s->up_waited;
+    }
+    return 0;
+}
+
 int tpc_session_set_genome_host(tpc_session* s, const tpc_genome* g) {
     if (!s || !g) return set_error("null argument");
     if (s->g.codes) return set_error("genome already set");
     uint64_t cw = tpc_code_words(g->n_positions), mw = tpc_mask_words(g->n_positions);
     CK(dev_alloc(&s->d_codes, cw * 8, s->stream));
     CK(dev_alloc(&s->d_nmask, mw * 8, s->stream));
-    CK(cudaMemcpyAsync(s->d_codes, g->codes, cw * 8, cudaMemcpyHostToDevice, s->stream));
-    CK(cudaMemcpyAsync(s->d_nmask, g->n_mask, mw * 8, cudaMemcpyHostToDevice, s->stream));
     s->g = GenomeView{s->d_codes, s->d_nmask, g->n_positions};
-    return adopt_records(s, g);
+    if (int rc = adopt_records(s, g)) return rc;
+    // Upload in position order on a second stream, one event per chunk: the first pass over the
+    // genome (k_bin / k_own, wave by wave) starts as soon as the chunks it reads have arrived.
+    if (!s->copy_stream) CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventRecord(s->ev[9], s->stream));                 // allocations are stream-ordered
+    CK(cudaStreamWaitEvent(s->copy_stream, s->ev[9], 0));
+    const uint64_t chunks = std::max<uint64_t>(1, std::min<uint64_t>(16, s->ntiles / 512));
+    for (uint64_t c = 0; c < chunks; ++c) {
+        uint64_t t0 = s->ntiles * c / chunks, t1 = s->ntiles * (c + 1) / chunks;
+        uint64_t c0 = t0 * kTileThreads, c1 = c + 1 == chunks ? cw : t1 * kTileThreads;
+        uint64_t m0 = t0 * (kTileThreads / 2), m1 = c + 1 == chunks ? mw : t1 * (kTileThreads / 2);
+        CK(cudaMemcpyAsync(s->d_codes + c0, g->codes + c0, (c1 - c0) * 8, cudaMemcpyHostToDevice, s->copy_stream));
+        CK(cudaMemcpyAsync(s->d_nmask + m0, g->n_mask + m0, (m1 - m0) * 8, cudaMemcpyHostToDevice, s->copy_stream));
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaEventRecord(e, s->copy_stream));
+        s->up_ev.push_back(e);
+        s->up_tile_begin.push_back(t0);
+    }
+    s->up_waited = 0;
+    return 0;
 }
 
 int tpc_session_set_genome_device(tpc_session* s, const tpc_genome* g) {
@@ -426,6 +464,7 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
             bool rebin = !(pass == 1 && nwaves == 1);           // one wave: the records serve both passes
             CK(cudaEventRecord(e0, s->stream));
             if (rebin) {
+                if (int wrc = wait_genome(s, t1)) return wrc;
                 CK(cudaMemsetAsync(s->d_bin_count, 0, (buckets + 1) * 8, s->stream));
                 CK(W_DISPATCH(s, bin(lc, s->g, kp, bv, t0, t1, base, s->d_stubmask)));  // stub mask doubles as ownership scratch
             }
@@ -482,6 +521,7 @@ int tpc_session_find_candidates(tpc_session* s) {
             CK(cudaMemsetAsync(s->d_hll, 0, 4u << kHllBits, s->stream));
             CK(cudaEventRecord(s->ev[0], s->stream));
         }
+        if (int wrc = wait_genome(s, s->ntiles)) return wrc;
         if (brc < 0) {
             CK(W_DISPATCH(s, fill(lc, s->g, s->d_filter, kp, s->ntiles, s->d_ctr)));
             CK(cudaEventRecord(s->ev[1], s->stream));
@@ -572,6 +612,7 @@ int tpc_session_local_junctions(tpc_session* s, const uint64_t** dev_words, uint
 
 int tpc_session_set_junctions(tpc_session* s, const uint64_t* dev_words_all, uint64_t n) {
     if (!s || !s->g.codes) return set_error("no genome set");
+    if (int wrc = wait_genome(s, s->ntiles)) return wrc;
     LaunchCtx lc = s->lctx();
     CK(cudaEventRecord(s->ev[5], s->stream));
     if (s->d_sorted) { CK(dev_free(s->d_sorted, s->stream)); s->d_sorted = nullptr; }
@@ -732,18 +773,63 @@ int tpc_session_run_to_count(tpc_session* s, uint64_t* image_bytes) {
     return 0;
 }
 
+// Emit the counted slice in `parts` tile ranges; after each range `on_part(byte_lo, byte_hi)` is
+// called with the image bytes that are now final on the device (the caller overlaps their transfer
+// with the emission of the next range).
+static int emit_write_parts(tpc_session* s, uint8_t* d_out, uint64_t image_bytes, uint32_t parts,
+                            const std::function<int(uint64_t, uint64_t)>& on_part) {
+    if (!s->have_count) return set_error("emit_count has not run");
+    LaunchCtx lc = s->lctx();
+    const uint64_t tb = s->slice_tile_begin, te = s->slice_tile_end, nt = te - tb;
+    const uint64_t unit_base = emit_prev_at(s, s->slice_pos_begin);
+    const uint64_t units = s->slice_records + emit_prev_at(s, s->slice_pos_end) - unit_base;
+    if (units * 12 > image_bytes) return set_error("output buffer too small: need %llu bytes", (unsigned long long)(units * 12));
+    parts = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(parts, nt));
+    // record prefix at the part boundaries (tiny device->host reads of the scanned tile counts)
+    std::vector<uint64_t> bt(parts + 1);
+    std::vector<unsigned long long> pref(parts + 1, 0);
+    for (uint32_t i = 0; i <= parts; ++i) {
+        bt[i] = tb + nt * i / parts;
+        CK(cudaMemcpyAsync(&pref[i], s->d_tile_rec + (bt[i] - tb), 8, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    KParams kp = s->kparams(0);
+    TableView J{s->d_J, s->J_log2, s->inline_keys()};
+    uint64_t byte_lo = 0;
+    for (uint32_t i = 0; i < parts; ++i) {
+        CK(W_DISPATCH(s, emit_write(lc, s->g, s->d_mask, s->d_stubmask, kp, J, s->rtable(), bt[i], bt[i + 1],
+                                    s->d_tile_rec + (bt[i] - tb), s->d_tile_stub + (bt[i] - tb), 0, 0, unit_base,
+                                    s->J_count + TPC_STUB_ID_OFFSET, (uint32_t*)d_out, units)));
+        uint64_t pos_hi = std::min<uint64_t>(bt[i + 1] * kTilePos, s->slice_pos_end);
+        uint64_t byte_hi = i + 1 == parts ? units * 12 : (pref[i + 1] + emit_prev_at(s, pos_hi) - unit_base) * 12;
+        if (int rc = on_part(byte_lo, byte_hi)) return rc;
+        byte_lo = byte_hi;
+    }
+    CK(cudaEventRecord(s->ev[8], s->stream));
+    s->st.occurrences = s->slice_records;
+    s->st.stubs = s->slice_stubs;
+    s->st.out_bytes = units * 12;
+    return 0;
+}
+
 int tpc_session_write_host(tpc_session* s, uint8_t* out_image, uint64_t image_bytes) {
     uint8_t* d_out = nullptr;
     CK(dev_alloc(&d_out, std::max<uint64_t>(image_bytes, 16), s->stream));
-    uint64_t off = 0, bytes = 0;
-    int rc = tpc_session_emit_write(s, 0, 0, d_out, image_bytes, &off, &bytes);
-    if (rc == 0 && bytes) {
-        cudaError_t e = cudaMemcpyAsync(out_image, d_out, bytes, cudaMemcpyDeviceToHost, s->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-        if (e != cudaSuccess) rc = set_error("CUDA error %s copying the image", cudaGetErrorName(e));
-    } else if (rc == 0) {
-        cudaStreamSynchronize(s->stream);
-    }
+    if (!s->copy_stream) CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    cudaEvent_t done;
+    CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    // device->host copy of part i (copy stream) overlaps the emission of part i+1 (compute stream)
+    int rc = emit_write_parts(s, d_out, image_bytes, 8, [&](uint64_t lo, uint64_t hi) -> int {
+        if (hi <= lo) return 0;
+        CK(cudaEventRecord(done, s->stream));
+        CK(cudaStreamWaitEvent(s->copy_stream, done, 0));
+        CK(cudaMemcpyAsync(out_image + lo, d_out + lo, hi - lo, cudaMemcpyDeviceToHost, s->copy_stream));
+        return 0;
+    });
+    cudaError_t e = cudaStreamSynchronize(s->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess && rc == 0) rc = set_error("CUDA error %s copying the image", cudaGetErrorName(e));
+    cudaEventDestroy(done);
     dev_free(d_out, s->stream);
     return rc;
 }
