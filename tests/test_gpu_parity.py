@@ -385,3 +385,16 @@ def test_position_identified_slots_for_short_k(name, golden, monkeypatch):
         recs = api.read_fasta(paths)
     img, st = api.junctions_host(api.pack_records(recs), k=spec["k"], filter_bits=spec.get("f", 24), q=spec.get("q", 5))
     assert canon_md5(bytes(img)) == g["canon_md5"] and st.junctions == g["distinct_junctions"]
+
+
+@pytest.mark.parametrize("name", ["family_k25", "family_k63"])
+def test_undersized_candidate_table_grows_and_redoes(name, golden, monkeypatch):
+    """The candidate table is sized from a HyperLogLog estimate; exactness must not depend on it:
+    a table started 64x too small overflows, is doubled and the insert pass redone until it fits."""
+    monkeypatch.setenv("TPC_TABLE_SHRINK", "6")
+    spec, g = CASES[name], golden[name]
+    with case_files(spec) as (paths, _, _):
+        recs = api.read_fasta(paths)
+    img, st = api.junctions_host(api.pack_records(recs), k=spec["k"], filter_bits=14, q=2)   # many false candidates
+    assert canon_md5(bytes(img)) == g["canon_md5"] and st.junctions == g["distinct_junctions"]
+    assert st.candidate_kmers > 2 * st.junctions

@@ -541,6 +541,7 @@ int tpc_session_find_candidates(tpc_session* s) {
         double est = hll_estimate(hll);
         if (est > (double)marks_r) est = (double)marks_r;
         uint32_t lg = std::max<uint32_t>(ceil_log2((uint64_t)(est * 1.15 * 2.0) + 64), 10);
+        if (const char* e = getenv("TPC_TABLE_SHRINK")) lg = std::max<int>(4, (int)lg - atoi(e));  // tests: force the grow-and-redo path
         for (;;) {
             uint64_t avail = available_bytes(s->device) + s->T_bytes;
             uint64_t need = sizeof(Slot) << lg;
