@@ -196,6 +196,7 @@ template <int W>
 __global__ void __launch_bounds__(kTileThreads)
 k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t ntiles, TableView T, Counters* ctr) {
     const uint64_t capmask = (1ull << T.log2cap) - 1;
+    const uint64_t probe_limit = capmask < 8192 ? capmask : 8192;  // a longer run means the table is too full: host grows it
     unsigned long long claimed = 0;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         uint64_t w = tile * kTileThreads + threadIdx.x;
@@ -219,7 +220,7 @@ k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t n
             if (W == 1 && T.inline_keys) {
                 const unsigned long long key1 = (o.fwd ? o.X.w[0] : o.Y.w[0]) + 1ull;
                 const unsigned long long fresh_meta = want | ((unsigned long long)p << kInlinePosShift);
-                for (uint64_t probe = 0; probe <= capmask; ++probe, idx = (idx + 1) & capmask) {
+                for (uint64_t probe = 0; probe <= probe_limit; ++probe, idx = (idx + 1) & capmask) {
                     Slot* cand = T.slots + idx;
                     ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(cand));
                     if (v.x == 0) {
@@ -240,7 +241,7 @@ k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t n
                 (void)fresh_meta;
             } else {
                 unsigned long long mine = hash_tag(o.h) | p;
-                for (uint64_t probe = 0; probe <= capmask; ++probe, idx = (idx + 1) & capmask) {
+                for (uint64_t probe = 0; probe <= probe_limit; ++probe, idx = (idx + 1) & capmask) {
                     Slot* cand = T.slots + idx;
                     ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(cand));
                     unsigned long long rep = v.x;
