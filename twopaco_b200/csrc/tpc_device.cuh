@@ -90,15 +90,6 @@ __device__ __forceinline__ uint64_t top_mask(uint32_t k) {
     return (~0ull) >> (64 - bits);
 }
 
-// 64 consecutive 2-bit... no: 32 bases (64 bits) starting at position p
-__device__ __forceinline__ uint64_t load_bases32(const uint64_t* __restrict__ codes, uint64_t p) {
-    uint64_t wi = p >> 5;
-    uint32_t sh = 2 * (uint32_t)(p & 31);
-    uint64_t lo = __ldg(codes + wi);
-    uint64_t hi = __ldg(codes + wi + 1);
-    return (lo >> sh) | ((hi << 1) << (63 - sh));
-}
-
 __device__ __forceinline__ uint32_t load_base(const uint64_t* __restrict__ codes, uint64_t p) {
     return (uint32_t)(__ldg(codes + (p >> 5)) >> (2 * (p & 31))) & 3u;
 }
@@ -321,13 +312,6 @@ __device__ __forceinline__ Neigh orient(bool fwd_is_canon, uint32_t prv, uint32_
     Neigh r;
     if (fwd_is_canon) { r.a = prv; r.a_n = prv_n; r.b = nxt; r.b_n = nxt_n; }
     else { r.a = 3u - nxt; r.a_n = nxt_n; r.b = 3u - prv; r.b_n = prv_n; }
-    return r;
-}
-
-__device__ __forceinline__ uint4 ld_nc_v4(const uint32_t* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 

@@ -219,7 +219,6 @@ k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t n
             unsigned long long meta = 0;
             if (W == 1 && T.inline_keys) {
                 const unsigned long long key1 = (o.fwd ? o.X.w[0] : o.Y.w[0]) + 1ull;
-                const unsigned long long fresh_meta = want | ((unsigned long long)p << kInlinePosShift);
                 for (uint64_t probe = 0; probe <= probe_limit; ++probe, idx = (idx + 1) & capmask) {
                     Slot* cand = T.slots + idx;
                     ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(cand));
@@ -238,7 +237,6 @@ k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t n
                     if (old == meta) break;
                     meta = old;
                 }
-                (void)fresh_meta;
             } else {
                 unsigned long long mine = hash_tag(o.h) | p;
                 for (uint64_t probe = 0; probe <= probe_limit; ++probe, idx = (idx + 1) & capmask) {
