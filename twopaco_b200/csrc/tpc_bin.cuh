@@ -227,9 +227,28 @@ k_own(GenomeView g, KParams kp, uint64_t word_begin, uint64_t word_end, uint32_t
 }
 
 constexpr int kBinListMax = kTilePos;
+constexpr int kTileCodeWords = kTileThreads + 8;        // tile + one word before + read-ahead (k <= 127)
+constexpr int kTileMaskWords = kTileThreads / 2 + 4;
 // R = records per thread per staging round (stage = 256 R records); small R = more CTAs per SM
 constexpr size_t bin_list_smem_bytes(int R) {
-    return kBinMaxBuckets * 8 + kBinMaxBuckets * 4 * 2 + 8 * 4 + 16 + (size_t)kTileThreads * R * 4 * 3 + kBinListMax * 2;
+    return kBinMaxBuckets * 8 + kBinMaxBuckets * 4 * 2 + 8 * 4 + 16 + (size_t)kTileThreads * R * (4 * 3 + 1) + kBinListMax * 2 +
+           (kTileCodeWords + kTileMaskWords) * 8;
+}
+
+// k-mer at tile-local position lp (position lp of a window whose word 0 is `words[0]`) out of shared memory
+template <int W>
+__device__ __forceinline__ Kmer<W> extract_kmer_smem(const uint64_t* words, uint32_t lp, uint32_t k) {
+    Kmer<W> x;
+    const uint32_t wi = lp >> 5, sh = 2 * (lp & 31);
+    uint64_t lo = words[wi];
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        uint64_t hi = words[wi + j + 1];
+        x.w[j] = (lo >> sh) | ((hi << 1) << (63 - sh));
+        lo = hi;
+    }
+    x.w[W - 1] &= top_mask<W>(k);
+    return x;
 }
 
 template <int W, int R>
@@ -239,7 +258,9 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
     constexpr uint32_t kStage = kTileThreads * R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* gbase = reinterpret_cast<unsigned long long*>(smem_raw);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(gbase + kBinMaxBuckets);
+    uint64_t* s_codes = reinterpret_cast<uint64_t*>(gbase + kBinMaxBuckets);   // words tw0-1 .. of the tile
+    uint64_t* s_nmask = s_codes + kTileCodeWords;                              // words (tw0-1)/2 .. (64 positions each)
+    uint32_t* hist = reinterpret_cast<uint32_t*>(s_nmask + kTileMaskWords);
     uint32_t* pref = hist + kBinMaxBuckets;
     uint32_t* warp_tot = pref + kBinMaxBuckets;
     uint32_t* list_total = warp_tot + 8;
@@ -247,12 +268,15 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
     uint32_t* st_b = st_a + kStage;
     uint32_t* st_c = st_b + kStage;
     uint16_t* list = reinterpret_cast<uint16_t*>(st_c + kStage);
-    const uint32_t nbuckets = 1u << bin.bucket_bits;
+    uint8_t* st_k = reinterpret_cast<uint8_t*>(list + kBinListMax);           // slice of each staged record
     const uint32_t sib_mask = (1u << bin.sib_bits) - 1u;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     for (uint64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         uint32_t own = __ldcs(own_mask + tile * kTileThreads + tid);
+        const uint64_t tw0 = tile * kTileThreads;              // first code word of the tile
+        const uint64_t cw_base = tw0 ? tw0 - 1 : 0;            // s_codes[0] = word cw_base
+        const uint64_t mw_base = cw_base >> 1;                 // s_nmask[0] = word mw_base
         // CTA-wide list of owned positions (tile-relative, in position order)
         uint32_t cnt = __popc(own), incl = cnt;
 #pragma unroll
@@ -260,8 +284,11 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
             uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        __syncthreads();  // previous tile's readers of list / warp_tot are done
+        __syncthreads();  // previous tile's readers of list / warp_tot / s_codes are done
         if (lane == 31) warp_tot[wid] = incl;
+        // stage the tile's slice of the packed genome (coalesced) for the dense phase
+        for (int j = tid; j < kTileCodeWords; j += kTileThreads) s_codes[j] = __ldg(g.codes + cw_base + j);
+        for (int j = tid; j < kTileMaskWords; j += kTileThreads) s_nmask[j] = __ldg(g.nmask + mw_base + j);
         __syncthreads();
         uint32_t off = incl - cnt;
         for (int j = 0; j < wid; ++j) off += warp_tot[j];
@@ -273,6 +300,9 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
         }
         __syncthreads();
         const uint32_t total = *list_total;
+        const uint32_t c_off = (uint32_t)(tw0 - cw_base) * 32;          // tile-local -> s_codes-local position
+        const uint32_t m_off = (uint32_t)(tw0 * 32 - mw_base * 64);     // tile-local -> s_nmask-local position
+        const uint64_t tile_rel = tile * kTilePos - wave_base;
 
         // dense processing of the list, kStage records per round
         for (uint32_t c0 = 0; c0 < total; c0 += kStage) {
@@ -285,13 +315,20 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
                 const uint32_t e = tid + j * kTileThreads;
                 rk[j] = ~0u; rm[j] = 0; rw[j] = 0;
                 if (e < n) {
-                    const uint64_t p = tile * kTilePos + list[c0 + e];
-                    Occ<W> o = occurrence_at<W>(g, p, kp);
-                    uint32_t code = load_base(g.codes, p - 1) | (load_base(g.codes, p + kp.k) << 3) | (o.fwd ? 64u : 0u) |
-                                    (load_n(g.nmask, p - 1) << 2) | (load_n(g.nmask, p + kp.k) << 5);
-                    const uint64_t s = hash_sector(o.h, kp.sector_shift);
-                    const uint64_t rel64 = p - wave_base;
-                    rm[j] = mask_seed(o.h);
+                    const uint32_t tp = list[c0 + e];                // tile-local position (>= 1 when tile 0: position 0 is N)
+                    const uint32_t lp = tp + c_off;
+                    Kmer<W> X = extract_kmer_smem<W>(s_codes, lp, kp.k);
+                    Kmer<W> Y = revcomp<W>(X, kp.k);
+                    const bool fwd = kmer_less<W>(X, Y);
+                    const uint64_t h = kmer_hash<W>(kmer_select<W>(fwd, X, Y), kp.seed);
+                    const uint32_t pp = lp - 1, np = lp + kp.k, pm = tp + m_off - 1, nm = tp + m_off + kp.k;
+                    uint32_t code = ((uint32_t)(s_codes[pp >> 5] >> (2 * (pp & 31))) & 3u) |
+                                    (((uint32_t)(s_codes[np >> 5] >> (2 * (np & 31))) & 3u) << 3) | (fwd ? 64u : 0u) |
+                                    (((uint32_t)(s_nmask[pm >> 6] >> (pm & 63)) & 1u) << 2) |
+                                    (((uint32_t)(s_nmask[nm >> 6] >> (nm & 63)) & 1u) << 5);
+                    const uint64_t s = hash_sector(h, kp.sector_shift);
+                    const uint64_t rel64 = tile_rel + tp;
+                    rm[j] = mask_seed(h);
                     rw[j] = ((uint32_t)s & sib_mask) | ((uint32_t)(rel64 >> 32) << bin.sib_bits) | (code << kBinCodeShift);
                     const uint32_t bucket = (uint32_t)(s >> bin.sib_bits);
                     rk[j] = (bucket << 16) | atomicAdd(&hist[bucket], 1u);
@@ -317,29 +354,24 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
                     uint32_t idx = pref[rk[j] >> 16] + (rk[j] & 0xFFFFu);
                     st_a[idx] = rm[j];
                     st_b[idx] = rw[j];
-                    st_c[idx] = (uint32_t)(tile * kTilePos + list[c0 + tid + j * kTileThreads] - wave_base);
+                    st_c[idx] = (uint32_t)(tile_rel + list[c0 + tid + j * kTileThreads]);
+                    st_k[idx] = (uint8_t)(rk[j] >> 16);
                 }
             }
             __syncthreads();
-            for (uint32_t b = wid; b < nbuckets; b += kTileThreads / 32) {
-                uint32_t nb = hist[b];
-                if (!nb) continue;
-                uint32_t s0 = pref[b];
-                unsigned long long gb = gbase[b];
-                uint32_t* ra = bin.rec + (uint64_t)b * 3 * bin.cap;
-                for (uint32_t j = lane; j < nb; j += 32) {
-                    unsigned long long dst = gb + j;
-                    if (dst < bin.cap) {
-                        __stcs(ra + dst, st_a[s0 + j]);
-                        __stcs(ra + bin.cap + dst, st_b[s0 + j]);
-                        __stcs(ra + 2 * bin.cap + dst, st_c[s0 + j]);
-                    } else {
-                        unsigned long long o = atomicAdd(bin.ov_count, 1ull);
-                        if (o < bin.ov_cap) {
-                            uint4 r = make_uint4(st_a[s0 + j], st_b[s0 + j], st_c[s0 + j], b);
-                            reinterpret_cast<uint4*>(bin.ov)[o] = r;
-                        }
-                    }
+            // copy-out: one thread per staged record (records of a slice are contiguous in the stage, so
+            // neighbouring threads write neighbouring words of the slice's arrays)
+            for (uint32_t idx = tid; idx < n; idx += kTileThreads) {
+                const uint32_t b = st_k[idx];
+                const unsigned long long dst = gbase[b] + (idx - pref[b]);
+                if (dst < bin.cap) {
+                    uint32_t* ra = bin.rec + (uint64_t)b * 3 * bin.cap + dst;
+                    __stcs(ra, st_a[idx]);
+                    __stcs(ra + bin.cap, st_b[idx]);
+                    __stcs(ra + 2 * bin.cap, st_c[idx]);
+                } else {
+                    unsigned long long o = atomicAdd(bin.ov_count, 1ull);
+                    if (o < bin.ov_cap) reinterpret_cast<uint4*>(bin.ov)[o] = make_uint4(st_a[idx], st_b[idx], st_c[idx], b);
                 }
             }
             __syncthreads();
