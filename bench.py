@@ -257,8 +257,18 @@ def main() -> None:
     dom_ms, dom_bytes = kernels[dom]
     gbps = lambda ms, nbytes: round(nbytes / (ms * 1e-3) / 1e9, 1) if ms > 0 else None
     achieved = gbps(dom_ms, dom_bytes) or 0.0
+    # DRAM traffic of that kernel: measured once per round with `ncu --set full` on the C2 workload
+    # (profiles/r*_traffic_c2.json: dram__bytes_read.sum + dram__bytes_write.sum per launch); reported here as
+    # measured-traffic/algorithmic-bytes ratio of that capture x this run's algorithmic bytes.
+    traffic, traffic_src = None, None
+    for f in sorted((ROOT / "profiles").glob("r*_traffic_c2.json"), reverse=True):
+        ratio = json.loads(f.read_text())["kernels"].get(dom, {}).get("traffic_over_algorithmic")
+        if ratio:
+            traffic, traffic_src = ratio * dom_bytes, f"{f.name}: ncu DRAM bytes / algorithmic bytes = {ratio} (C2 capture), scaled to this workload"
+        break
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "peak_source": "measured" if peaks else "fallback", "traffic": None,
+                "frac": round(achieved / peak, 4), "peak_source": "measured" if peaks else "fallback", "traffic": traffic,
+                "traffic_source": traffic_src,
                 "algorithmic_bytes_per_step": dom_bytes, "ms_per_step": round(dom_ms, 3),
                 "filter_path": "binned (L2-resident slices)" if st.bin_waves else "direct (random HBM sectors)",
                 "filter_touches_per_s_G": {k: round(recs / (v[0] * 1e-3) / 1e9, 2) for k, v in kernels.items()
