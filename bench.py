@@ -142,7 +142,8 @@ class Runner:
         from twopaco_b200 import dist as tdist
         if self.session is not None:
             self.session.close()
-        s = api.Session(k=wl["k"], filter_bits=wl["f"], q=wl["q"], shard_index=self.rank, shard_count=self.world)
+        s = api.Session(k=wl["k"], filter_bits=wl["f"], q=wl["q"], rounds=wl.get("rounds", 1),
+                        shard_index=self.rank, shard_count=self.world)
         self.session = s
         dg.attach(s)
         self.last, self.out = tdist.sharded_run(s, dg, self.rank, self.world, self.out)
@@ -159,8 +160,11 @@ def main() -> None:
     ap.add_argument("--sim-world", type=int, default=0,
                     help="kernel tuning aid: time only pass 1+2 of shard 0 of N on ONE GPU (not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rounds", type=int, default=0, help="-r of the run (default: the workload's, 1)")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.rounds:
+        wl["rounds"] = args.rounds
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TPC_ABI_VERSION 1
+#define TPC_ABI_VERSION 2
 #define TPC_INVALID_VERTEX INT64_MAX          /* src/graphconstructor/common.cpp:5 */
 #define TPC_SEPARATOR_POS 0xFFFFFFFFu         /* src/common/junctionapi.h:36-37 */
 #define TPC_MAX_K 127                         /* 4 x 64-bit words per packed k-mer in this build
@@ -65,6 +65,9 @@ typedef struct tpc_stats {
     uint32_t kernel_launches;    /* kernels of this library launched by the call              */
     uint32_t bin_waves;          /* binned path: waves of records per pass (1 = records shared by
                                     fill and query); 0 = direct path                             */
+    uint32_t sub_rounds;         /* hash sub-ranges per -r round chosen so that one round's records
+                                    fit HBM in one wave (1 = none); unobservable in the output    */
+    uint32_t reserved0;
 } tpc_stats;
 
 /* ------------------------------------------------------------------------------------------

@@ -359,6 +359,47 @@ def test_binned_rounds_and_shards(monkeypatch, golden):
     assert bytes(img) == ref   # (falls back to the direct kernels when the overflow area is exceeded)
 
 
+@pytest.mark.parametrize("sub,user_rounds", [(2, 1), (3, 1), (5, 2), (9, 2)])
+@pytest.mark.parametrize("name", ["family_k25", "family_k63", "family_k127", "selftest_s3_k9", "family_seam_k25"])
+def test_sub_rounds_share_one_ownership_scan(name, sub, user_rounds, golden, monkeypatch):
+    """Sub-rounds (automatic when one round's records do not fit HBM; forced here): the ownership of all
+    the rounds of a GPU comes from ONE k_own scan as bit planes (2, 2, 4 planes; 18 rounds: one scan per
+    round).  Like -r, the split must not change the result."""
+    spec, g = CASES[name], golden[name]
+    monkeypatch.setenv("TPC_FILTER_MODE", "binned")
+    monkeypatch.setenv("TPC_SLICE_LOG2", "12")
+    monkeypatch.setenv("TPC_SUBROUNDS", str(sub))
+    with case_files(spec) as (paths, _, _):
+        recs = api.read_fasta(paths)
+    img, st = api.junctions_host(api.pack_records(recs), k=spec["k"], filter_bits=20, q=4, rounds=user_rounds)
+    assert st.ms_bin > 0 and st.sub_rounds == sub
+    assert canon_md5(bytes(img)) == g["canon_md5"] and st.junctions == g["distinct_junctions"]
+
+
+def test_sub_rounds_direct_path_and_shards(monkeypatch, golden):
+    """Sub-rounds on the direct kernels (ownership decided inline) and combined with hash-range shards."""
+    import torch
+    spec, g = CASES["family_k25"], golden["family_k25"]
+    with case_files(spec) as (paths, _, _):
+        recs = api.read_fasta(paths)
+    gen = api.pack_records(recs)
+    monkeypatch.setenv("TPC_SUBROUNDS", "3")
+    monkeypatch.setenv("TPC_FILTER_MODE", "direct")
+    img, st = api.junctions_host(gen, k=25, filter_bits=18, q=3)
+    assert st.ms_bin == 0 and canon_md5(bytes(img)) == g["canon_md5"]
+    monkeypatch.setenv("TPC_FILTER_MODE", "binned")
+    monkeypatch.setenv("TPC_SLICE_LOG2", "12")
+    total = 0
+    for i in range(2):
+        s = api.Session(k=25, filter_bits=20, shard_index=i, shard_count=2)
+        s.set_genome_host(gen)
+        s.find_candidates()
+        total += s.local_junctions()[1]
+        assert s.stats().sub_rounds == 3
+        s.close()
+    assert total == g["distinct_junctions"]
+
+
 def test_multi_gpu_torchrun():
     """N > 1: hash-range shards over NCCL (skipped on single-GPU boxes)."""
     import subprocess

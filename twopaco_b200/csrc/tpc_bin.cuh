@@ -33,10 +33,7 @@ struct BinView {
     uint32_t q;                    // Bloom bits per edge (the apply kernels expand the mask seed)
 };
 
-// occurrence code (7 bits): prev base | prev is N << 2 | next base << 3 | next is N << 5 | forward strand is canonical << 6
-__device__ __forceinline__ Neigh decode_occurrence(uint32_t c) {
-    return orient((c >> 6) & 1u, c & 3u, (c >> 3) & 3u, (c >> 2) & 1u, (c >> 5) & 1u);
-}
+// record word 1 carries the 6-bit occurrence code in canonical orientation (occurrence_code, tpc_device.cuh)
 
 template <int W>
 __global__ void __launch_bounds__(kTileThreads, 2)
@@ -96,8 +93,9 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
                     {   // (k_bin runs unsharded rounds only: every definite k-mer is owned)
                         const uint64_t h = kmer_hash<W>(canon, kp.seed);
                         const uint64_t s = hash_sector(h, kp.sector_shift);
-                        uint32_t code = prv | (nxt << 3) | (fwd ? 64u : 0u);
-                        if (any_n) code |= (((win.prev_n >> i) & 1u) << 2) | (((win.next_n >> i) & 1u) << 5);
+                        uint32_t pn = 0, nn = 0;
+                        if (any_n) { pn = (win.prev_n >> i) & 1u; nn = (win.next_n >> i) & 1u; }
+                        const uint32_t code = occurrence_code(fwd, prv, nxt, pn, nn);
                         rm[j] = mask_seed(h);
                         rw[j] = ((uint32_t)s & sib_mask) | relhigh | (code << kBinCodeShift);
                         const uint32_t bucket = (uint32_t)(s >> bin.sib_bits);
@@ -161,15 +159,18 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
 
 // ---- sharded variant (nparts > 1): ownership is sparse (1/nparts of the positions).
 // k_own decides ownership of EVERY position with as few instructions as possible (cheap fold of
-// the canonical k-mer, high occupancy) and writes 1 bit per position; k_bin_list compacts the
-// owned positions of a tile into a CTA-wide list and runs the expensive part (64-bit hash, record,
-// counting sort by slice) densely on it.
-template <int W>
+// the canonical k-mer, high occupancy); k_bin_list compacts the owned positions of a tile into a
+// CTA-wide list and runs the expensive part (64-bit hash, record, counting sort by slice) densely
+// on it.  One scan serves all the rounds of this GPU: the local round that owns a position
+// (1 + round, 0 = none / not a definite k-mer) is written as P bit planes of 1 bit per position.
+template <int W, int P>
 __global__ void __launch_bounds__(kTileThreads)
-k_own(GenomeView g, KParams kp, uint64_t word_begin, uint64_t word_end, uint32_t* __restrict__ own_mask) {
+k_own(GenomeView g, KParams kp, uint32_t part_base, uint32_t nlocal, uint64_t word_begin, uint64_t word_end, OwnPlanes op) {
     for (uint64_t w = word_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < word_end;
          w += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t own = 0;
+        uint32_t pl[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) pl[j] = 0;
         if (w * 32 < g.npos) {
             if (W == 1) {
                 // k <= 31: every k-mer of this thread lies inside two code words; extract both strands
@@ -200,9 +201,16 @@ k_own(GenomeView g, KParams kp, uint64_t word_begin, uint64_t word_end, uint32_t
                     const uint64_t y = (i ? ((r_lo >> (64 - 2 * i)) | (r_hi << (2 * i))) : r_hi) & kmask;
                     Kmer<1> canon;
                     canon.w[0] = x < y ? x : y;
-                    own |= (owner_part(owner_fold<1>(canon), kp.nparts) == kp.part ? 1u : 0u) << i;
+                    const uint32_t local = owner_part(owner_fold<1>(canon), kp.nparts) - part_base;
+                    if (P == 1) pl[0] |= (local < nlocal ? 1u : 0u) << i;
+                    else {
+                        const uint32_t id = local < nlocal ? local + 1u : 0u;
+#pragma unroll
+                        for (int j = 0; j < P; ++j) pl[j] |= ((id >> j) & 1u) << i;
+                    }
                 }
-                own &= valid;
+#pragma unroll
+                for (int j = 0; j < P; ++j) pl[j] &= valid;
             } else {
                 Window<W> win;
                 win.load(g, w, kp.k);
@@ -214,47 +222,31 @@ k_own(GenomeView g, KParams kp, uint64_t word_begin, uint64_t word_end, uint32_t
                         nf >>= 2;
                         if ((win.valid >> i) & 1u) {
                             bool fwd = kmer_less<W>(win.X, win.Y);
-                            uint32_t part = owner_part(owner_fold<W>(kmer_select<W>(fwd, win.X, win.Y)), kp.nparts);
-                            own |= (part == kp.part ? 1u : 0u) << i;
+                            const uint32_t local = owner_part(owner_fold<W>(kmer_select<W>(fwd, win.X, win.Y)), kp.nparts) - part_base;
+                            const uint32_t id = local < nlocal ? local + 1u : 0u;
+#pragma unroll
+                            for (int j = 0; j < P; ++j) pl[j] |= ((id >> j) & 1u) << i;
                         }
                         roll<W>(win.X, win.Y, nxt, kp.k);
                     }
                 }
             }
         }
-        own_mask[w] = own;
+#pragma unroll
+        for (int j = 0; j < P; ++j) op.p[j][w] = pl[j];
     }
 }
 
 constexpr int kBinListMax = kTilePos;
-constexpr int kTileCodeWords = kTileThreads + 8;        // tile + one word before + read-ahead (k <= 127)
-constexpr int kTileMaskWords = kTileThreads / 2 + 4;
 // R = records per thread per staging round (stage = 256 R records); small R = more CTAs per SM
 constexpr size_t bin_list_smem_bytes(int R) {
     return kBinMaxBuckets * 8 + kBinMaxBuckets * 4 * 2 + 8 * 4 + 16 + (size_t)kTileThreads * R * (4 * 3 + 1) + kBinListMax * 2 +
            (kTileCodeWords + kTileMaskWords) * 8;
 }
 
-// k-mer at tile-local position lp (position lp of a window whose word 0 is `words[0]`) out of shared memory
-template <int W>
-__device__ __forceinline__ Kmer<W> extract_kmer_smem(const uint64_t* words, uint32_t lp, uint32_t k) {
-    Kmer<W> x;
-    const uint32_t wi = lp >> 5, sh = 2 * (lp & 31);
-    uint64_t lo = words[wi];
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-        uint64_t hi = words[wi + j + 1];
-        x.w[j] = (lo >> sh) | ((hi << 1) << (63 - sh));
-        lo = hi;
-    }
-    x.w[W - 1] &= top_mask<W>(k);
-    return x;
-}
-
 template <int W, int R>
 __global__ void __launch_bounds__(kTileThreads, (R <= 8 ? 3 : 2))
-k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_end, uint64_t wave_base,
-           const uint32_t* __restrict__ own_mask) {
+k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_end, uint64_t wave_base, OwnPlanes op) {
     constexpr uint32_t kStage = kTileThreads * R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* gbase = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -273,7 +265,7 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     for (uint64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
-        uint32_t own = __ldcs(own_mask + tile * kTileThreads + tid);
+        uint32_t own = own_word(op, tile * kTileThreads + tid);
         const uint64_t tw0 = tile * kTileThreads;              // first code word of the tile
         const uint64_t cw_base = tw0 ? tw0 - 1 : 0;            // s_codes[0] = word cw_base
         const uint64_t mw_base = cw_base >> 1;                 // s_nmask[0] = word mw_base
@@ -322,10 +314,10 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
                     const bool fwd = kmer_less<W>(X, Y);
                     const uint64_t h = kmer_hash<W>(kmer_select<W>(fwd, X, Y), kp.seed);
                     const uint32_t pp = lp - 1, np = lp + kp.k, pm = tp + m_off - 1, nm = tp + m_off + kp.k;
-                    uint32_t code = ((uint32_t)(s_codes[pp >> 5] >> (2 * (pp & 31))) & 3u) |
-                                    (((uint32_t)(s_codes[np >> 5] >> (2 * (np & 31))) & 3u) << 3) | (fwd ? 64u : 0u) |
-                                    (((uint32_t)(s_nmask[pm >> 6] >> (pm & 63)) & 1u) << 2) |
-                                    (((uint32_t)(s_nmask[nm >> 6] >> (nm & 63)) & 1u) << 5);
+                    const uint32_t code = occurrence_code(fwd, (uint32_t)(s_codes[pp >> 5] >> (2 * (pp & 31))) & 3u,
+                                                          (uint32_t)(s_codes[np >> 5] >> (2 * (np & 31))) & 3u,
+                                                          (uint32_t)(s_nmask[pm >> 6] >> (pm & 63)) & 1u,
+                                                          (uint32_t)(s_nmask[nm >> 6] >> (nm & 63)) & 1u);
                     const uint64_t s = hash_sector(h, kp.sector_shift);
                     const uint64_t rel64 = tile_rel + tp;
                     rm[j] = mask_seed(h);

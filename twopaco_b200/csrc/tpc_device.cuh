@@ -229,9 +229,11 @@ __device__ __forceinline__ uint64_t hash_slot(uint64_t h, uint32_t log2cap) {
 __device__ __forceinline__ uint32_t mask_seed(uint64_t h) {  // 32 hash bits the Bloom mask derives from
     return (uint32_t)h ^ ((uint32_t)(h >> 32) * 0x85EBCA77u);
 }
+// The seed already is 32 mixed hash bits, so the Q bit positions are simply its 5-bit fields (one
+// shift + one wrapping shift + a shared OR per field); a second word is derived only for Q > 6.
 template <int Q>
 __device__ __forceinline__ uint32_t mask_from_seed(uint32_t seed32) {
-    uint32_t g = fmix32(seed32);
+    uint32_t g = seed32;
     uint32_t m = 0;
 #pragma unroll
     for (int t = 0; t < Q; ++t) {
@@ -241,13 +243,16 @@ __device__ __forceinline__ uint32_t mask_from_seed(uint32_t seed32) {
     return m;
 }
 __device__ __forceinline__ uint32_t mask_from_seed_rt(uint32_t seed32, uint32_t q) {  // same bits, run-time q
-    uint32_t g = fmix32(seed32);
-    uint32_t m = 0;
-    for (uint32_t t = 0; t < q; ++t) {
-        if (t == 6) g = g * 0x9E3779B1u + 0x7F4A7C15u, g ^= g >> 15;
-        m |= 1u << ((g >> (5 * (t % 6))) & 31u);
+    switch (q) {
+        case 1: return mask_from_seed<1>(seed32);
+        case 2: return mask_from_seed<2>(seed32);
+        case 3: return mask_from_seed<3>(seed32);
+        case 4: return mask_from_seed<4>(seed32);
+        case 5: return mask_from_seed<5>(seed32);
+        case 6: return mask_from_seed<6>(seed32);
+        case 7: return mask_from_seed<7>(seed32);
+        default: return mask_from_seed<8>(seed32);
     }
-    return m;
 }
 template <int Q>
 __device__ __forceinline__ uint32_t vertex_mask(uint64_t h) {
@@ -313,6 +318,14 @@ __device__ __forceinline__ Neigh orient(bool fwd_is_canon, uint32_t prv, uint32_
     if (fwd_is_canon) { r.a = prv; r.a_n = prv_n; r.b = nxt; r.b_n = nxt_n; }
     else { r.a = 3u - nxt; r.a_n = nxt_n; r.b = 3u - prv; r.b_n = prv_n; }
     return r;
+}
+
+// 6-bit occurrence code in canonical orientation: a | a_n << 2 | b << 3 | b_n << 5
+__device__ __forceinline__ uint32_t occurrence_code(bool fwd_is_canon, uint32_t prv, uint32_t nxt, uint32_t prv_n, uint32_t nxt_n) {
+    const uint32_t f = (prv | (prv_n << 2)) | ((nxt | (nxt_n << 2)) << 3);
+    const uint32_t x = f ^ 27u;                       // complement both bases
+    const uint32_t r = ((x >> 3) | (x << 3)) & 63u;   // and swap the sides
+    return fwd_is_canon ? f : r;
 }
 
 // One whole 32-byte filter sector with ONE 256-bit load (sm_100: LDG.E.256): a random sector per

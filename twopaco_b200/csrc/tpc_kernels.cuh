@@ -20,6 +20,7 @@
 // reference); only "no false negatives" matters, which holds by construction.
 #pragma once
 #include "tpc_device.cuh"
+#include "tpc_tile.cuh"
 
 namespace tpc {
 
@@ -53,30 +54,45 @@ __device__ __forceinline__ uint32_t filter_set(uint32_t* word, uint32_t cur, uin
     return 0;
 }
 
-// Record the in-edge and the out-edge of one occurrence in the vertex's sector (one 256-bit load,
-// test, then atomicOr only on the words that miss bits).  An 'N' neighbour is unique: make every
-// occurrence of this k-mer a candidate by recording two distinct dummy edges (h:1044-1058).
-__device__ __forceinline__ uint32_t fill_vertex(uint32_t* sec, uint32_t m, const Neigh& nb) {
-    Sector s = ld_sector_cg(sec);
+// Record the in-edge and the out-edge of one occurrence in the vertex's sector (already loaded with one
+// 256-bit load): test, then atomicOr only on the words that miss bits.  `code` is the occurrence code
+// in canonical orientation (occurrence_code).  An 'N' neighbour is unique: make every occurrence of
+// this k-mer a candidate by recording two distinct dummy edges (h:1044-1058).
+__device__ __forceinline__ uint32_t fill_sector(uint32_t* sec, const Sector& s, uint32_t m, uint32_t code) {
+    const uint32_t a = code & 3u, b = (code >> 3) & 3u;
     uint32_t fresh = 0;
-    if (!nb.a_n) fresh += filter_set(sec + nb.a, pick4(s.w[0], s.w[1], s.w[2], s.w[3], nb.a), m);
+    if ((code & 0x24u) == 0) {  // no 'N' neighbour (all but a few occurrences)
+        fresh += filter_set(sec + a, pick4(s.w[0], s.w[1], s.w[2], s.w[3], a), m);
+        fresh += filter_set(sec + 4 + b, pick4(s.w[4], s.w[5], s.w[6], s.w[7], b), m);
+        return fresh;
+    }
+    if (!(code & 4u)) fresh += filter_set(sec + a, pick4(s.w[0], s.w[1], s.w[2], s.w[3], a), m);
     else { fresh += filter_set(sec + 0, s.w[0], m); fresh += filter_set(sec + 3, s.w[3], m); }
-    if (!nb.b_n) fresh += filter_set(sec + 4 + nb.b, pick4(s.w[4], s.w[5], s.w[6], s.w[7], nb.b), m);
+    if (!(code & 32u)) fresh += filter_set(sec + 4 + b, pick4(s.w[4], s.w[5], s.w[6], s.w[7], b), m);
     else { fresh += filter_set(sec + 4, s.w[4], m); fresh += filter_set(sec + 7, s.w[7], m); }
     return fresh;
 }
+__device__ __forceinline__ uint32_t fill_vertex(uint32_t* sec, uint32_t m, uint32_t code) {
+    Sector s = ld_sector_cg(sec);
+    return fill_sector(sec, s, m, code);
+}
 
-// All 8 edge queries of one k-mer from its sector (h:640-660): the edge actually present at
-// this occurrence counts once; any other edge recorded in the filter counts too.
-__device__ __forceinline__ bool query_vertex(const uint32_t* sec, uint32_t m, const Neigh& nb) {
-    Sector s = ld_sector_nc(sec);
-    uint32_t in_cnt = nb.a_n ? 2u : 0u, out_cnt = nb.b_n ? 2u : 0u;
+// All 8 edge queries of one k-mer from its sector (h:640-660).  The fill pass has recorded the edges
+// of THIS occurrence (or two dummy edges per 'N' side) in the same sector, so "the edge present here
+// counts once, any other recorded edge counts too" is simply: two or more of the four in-edge words,
+// or of the four out-edge words, hold the vertex's mask.  No neighbour information is needed.
+__device__ __forceinline__ bool query_sector(const Sector& s, uint32_t m) {
+    uint32_t in_cnt = 0, out_cnt = 0;
 #pragma unroll
     for (uint32_t c = 0; c < 4; ++c) {
-        in_cnt += (c == nb.a || (s.w[c] & m) == m) ? 1u : 0u;
-        out_cnt += (c == nb.b || (s.w[4 + c] & m) == m) ? 1u : 0u;
+        in_cnt += ((s.w[c] & m) == m) ? 1u : 0u;
+        out_cnt += ((s.w[4 + c] & m) == m) ? 1u : 0u;
     }
     return in_cnt > 1 || out_cnt > 1;
+}
+__device__ __forceinline__ bool query_vertex(const uint32_t* sec, uint32_t m) {
+    Sector s = ld_sector_nc(sec);
+    return query_sector(s, m);
 }
 
 template <int W, int Q>
@@ -100,9 +116,9 @@ k_fill(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t ntiles,
                 Kmer<W> canon = kmer_select<W>(fwd, win.X, win.Y);
                 if (kp.nparts == 1 || owner_part(owner_fold<W>(canon), kp.nparts) == kp.part) {
                     uint64_t h = kmer_hash<W>(canon, kp.seed);
-                    Neigh nb = orient(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
+                    uint32_t code = occurrence_code(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
                     uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
-                    fresh += fill_vertex(sec, vertex_mask<Q>(h), nb);
+                    fresh += fill_vertex(sec, vertex_mask<Q>(h), code);
                 }
             }
             roll<W>(win.X, win.Y, nxt, kp.k);
@@ -128,20 +144,19 @@ k_query(GenomeView g, const uint32_t* __restrict__ filter, KParams kp, uint64_t 
         win.load(g, w, kp.k);
         uint32_t out = 0;
         if (win.valid != 0) {
-            uint64_t nf = win.next_feed, pf = win.prev_feed;
+            uint64_t nf = win.next_feed;
 #pragma unroll 2
             for (int i = 0; i < 32; ++i) {
-                uint32_t nxt = (uint32_t)nf & 3u, prv = (uint32_t)pf & 3u;
-                nf >>= 2; pf >>= 2;
+                uint32_t nxt = (uint32_t)nf & 3u;
+                nf >>= 2;
                 if ((win.valid >> i) & 1u) {
                     bool fwd = kmer_less<W>(win.X, win.Y);
                     Kmer<W> canon = kmer_select<W>(fwd, win.X, win.Y);
                     if (kp.nparts == 1 || owner_part(owner_fold<W>(canon), kp.nparts) == kp.part) {
                         uint64_t h = kmer_hash<W>(canon, kp.seed);
-                        Neigh nb = orient(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
                         const uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
                         uint32_t vm = vertex_mask<Q>(h);
-                        if (query_vertex(sec, vm, nb)) {
+                        if (query_vertex(sec, vm)) {
                             out |= 1u << i;
                             hll_add(hll, vm, hash_sector(h, kp.sector_shift));
                         }
@@ -192,24 +207,34 @@ __device__ __forceinline__ int match_rep(const GenomeView& g, unsigned long long
     return 0;
 }
 
+// Candidate marks are sparse (a few % of the positions), so the marks of a tile are compacted into a
+// CTA-wide list and inserted one per thread (tpc_tile.cuh).  `op` (optional) selects this round's
+// marks through the ownership planes; without planes ownership is recomputed from the k-mer.
 template <int W>
 __global__ void __launch_bounds__(kTileThreads)
-k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t ntiles, TableView T, Counters* ctr) {
+k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t ntiles, TableView T, Counters* ctr, OwnPlanes op) {
+    __shared__ TileStage ts;
     const uint64_t capmask = (1ull << T.log2cap) - 1;
     const uint64_t probe_limit = capmask < 8192 ? capmask : 8192;  // a longer run means the table is too full: host grows it
     unsigned long long claimed = 0;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        uint64_t w = tile * kTileThreads + threadIdx.x;
-        if (w * 32 >= g.npos) continue;
+        const uint64_t w = tile * kTileThreads + threadIdx.x;
         uint32_t m = mask[w];
-        while (m) {
-            int i = __ffs(m) - 1;
-            m &= m - 1;
-            uint64_t p = w * 32 + i;
-            Occ<W> o = occurrence_at<W>(g, p, kp);
-            if (kp.nparts > 1 && owner_part(o.fold, kp.nparts) != kp.part) continue;  // marked in another round
-            bool pn = load_n(g.nmask, p - 1), nn = load_n(g.nmask, p + kp.k);
-            Neigh nb = orient(o.fwd, load_base(g.codes, p - 1), load_base(g.codes, p + kp.k), pn, nn);
+        if (op.n) m &= own_word(op, w);
+        TileGeom tg;
+        const uint32_t total = tile_compact(ts, g, tile, m, tg);
+        for (uint32_t e = threadIdx.x; e < total; e += kTileThreads) {
+            const uint32_t tp = ts.list[e];
+            const uint64_t p = tile * kTilePos + tp;
+            const uint32_t lp = tp + tg.c_off, mp = tp + tg.m_off;
+            Occ<W> o;
+            o.X = extract_kmer_smem<W>(ts.codes, lp, kp.k);
+            o.Y = revcomp<W>(o.X, kp.k);
+            o.fwd = kmer_less<W>(o.X, o.Y);
+            const Kmer<W> canon = kmer_select<W>(o.fwd, o.X, o.Y);
+            if (!op.n && kp.nparts > 1 && owner_part(owner_fold<W>(canon), kp.nparts) != kp.part) continue;  // marked in another round
+            o.h = kmer_hash<W>(canon, kp.seed);
+            Neigh nb = orient(o.fwd, stage_base(ts, lp - 1), stage_base(ts, lp + kp.k), stage_n(ts, mp - 1), stage_n(ts, mp + kp.k));
             // neighbour sets in canonical orientation (candidateoccurence.h:25-50; h:778-796)
             unsigned long long want = 0;
             if (!nb.a_n) want |= 1ull << nb.a;
@@ -218,7 +243,7 @@ k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t n
             Slot* s = nullptr;
             unsigned long long meta = 0;
             if (W == 1 && T.inline_keys) {
-                const unsigned long long key1 = (o.fwd ? o.X.w[0] : o.Y.w[0]) + 1ull;
+                const unsigned long long key1 = canon.w[0] + 1ull;
                 for (uint64_t probe = 0; probe <= probe_limit; ++probe, idx = (idx + 1) & capmask) {
                     Slot* cand = T.slots + idx;
                     ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(cand));

@@ -113,41 +113,164 @@ k_probe(uint32_t* __restrict__ table, uint32_t sector_bits, uint32_t mode, uint6
 }
 
 // ---- apply: one launch per slice; the slice stays in L2 ------------------------------------------
-__global__ void __launch_bounds__(256)
+// A thread takes kApplyU consecutive records per iteration: the record words come in as 128-bit
+// streaming loads, then all kApplyU sector loads (one 256-bit load each, random inside the
+// L2-resident slice) are in flight together before any of them is consumed.
+constexpr int kApplyU = 4;
+
+// Pull the slice into L2 with sequential line prefetches at the start of the launch: a first touch by
+// a random 32-byte access costs a whole HBM row activation, a streaming prefetch of the 64 MiB does not.
+__device__ __forceinline__ void prefetch_slice(const uint32_t* slice, uint32_t sectors, uint32_t gtid, uint32_t gsize) {
+    const char* base = reinterpret_cast<const char*>(slice);
+    const size_t bytes = (size_t)sectors * 32;
+    for (size_t off = (size_t)gtid * 128; off < bytes; off += (size_t)gsize * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+}
+
+__device__ __forceinline__ uint32_t u4_get(const uint4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
+
+// Record words reach the thread through a private ring of cp.async (LDGSTS) stages in shared memory,
+// kApplyDepth iterations ahead: the HBM latency of the record stream is off the critical path, which is
+// then just "sector load -> test -> (atomicOr)".  Each thread reads back only what it copied itself, so
+// cp.async.wait_group is the only synchronisation.
+constexpr int kApplyDepth = 4;
+struct ApplyRing {
+    uint4 sd[kApplyDepth][256];
+    uint4 w1[kApplyDepth][256];
+};
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, uint64_t policy) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct ApplyStream {   // per-thread state of the record prefetcher
+    const uint4* sd;
+    const uint4* w1;
+    uint32_t next, nvec, gsize;
+    uint64_t policy;
+    int slot;
+    __device__ __forceinline__ void issue(ApplyRing& ring, int d) {
+        if (next < nvec) {
+            cp_async16(&ring.sd[d][threadIdx.x], sd + next, policy);
+            cp_async16(&ring.w1[d][threadIdx.x], w1 + next, policy);
+        }
+        cp_async_commit();
+        next += gsize;
+    }
+    __device__ __forceinline__ void start(ApplyRing& ring, const uint32_t* rec, const uint32_t* rec_b, uint32_t gtid, uint32_t gs, uint32_t nv) {
+        sd = reinterpret_cast<const uint4*>(rec); w1 = reinterpret_cast<const uint4*>(rec_b);
+        next = gtid; nvec = nv; gsize = gs; slot = 0;
+        policy = l2_evict_first_policy();
+#pragma unroll
+        for (int d = 0; d < kApplyDepth; ++d) issue(ring, d);
+    }
+    // records of the current iteration; call refill() once their consumers have been issued
+    __device__ __forceinline__ void take(ApplyRing& ring, uint4& a, uint4& b) {
+        cp_async_wait<kApplyDepth - 1>();
+        a = ring.sd[slot][threadIdx.x];
+        b = ring.w1[slot][threadIdx.x];
+    }
+    __device__ __forceinline__ void refill(ApplyRing& ring) {
+        issue(ring, slot);
+        slot = slot + 1 == kApplyDepth ? 0 : slot + 1;
+    }
+};
+
+template <int Q>
+__global__ void __launch_bounds__(256, 4)
 k_apply_fill(uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, const unsigned long long* __restrict__ count,
-             uint64_t cap, uint32_t sib_mask, uint32_t q, Counters* ctr) {
+             uint64_t cap, uint32_t sib_mask, Counters* ctr) {
     __shared__ unsigned long long red[8];
+    __shared__ ApplyRing ring;
     unsigned long long n64 = *count;
     const uint32_t n = (uint32_t)(n64 > cap ? cap : n64);
     const uint32_t* __restrict__ rec_b = rec + cap;
-    unsigned long long fresh = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t seed = __ldcs(rec + i), w1 = __ldcs(rec_b + i);
-        fresh += fill_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), mask_from_seed_rt(seed, q),
-                             decode_occurrence(w1 >> kBinCodeShift));
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    uint32_t fresh = 0;
+    const uint32_t nvec = n / kApplyU;
+    ApplyStream st;
+    st.start(ring, rec, rec_b, gtid, gsize, nvec);
+    prefetch_slice(slice, sib_mask + 1u, gtid, gsize);
+    for (uint32_t v = gtid; v < nvec; v += gsize) {
+        uint4 sd, w1;
+        st.take(ring, sd, w1);
+        uint32_t* sec[kApplyU];
+        Sector s[kApplyU];
+#pragma unroll
+        for (int j = 0; j < kApplyU; ++j) {
+            sec[j] = slice + ((uint64_t)(u4_get(w1, j) & sib_mask) << 3);
+            s[j] = ld_sector_cg(sec[j]);
+        }
+        st.refill(ring);
+#pragma unroll
+        for (int j = 0; j < kApplyU; ++j)
+            fresh += fill_sector(sec[j], s[j], mask_from_seed<Q>(u4_get(sd, j)), u4_get(w1, j) >> kBinCodeShift);
+    }
+    cp_async_wait<0>();
+    for (uint32_t i = nvec * kApplyU + gtid; i < n; i += gsize) {
+        const uint32_t w1 = __ldcs(rec_b + i);
+        fresh += fill_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), mask_from_seed<Q>(__ldcs(rec + i)), w1 >> kBinCodeShift);
     }
     unsigned long long t = block_sum(fresh, red);
     if (threadIdx.x == 0 && t) atomicAdd(&ctr->filter_new, t);
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void apply_mark(uint32_t* __restrict__ mask, uint32_t* __restrict__ hll, uint32_t m, uint32_t w1,
+                                           uint32_t relpos, uint32_t sib_bits, uint64_t wave_base, uint64_t slice_first_sector) {
+    const uint32_t sib_mask = (1u << sib_bits) - 1u;
+    hll_add(hll, m, slice_first_sector | (w1 & sib_mask));
+    const uint64_t p = wave_base + (((uint64_t)((w1 & ((1u << kBinCodeShift) - 1u)) >> sib_bits)) << 32) + relpos;
+    atomicOr(mask + (p >> 5), 1u << (p & 31));
+}
+
+template <int Q>
+__global__ void __launch_bounds__(256, 4)
 k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, const unsigned long long* __restrict__ count,
-              uint64_t cap, uint32_t sib_bits, uint32_t q, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr,
+              uint64_t cap, uint32_t sib_bits, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr,
               uint32_t* __restrict__ hll, uint64_t slice_first_sector) {
     __shared__ unsigned long long red[8];
+    __shared__ ApplyRing ring;
     unsigned long long n64 = *count;
     const uint32_t n = (uint32_t)(n64 > cap ? cap : n64);
     const uint32_t* __restrict__ rec_b = rec + cap;
-    const uint32_t* __restrict__ rec_c = rec + 2 * cap;
+    const uint32_t* __restrict__ rec_c = rec + 2 * cap;   // relative positions: read only for the (few) candidates
     const uint32_t sib_mask = (1u << sib_bits) - 1u;
-    unsigned long long marks = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t seed = __ldcs(rec + i), w1 = __ldcs(rec_b + i);
-        uint32_t m = mask_from_seed_rt(seed, q);
-        if (query_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), m, decode_occurrence(w1 >> kBinCodeShift))) {
-            hll_add(hll, m, slice_first_sector | (w1 & sib_mask));
-            uint64_t p = wave_base + (((uint64_t)((w1 & ((1u << kBinCodeShift) - 1u)) >> sib_bits)) << 32) + __ldcs(rec_c + i);
-            atomicOr(mask + (p >> 5), 1u << (p & 31));
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    uint32_t marks = 0;
+    const uint32_t nvec = n / kApplyU;
+    ApplyStream st;
+    st.start(ring, rec, rec_b, gtid, gsize, nvec);
+    prefetch_slice(slice, sib_mask + 1u, gtid, gsize);
+    for (uint32_t v = gtid; v < nvec; v += gsize) {
+        uint4 sd, w1;
+        st.take(ring, sd, w1);
+        Sector s[kApplyU];
+#pragma unroll
+        for (int j = 0; j < kApplyU; ++j) s[j] = ld_sector_nc(slice + ((uint64_t)(u4_get(w1, j) & sib_mask) << 3));
+        st.refill(ring);
+#pragma unroll
+        for (int j = 0; j < kApplyU; ++j) {
+            const uint32_t m = mask_from_seed<Q>(u4_get(sd, j));
+            if (query_sector(s[j], m)) {
+                apply_mark(mask, hll, m, u4_get(w1, j), __ldcs(rec_c + (uint64_t)v * kApplyU + j), sib_bits, wave_base, slice_first_sector);
+                ++marks;
+            }
+        }
+    }
+    cp_async_wait<0>();
+    for (uint32_t i = nvec * kApplyU + gtid; i < n; i += gsize) {
+        const uint32_t w1 = __ldcs(rec_b + i);
+        const uint32_t m = mask_from_seed<Q>(__ldcs(rec + i));
+        if (query_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), m)) {
+            apply_mark(mask, hll, m, w1, __ldcs(rec_c + i), sib_bits, wave_base, slice_first_sector);
             ++marks;
         }
     }
@@ -164,18 +287,14 @@ k_apply_overflow(uint32_t* __restrict__ filter, const uint32_t* __restrict__ ov,
     unsigned long long n = *ov_count;
     if (n > ov_cap) n = ov_cap;
     unsigned long long acc = 0;
-    const uint32_t sib_mask = (1u << sib_bits) - 1u;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         uint4 r = reinterpret_cast<const uint4*>(ov)[i];
-        uint32_t* sec = filter + ((((uint64_t)r.w << sib_bits) | (r.y & sib_mask)) << 3);
-        Neigh nb = decode_occurrence(r.y >> kBinCodeShift);
+        uint32_t* sec = filter + ((((uint64_t)r.w << sib_bits) | (r.y & ((1u << sib_bits) - 1u))) << 3);
         uint32_t m = mask_from_seed_rt(r.x, q);
-        if (!do_query) acc += fill_vertex(sec, m, nb);
-        else if (query_vertex(sec, m, nb)) {
-            hll_add(hll, m, ((uint64_t)r.w << sib_bits) | (r.y & sib_mask));
-            uint64_t p = wave_base + (((uint64_t)((r.y & ((1u << kBinCodeShift) - 1u)) >> sib_bits)) << 32) + r.z;
-            atomicOr(mask + (p >> 5), 1u << (p & 31));
+        if (!do_query) acc += fill_vertex(sec, m, r.y >> kBinCodeShift);
+        else if (query_vertex(sec, m)) {
+            apply_mark(mask, hll, m, r.y, r.z, sib_bits, wave_base, (uint64_t)r.w << sib_bits);
             ++acc;
         }
     }

@@ -8,6 +8,7 @@ namespace tpc {
 struct Counters;
 struct RecordTable;
 struct BinView;
+struct OwnPlanes;
 
 struct LaunchCtx {
     cudaStream_t stream;
@@ -20,9 +21,14 @@ struct Launch {
     static cudaError_t fill(const LaunchCtx&, GenomeView, uint32_t* filter, KParams, uint64_t ntiles, Counters*);
     static cudaError_t query(const LaunchCtx&, GenomeView, const uint32_t* filter, KParams, uint64_t ntiles,
                              uint32_t* mask, int accumulate, Counters*, uint32_t* hll);
+    // ownership planes of the tiles [tile_begin, tile_end): local round (part - part_base, < nlocal) of every position
+    static cudaError_t own(const LaunchCtx&, GenomeView, KParams, uint32_t part_base, uint32_t nlocal, uint64_t tile_begin,
+                           uint64_t tile_end, const OwnPlanes&);
+    // records of the owned positions partitioned by filter slice; planes == nullptr: unsharded (every k-mer is owned)
     static cudaError_t bin(const LaunchCtx&, GenomeView, KParams, const BinView&, uint64_t tile_begin, uint64_t tile_end,
-                           uint64_t wave_base, uint32_t* own_scratch);
-    static cudaError_t insert(const LaunchCtx&, GenomeView, const uint32_t* mask, KParams, uint64_t ntiles, TableView T, Counters*);
+                           uint64_t wave_base, const OwnPlanes* planes);
+    static cudaError_t insert(const LaunchCtx&, GenomeView, const uint32_t* mask, KParams, uint64_t ntiles, TableView T, Counters*,
+                              const OwnPlanes* planes);
     static cudaError_t build_index(const LaunchCtx&, GenomeView, const unsigned long long* sorted, uint64_t n, KParams, TableView J);
     static cudaError_t ends(const LaunchCtx&, GenomeView, const RecordTable&, KParams, TableView J, uint32_t* stubmask,
                             uint64_t pos_begin, uint64_t pos_end);

@@ -54,7 +54,7 @@ cudaError_t Launch<W>::query(const LaunchCtx& c, GenomeView g, const uint32_t* f
 
 template <int W, int R>
 static void launch_bin_list(const LaunchCtx& c, GenomeView g, KParams kp, const BinView& bv, uint64_t tile_begin, uint64_t tile_end,
-                            uint64_t wave_base, const uint32_t* own) {
+                            uint64_t wave_base, const OwnPlanes& op) {
     constexpr size_t smem = bin_list_smem_bytes(R);
     static bool configured = false;
     if (!configured) {
@@ -64,24 +64,42 @@ static void launch_bin_list(const LaunchCtx& c, GenomeView g, KParams kp, const 
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_list<W, R>, kTileThreads, smem);
     uint64_t grid = std::min<uint64_t>((uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count, tile_end - tile_begin);
-    k_bin_list<W, R><<<(int)grid, kTileThreads, smem, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base, own);
+    k_bin_list<W, R><<<(int)grid, kTileThreads, smem, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base, op);
+}
+
+template <int W, int P>
+static void launch_own(const LaunchCtx& c, GenomeView g, KParams kp, uint32_t part_base, uint32_t nlocal, uint64_t tile_begin,
+                       uint64_t tile_end, const OwnPlanes& op) {
+    int grid = persistent_grid(k_own<W, P>, kTileThreads, c.sm_count, tile_end - tile_begin);
+    k_own<W, P><<<grid, kTileThreads, 0, c.stream>>>(g, kp, part_base, nlocal, tile_begin * kTileThreads, tile_end * kTileThreads, op);
+}
+
+template <int W>
+cudaError_t Launch<W>::own(const LaunchCtx& c, GenomeView g, KParams kp, uint32_t part_base, uint32_t nlocal, uint64_t tile_begin,
+                           uint64_t tile_end, const OwnPlanes& op) {
+    if (tile_end <= tile_begin) return cudaSuccess;
+    switch (op.n) {
+        case 1: launch_own<W, 1>(c, g, kp, part_base, nlocal, tile_begin, tile_end, op); break;
+        case 2: launch_own<W, 2>(c, g, kp, part_base, nlocal, tile_begin, tile_end, op); break;
+        case 3: launch_own<W, 3>(c, g, kp, part_base, nlocal, tile_begin, tile_end, op); break;
+        default: launch_own<W, 4>(c, g, kp, part_base, nlocal, tile_begin, tile_end, op); break;
+    }
+    ++*c.launches;
+    return cudaGetLastError();
 }
 
 template <int W>
 cudaError_t Launch<W>::bin(const LaunchCtx& c, GenomeView g, KParams kp, const BinView& bv, uint64_t tile_begin, uint64_t tile_end,
-                           uint64_t wave_base, uint32_t* own_scratch) {
+                           uint64_t wave_base, const OwnPlanes* planes) {
     if (tile_end <= tile_begin) return cudaSuccess;
     const uint64_t ntiles = tile_end - tile_begin;
-    if (kp.nparts > 1) {
-        // (1) ownership bit per position, (2) dense binning of the owned positions
-        int grid_own = persistent_grid(k_own<W>, kTileThreads, c.sm_count, ntiles);
-        k_own<W><<<grid_own, kTileThreads, 0, c.stream>>>(g, kp, tile_begin * kTileThreads, tile_end * kTileThreads, own_scratch);
-        ++*c.launches;
-        // stage size >= 1.25 x the expected owned positions of a tile (more CTAs per SM when it is small)
+    if (planes) {
+        // dense binning of the owned positions; stage size >= 1.25 x the expected owned positions of a
+        // tile (more CTAs per SM when it is small)
         const uint32_t expect = (uint32_t)(kTilePos / kp.nparts) * 5 / 4;
-        if (expect <= 4 * kTileThreads) launch_bin_list<W, 4>(c, g, kp, bv, tile_begin, tile_end, wave_base, own_scratch);
-        else if (expect <= 8 * kTileThreads) launch_bin_list<W, 8>(c, g, kp, bv, tile_begin, tile_end, wave_base, own_scratch);
-        else launch_bin_list<W, 16>(c, g, kp, bv, tile_begin, tile_end, wave_base, own_scratch);
+        if (expect <= 4 * kTileThreads) launch_bin_list<W, 4>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
+        else if (expect <= 8 * kTileThreads) launch_bin_list<W, 8>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
+        else launch_bin_list<W, 16>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
     } else {
         static bool configured = false;
         if (!configured) {
@@ -99,9 +117,12 @@ cudaError_t Launch<W>::bin(const LaunchCtx& c, GenomeView g, KParams kp, const B
 
 template <int W>
 cudaError_t Launch<W>::insert(const LaunchCtx& c, GenomeView g, const uint32_t* mask, KParams kp, uint64_t ntiles, TableView T,
-                              Counters* ctr) {
+                              Counters* ctr, const OwnPlanes* planes) {
+    if (ntiles == 0) return cudaSuccess;
+    OwnPlanes op{};
+    if (planes) op = *planes;
     int grid = persistent_grid(k_insert<W>, kTileThreads, c.sm_count, ntiles);
-    k_insert<W><<<grid, kTileThreads, 0, c.stream>>>(g, mask, kp, ntiles, T, ctr);
+    k_insert<W><<<grid, kTileThreads, 0, c.stream>>>(g, mask, kp, ntiles, T, ctr, op);
     ++*c.launches;
     return cudaGetLastError();
 }

@@ -114,12 +114,24 @@ cudaError_t launch_scan_exclusive(const LaunchCtx& c, unsigned long long* data, 
     return cudaGetLastError();
 }
 
-static int apply_grid(const LaunchCtx& c) { return c.sm_count * 8; }
+static int apply_grid(const LaunchCtx& c) { return c.sm_count * 4; }
+
+#define TPC_APPLY_Q_SWITCH(q, ...)                             \
+    switch (q) {                                               \
+        case 1: { constexpr int Q = 1; __VA_ARGS__; } break;   \
+        case 2: { constexpr int Q = 2; __VA_ARGS__; } break;   \
+        case 3: { constexpr int Q = 3; __VA_ARGS__; } break;   \
+        case 4: { constexpr int Q = 4; __VA_ARGS__; } break;   \
+        case 5: { constexpr int Q = 5; __VA_ARGS__; } break;   \
+        case 6: { constexpr int Q = 6; __VA_ARGS__; } break;   \
+        case 7: { constexpr int Q = 7; __VA_ARGS__; } break;   \
+        default: { constexpr int Q = 8; __VA_ARGS__; } break;  \
+    }
 
 cudaError_t launch_apply_fill(const LaunchCtx& c, uint32_t* filter, const BinView& bv, uint32_t bucket, Counters* ctr) {
     uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
-    k_apply_fill<<<apply_grid(c), 256, 0, c.stream>>>(slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap,
-                                                      (1u << bv.sib_bits) - 1u, bv.q, ctr);
+    TPC_APPLY_Q_SWITCH(bv.q, (k_apply_fill<Q><<<apply_grid(c), 256, 0, c.stream>>>(
+        slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap, (1u << bv.sib_bits) - 1u, ctr)));
     ++*c.launches;
     return cudaGetLastError();
 }
@@ -127,8 +139,9 @@ cudaError_t launch_apply_fill(const LaunchCtx& c, uint32_t* filter, const BinVie
 cudaError_t launch_apply_query(const LaunchCtx& c, const uint32_t* filter, const BinView& bv, uint32_t bucket, uint32_t* mask,
                                uint64_t wave_base, Counters* ctr, uint32_t* hll) {
     const uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
-    k_apply_query<<<apply_grid(c), 256, 0, c.stream>>>(slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap,
-                                                       bv.sib_bits, bv.q, mask, wave_base, ctr, hll, (uint64_t)bucket << bv.sib_bits);
+    TPC_APPLY_Q_SWITCH(bv.q, (k_apply_query<Q><<<apply_grid(c), 256, 0, c.stream>>>(
+        slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap, bv.sib_bits, mask, wave_base, ctr, hll,
+        (uint64_t)bucket << bv.sib_bits)));
     ++*c.launches;
     return cudaGetLastError();
 }
@@ -200,10 +213,25 @@ struct tpc_session {
     int filter_mode = 0;           // 0 auto, 1 direct, 2 binned (env TPC_FILTER_MODE)
     uint32_t slice_log2 = 26;      // filter slice kept L2-resident by the apply kernels (env TPC_SLICE_LOG2)
     uint64_t bin_budget_bytes = 0; // 0 = 70 % of free HBM (env TPC_BIN_BUFFER_MB)
-    uint32_t* d_bin_rec = nullptr;
+    uint32_t* d_bin_rec = nullptr;  // record scratch of the call: the rounds' record waves, then (between the
+    uint64_t bin_rec_bytes = 0;     //   filter passes and the next round) the round's candidate table
     unsigned long long* d_bin_count = nullptr;
     uint32_t* d_bin_ov = nullptr;
+    BinView bin_view{};             // layout of the scratch, fixed for all rounds of a call
+    uint64_t bin_wave_tiles = 0, bin_nwaves = 0;
+    bool bin_ready = false;
     bool used_binned = false;
+    bool T_in_scratch = false;
+
+    // hash sub-ranges processed in sequence by this GPU: the user's -r times the sub-rounds chosen so
+    // that one round's records fit HBM in one wave (choose_sub_rounds); ownership planes of all of
+    // them come from ONE scan (k_own), plane 0 lives in the stub mask until the emit stage
+    uint32_t sub_rounds = 1, rounds_eff = 1;
+    int sub_rounds_env = 0;        // env TPC_SUBROUNDS (0 = automatic)
+    uint32_t* d_own_extra = nullptr;
+    OwnPlanes own{};
+    bool own_shared = false;
+    uint64_t own_done_tiles = 0;
 
     // host->device upload of the genome overlapped with the first binning pass (set_genome_host)
     cudaStream_t copy_stream = nullptr;
@@ -212,7 +240,7 @@ struct tpc_session {
     size_t up_waited = 0;                    // chunks the compute stream already waits for
 
     tpc_stats st{};
-    cudaEvent_t ev[10]{};
+    cudaEvent_t ev[12]{};
     uint32_t launches = 0;
 
     bool allow_inline = true;      // env TPC_INLINE_KEYS=0 forces position-identified slots for every k
@@ -223,7 +251,7 @@ struct tpc_session {
         kp.k = prm.k;
         kp.q = std::min<uint32_t>(std::max<uint32_t>(prm.q, 1u), 8u);
         kp.sector_shift = 64 - (filter_bits_eff - 8);
-        kp.nparts = prm.rounds * prm.shard_count;
+        kp.nparts = rounds_eff * prm.shard_count;
         kp.part = part;
         kp.count_occurrences = prm.abundance != ~0ull;
         kp.seed = prm.seed;
@@ -283,6 +311,8 @@ int tpc_session_create(const tpc_params* params, void* stream, tpc_session** out
     if (const char* e = getenv("TPC_INLINE_KEYS")) s->allow_inline = atoi(e) != 0;
     if (const char* e = getenv("TPC_SLICE_LOG2")) s->slice_log2 = std::min(31, std::max(8, atoi(e)));
     if (const char* e = getenv("TPC_BIN_BUFFER_MB")) s->bin_budget_bytes = (uint64_t)atoll(e) << 20;
+    if (const char* e = getenv("TPC_SUBROUNDS")) s->sub_rounds_env = std::min(64, std::max(0, atoi(e)));
+    s->rounds_eff = params->rounds;
     cudaGetDevice(&s->device);
     configure_pool(s->device);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
@@ -302,7 +332,7 @@ void tpc_session_destroy(tpc_session* s) {
     cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_codes, s->d_nmask, s->d_rec_start, s->d_rec_len, s->d_sep_before, s->d_filter, s->d_mask,
                     s->d_stubmask, s->d_T, s->d_J, s->d_local, s->d_sorted, s->d_sort_tmp, s->d_ctr, s->d_id,
-                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch, s->d_bin_rec, s->d_bin_count, s->d_bin_ov, s->d_hll};
+                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch, s->d_bin_rec, s->d_bin_count, s->d_bin_ov, s->d_hll, s->d_own_extra};
     for (void* p : ptrs)
         dev_free(p, s->stream);
     cudaStreamSynchronize(s->stream);
@@ -400,21 +430,60 @@ static double hll_estimate(const std::vector<uint32_t>& reg) {
     return e;
 }
 
-// Filter passes of one round through the binned path.  Returns -1 when the binned path does not
-// apply and -2 when a slice overflowed beyond the overflow area (then the caller uses k_fill /
-// k_query), 0 on success, >0 on error.
-static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin, float* ms_fill, float* ms_query) {
-    if (s->filter_mode == 1) return -1;
+// the binned path needs 2..256 filter slices and an input large enough to be worth it
+static bool binned_applies(const tpc_session* s, BinView* out) {
+    if (s->filter_mode == 1) return false;
     int bb = (int)s->filter_bits_eff - 3 - (int)s->slice_log2;
-    if (bb < 1 || bb > 8) return -1;
-    if (s->filter_mode == 0 && s->g.npos < (1ull << 22)) return -1;
-    LaunchCtx lc = s->lctx();
+    if (bb < 1 || bb > 8) return false;
+    if (s->filter_mode == 0 && s->g.npos < (1ull << 22)) return false;
+    uint32_t sib = s->filter_bits_eff - 8 - (uint32_t)bb;
+    if (sib > (uint32_t)kBinCodeShift) return false;
+    if (out) { out->bucket_bits = (uint32_t)bb; out->sib_bits = sib; }
+    return true;
+}
+
+static uint32_t own_planes_for(uint32_t rounds_local) {  // bits needed for ids 1..rounds_local; 0 = no shared scan
+    if (rounds_local > 15) return 0;
+    uint32_t p = 1;
+    while ((1u << p) <= rounds_local) ++p;
+    return p;
+}
+
+// Sub-rounds: a round whose records (12 B per owned k-mer) fit free HBM in ONE wave is binned once
+// for both filter passes, and its filter holds 1/S of the vertices, so Bloom false positives (the
+// marks pass 2 has to remove) drop steeply.  -r and -f keep their meaning; like -r, the split is
+// unobservable in the output.
+static uint32_t choose_sub_rounds(const tpc_session* s) {
+    if (s->sub_rounds_env) return (uint32_t)s->sub_rounds_env;
+    if (s->bin_budget_bytes || !binned_applies(s, nullptr)) return 1;
+    const uint64_t avail = available_bytes(s->device);
+    const uint64_t plane_bytes = s->ntiles * kTileThreads * 4;
+    const uint64_t base = (uint64_t)s->prm.rounds * s->prm.shard_count;
+    for (uint32_t S = 1; S <= 8; ++S) {
+        uint32_t planes = own_planes_for(s->prm.rounds * S);
+        uint64_t extra = planes > 1 ? (planes - 1) * plane_bytes : 0;
+        if (avail <= extra) break;
+        if ((double)(s->g.npos / (base * S)) * 14.0 <= (double)(avail - extra) * 0.88) return S;  // (binning takes 92 %)
+    }
+    return 8;
+}
+
+// first tile boundary in (from, to] at which another upload chunk has to be waited for
+static uint64_t next_cut(const tpc_session* s, uint64_t from, uint64_t to) {
+    for (size_t c = s->up_waited; c < s->up_ev.size(); ++c)
+        if (s->up_tile_begin[c] > from) return std::min(to, s->up_tile_begin[c]);
+    return to;
+}
+
+// Record scratch of the binned path: sized once per find_candidates call (every round owns the same
+// share of the positions) and kept until the call ends, so the rounds do not go through the allocator.
+// Returns -1 when the binned path does not apply, 0 on success, >0 on error.
+static int binned_setup(tpc_session* s, const KParams& kp) {
+    if (s->bin_ready) return 0;
     BinView bv{};
-    bv.bucket_bits = (uint32_t)bb;
-    bv.sib_bits = s->filter_bits_eff - 8 - (uint32_t)bb;
-    if (bv.sib_bits > (uint32_t)kBinCodeShift) return -1;
+    if (!binned_applies(s, &bv)) return -1;
     bv.q = kp.q;
-    const uint32_t buckets = 1u << bb;
+    const uint32_t buckets = 1u << bv.bucket_bits;
     uint64_t budget = s->bin_budget_bytes ? s->bin_budget_bytes : (uint64_t)(available_bytes(s->device) * 0.92);
     uint64_t wave_tiles = 0, nwaves = 0;
     for (int attempt = 0;; ++attempt) {
@@ -429,11 +498,13 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
         uint64_t est = wave_tiles * kTilePos / kp.nparts;
         bv.cap = ((uint64_t)(est / buckets * 1.08) + 8192 + 31) / 32 * 32;
         bv.ov_cap = std::max<uint64_t>(1 << 16, est / 64);
-        cudaError_t e = dev_alloc(&s->d_bin_rec, (uint64_t)buckets * 3 * bv.cap * 4, s->stream);
+        s->bin_rec_bytes = (uint64_t)buckets * 3 * bv.cap * 4;
+        cudaError_t e = dev_alloc(&s->d_bin_rec, s->bin_rec_bytes, s->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
         if (e == cudaErrorMemoryAllocation && attempt < 4 && !s->bin_budget_bytes) {
             cudaGetLastError();  // not enough contiguous memory after all: smaller waves
             s->d_bin_rec = nullptr;
+            s->bin_rec_bytes = 0;
             budget = budget * 6 / 10;
             continue;
         }
@@ -443,6 +514,32 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
     CK(dev_alloc(&s->d_bin_count, (buckets + 1) * 8, s->stream));
     CK(dev_alloc(&s->d_bin_ov, bv.ov_cap * 16, s->stream));
     bv.rec = s->d_bin_rec; bv.count = s->d_bin_count; bv.ov_count = s->d_bin_count + buckets; bv.ov = s->d_bin_ov;
+    s->bin_view = bv;
+    s->bin_wave_tiles = wave_tiles;
+    s->bin_nwaves = nwaves;
+    s->bin_ready = true;
+    return 0;
+}
+
+static int binned_release(tpc_session* s) {
+    for (void** p : {(void**)&s->d_bin_rec, (void**)&s->d_bin_count, (void**)&s->d_bin_ov}) {
+        if (*p) CK(dev_free(*p, s->stream));
+        *p = nullptr;
+    }
+    s->bin_rec_bytes = 0;
+    s->bin_ready = false;
+    return 0;
+}
+
+// Filter passes of one round through the binned path.  Returns -1 when the binned path does not
+// apply and -2 when a slice overflowed beyond the overflow area (then the caller uses k_fill /
+// k_query), 0 on success, >0 on error.
+static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin, float* ms_fill, float* ms_query) {
+    if (int rc = binned_setup(s, kp)) return rc;
+    LaunchCtx lc = s->lctx();
+    const BinView bv = s->bin_view;
+    const uint32_t buckets = 1u << bv.bucket_bits;
+    const uint64_t wave_tiles = s->bin_wave_tiles, nwaves = s->bin_nwaves;
     cudaEvent_t e0, e1, e2;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
     unsigned long long ov_total = 0, ov_now = 0;
@@ -456,6 +553,28 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
         ov_total = std::max(ov_total, ov_now);
         return 0;
     };
+    // bin the tiles [t0, t1): cut at the upload chunks still in flight so that the first pass over a
+    // host genome overlaps its upload; sharded rounds read the ownership planes (one k_own scan for all
+    // the rounds of this call when they fit kMaxOwnPlanes, else one scan per round)
+    const bool sharded = kp.nparts > 1;
+    const uint32_t part_base = s->prm.shard_index * s->rounds_eff;
+    OwnPlanes op = s->own;
+    op.id = s->own_shared ? kp.part - part_base + 1 : 1;
+    if (!s->own_shared) op.n = 1;
+    auto bin_range = [&](uint64_t t0, uint64_t t1, uint64_t base) -> int {
+        for (uint64_t a = t0; a < t1;) {
+            const uint64_t b = next_cut(s, a, t1);
+            if (int wrc = wait_genome(s, b)) return wrc;
+            if (sharded && !s->own_shared) CK(W_DISPATCH(s, own(lc, s->g, kp, kp.part, 1, a, b, op)));
+            if (sharded && s->own_shared && s->own_done_tiles < b) {
+                CK(W_DISPATCH(s, own(lc, s->g, kp, part_base, s->rounds_eff, s->own_done_tiles, b, s->own)));
+                s->own_done_tiles = b;
+            }
+            CK(W_DISPATCH(s, bin(lc, s->g, kp, bv, a, b, base, sharded ? &op : nullptr)));
+            a = b;
+        }
+        return 0;
+    };
     int rc = 0;
     for (int pass = 0; pass < 2 && rc == 0; ++pass) {           // 0 = fill, 1 = query
         for (uint64_t wv = 0; wv < nwaves && rc == 0; ++wv) {
@@ -464,9 +583,8 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
             bool rebin = !(pass == 1 && nwaves == 1);           // one wave: the records serve both passes
             CK(cudaEventRecord(e0, s->stream));
             if (rebin) {
-                if (int wrc = wait_genome(s, t1)) return wrc;
                 CK(cudaMemsetAsync(s->d_bin_count, 0, (buckets + 1) * 8, s->stream));
-                CK(W_DISPATCH(s, bin(lc, s->g, kp, bv, t0, t1, base, s->d_stubmask)));  // stub mask doubles as ownership scratch
+                if (int brc = bin_range(t0, t1, base)) return brc;
             }
             CK(cudaEventRecord(e1, s->stream));
             for (uint32_t b = 0; b < buckets; ++b) {
@@ -479,10 +597,6 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
         }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
-    for (void** p : {(void**)&s->d_bin_rec, (void**)&s->d_bin_count, (void**)&s->d_bin_ov}) {
-        dev_free(*p, s->stream);
-        *p = nullptr;
-    }
     if (rc) return rc;
     if (ov_total > bv.ov_cap) return -2;  // heavily skewed input: the caller redoes the round with k_fill / k_query
     s->used_binned = true;
@@ -507,8 +621,28 @@ int tpc_session_find_candidates(tpc_session* s) {
     s->st.positions = s->g.npos;
     float ms_bin = 0, ms_fill = 0, ms_query = 0, ms_insert = 0, ms_classify = 0;
     Counters prev{}, cur{};
-    for (uint32_t r = 0; r < s->prm.rounds; ++r) {
-        KParams kp = s->kparams(s->prm.shard_index * s->prm.rounds + r);
+    CK(cudaStreamSynchronize(s->stream));  // the allocations above are visible to available_bytes()
+    s->sub_rounds = choose_sub_rounds(s);
+    s->rounds_eff = s->prm.rounds * s->sub_rounds;
+    s->st.sub_rounds = s->sub_rounds;
+    {   // ownership planes shared by all rounds of this call
+        const uint32_t planes = s->rounds_eff * s->prm.shard_count > 1 ? own_planes_for(s->rounds_eff) : 0;
+        s->own = OwnPlanes{};
+        s->own.p[0] = s->d_stubmask;
+        s->own.n = std::max<uint32_t>(planes, 1);
+        s->own_shared = planes > 0;
+        s->own_done_tiles = 0;
+        if (s->d_own_extra) { CK(dev_free(s->d_own_extra, s->stream)); s->d_own_extra = nullptr; }
+        if (planes > 1 && binned_applies(s, nullptr)) {
+            CK(dev_alloc(&s->d_own_extra, (uint64_t)(planes - 1) * std::max<uint64_t>(mask_words, 1) * 4, s->stream));
+            for (uint32_t j = 1; j < planes; ++j) s->own.p[j] = s->d_own_extra + (uint64_t)(j - 1) * mask_words;
+        } else if (planes > 1) {
+            s->own_shared = false;  // direct path: ownership is decided inline
+            s->own.n = 1;
+        }
+    }
+    for (uint32_t r = 0; r < s->rounds_eff; ++r) {
+        KParams kp = s->kparams(s->prm.shard_index * s->rounds_eff + r);
         CK(cudaEventRecord(s->ev[0], s->stream));
         CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));  // h:257: zero-filled each round
         CK(cudaMemsetAsync(s->d_hll, 0, 4u << kHllBits, s->stream));
@@ -543,18 +677,31 @@ int tpc_session_find_candidates(tpc_session* s) {
         uint32_t lg = std::max<uint32_t>(ceil_log2((uint64_t)(est * 1.15 * 2.0) + 64), 10);
         if (const char* e = getenv("TPC_TABLE_SHRINK")) lg = std::max<int>(4, (int)lg - atoi(e));  // tests: force the grow-and-redo path
         for (;;) {
-            uint64_t avail = available_bytes(s->device) + s->T_bytes;
             uint64_t need = sizeof(Slot) << lg;
-            if (need > avail) return set_error("candidate table of 2^%u slots does not fit in device memory", lg);
-            if (need > s->T_bytes) {
-                if (s->d_T) CK(dev_free(s->d_T, s->stream));
-                s->d_T = nullptr; s->T_bytes = 0;
-                CK(dev_alloc(&s->d_T, need, s->stream));
-                s->T_bytes = need;
+            if (s->d_T && (s->T_in_scratch || need > s->T_bytes)) {
+                if (!s->T_in_scratch) CK(dev_free(s->d_T, s->stream));
+                s->d_T = nullptr; s->T_bytes = 0; s->T_in_scratch = false;
+            }
+            if (!s->d_T) {
+                if (s->d_bin_rec && need <= s->bin_rec_bytes) {   // the record waves of this round are spent
+                    s->d_T = reinterpret_cast<Slot*>(s->d_bin_rec);
+                    s->T_bytes = s->bin_rec_bytes;
+                    s->T_in_scratch = true;
+                } else {
+                    if (need > available_bytes(s->device)) return set_error("candidate table of 2^%u slots does not fit in device memory", lg);
+                    CK(dev_alloc(&s->d_T, need, s->stream));
+                    s->T_bytes = need;
+                }
             }
             s->T_log2 = lg;
+            CK(cudaEventRecord(s->ev[10], s->stream));
             CK(cudaMemsetAsync(s->d_T, 0, need, s->stream));
-            CK(W_DISPATCH(s, insert(lc, s->g, s->d_mask, kp, s->ntiles, TableView{s->d_T, lg, s->inline_keys()}, s->d_ctr)));
+            // ownership planes (valid for every tile once a binned round has run) pick this round's marks
+            OwnPlanes iop = s->own;
+            iop.id = kp.part - s->prm.shard_index * s->rounds_eff + 1;
+            const bool planes_ok = brc == 0 && s->own_shared && kp.nparts > 1 && s->own_done_tiles >= s->ntiles;
+            CK(W_DISPATCH(s, insert(lc, s->g, s->d_mask, kp, s->ntiles, TableView{s->d_T, lg, s->inline_keys()}, s->d_ctr,
+                                    planes_ok ? &iop : nullptr)));
             CK(cudaEventRecord(s->ev[3], s->stream));
             CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
             CK(cudaStreamSynchronize(s->stream));
@@ -569,7 +716,8 @@ int tpc_session_find_candidates(tpc_session* s) {
         TableView T{s->d_T, s->T_log2, s->inline_keys()};
         uint64_t distinct_r = cur.distinct - prev.distinct;
         if (s->local_count + distinct_r > s->local_cap) {
-            uint64_t ncap = std::max<uint64_t>(s->local_count + distinct_r, 1024);
+            // room for the remaining rounds too (they own equal shares), so the list is grown once
+            uint64_t ncap = std::max<uint64_t>(s->local_count + distinct_r * (s->rounds_eff - r) * 9 / 8, 1024);
             unsigned long long* nl = nullptr;
             CK(dev_alloc(&nl, ncap * 8, s->stream));
             if (s->local_count) CK(cudaMemcpyAsync(nl, s->d_local, s->local_count * 8, cudaMemcpyDeviceToDevice, s->stream));
@@ -589,12 +737,16 @@ int tpc_session_find_candidates(tpc_session* s) {
         } else {
             ms_bin += b_bin; ms_fill += b_fill; ms_query += b_query;
         }
-        cudaEventElapsedTime(&t, s->ev[2], s->ev[3]); ms_insert += t;
+        cudaEventElapsedTime(&t, s->ev[10], s->ev[3]); ms_insert += t;
         cudaEventElapsedTime(&t, s->ev[3], s->ev[4]); ms_classify += t;
         prev = cur;
+        // the table is only needed inside a round (h:337-338: per-round OccurenceSet); the next round's
+        // record wave wants the memory
+        if (s->T_in_scratch) { s->d_T = nullptr; s->T_bytes = 0; s->T_in_scratch = false; }
     }
-    // the table is only needed inside a round (h:337-338: per-round OccurenceSet)
     if (s->d_T) { CK(dev_free(s->d_T, s->stream)); s->d_T = nullptr; s->T_bytes = 0; }
+    if (int rc = binned_release(s)) return rc;
+    if (s->d_own_extra) { CK(dev_free(s->d_own_extra, s->stream)); s->d_own_extra = nullptr; }
     s->st.candidate_marks = cur.marks;
     s->st.candidate_kmers = cur.distinct;
     s->st.filter_edges_set = cur.filter_new;
