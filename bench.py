@@ -316,8 +316,41 @@ def main() -> None:
                          "h2d_bytes_per_step": int(pinned.codes.nbytes + pinned.n_mask.nbytes),
                          "d2h_bytes_per_step": int(len(img)), "ms_per_step": round(e2e_s * 1e3, 3),
                          "api": "tpc_junctions_host (pinned host genome -> pinned host de_bruijn.bin image)"}
-    elif world > 1:
-        result["e2e"] = None
+    elif not args.no_e2e:
+        # N GPUs, host buffers in / host buffers out (twopaco_b200.dist.sharded_run_host): every rank uploads
+        # 1/N of the packed genome from pinned host memory, NCCL all-gathers it over NVLink, runs its shard,
+        # and copies its slice of the image back to pinned host memory.  Wall clock between barriers, max over ranks.
+        from twopaco_b200 import dist as tdist
+        runner.session.close()
+        runner.out = None
+        L = api.lib()
+        cw, mw = L.tpc_code_words(dg.n_positions), L.tpc_mask_words(dg.n_positions)
+        (c_lo, c_hi), (m_lo, m_hi) = tdist.shard_bounds(cw, rank, world), tdist.shard_bounds(mw, rank, world)
+        shard = tdist.HostGenomeShard(
+            torch.from_numpy(dg.codes.to_host((c_hi - c_lo) * 8, c_lo * 8).view(np.int64)).pin_memory(),
+            torch.from_numpy(dg.n_mask.to_host((m_hi - m_lo) * 8, m_lo * 8).view(np.int64)).pin_memory(),
+            cw, mw, dg.n_positions, dg.rec_start, dg.rec_len)
+        dg.codes.close(); dg.n_mask.close()                     # the e2e region starts from HOST buffers only
+        out_host, dev_out, times = None, None, []
+        for i in range(1 + max(1, min(args.steps, 3))):
+            barrier()
+            t0 = time.perf_counter()
+            info, out_host, dev_out = tdist.sharded_run_host(shard, rank, world, wl["k"], wl["f"], wl["q"], wl.get("rounds", 1),
+                                                             out_host, dev_out)
+            barrier()
+            if i:
+                times.append(time.perf_counter() - t0)
+        t = torch.tensor([float(np.mean(times)), float(shard.nbytes), float(info["slice_bytes"])], dtype=torch.float64, device="cuda")
+        tmax = t.clone()
+        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(t)
+        e2e_s = float(tmax[0].item())
+        result["e2e"] = {"value": round(total_bp / e2e_s / 1e9, 4), "unit": "Gbp/s",
+                         "h2d_bytes_per_step": int(t[1].item()), "d2h_bytes_per_step": int(t[2].item()),
+                         "ms_per_step": round(e2e_s * 1e3, 3),
+                         "api": "twopaco_b200.dist.sharded_run_host (each rank: pinned 1/N of the packed genome -> NCCL all-gather -> "
+                                "shard run -> its slice of the de_bruijn.bin image in pinned host memory)",
+                         "junctions": info["junctions"], "records": info["records"]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(sample, wl)

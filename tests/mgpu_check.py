@@ -51,6 +51,15 @@ def main():
                 assert bytes(image) == ref, f"multi-GPU image differs from the oracle (k={c['k']}, {mode})"
                 print(f"mgpu ok: world={world} mode={mode} k={c['k']} junctions={nj} records={nm}", flush=True)
             s.close()
+            # the same case from HOST buffers: 1/N upload + NCCL all-gather of the genome, image slices in host memory
+            sh = tdist.host_shard(g.codes, g.n_mask, g.n_positions, g.rec_start, g.rec_len, rank, world)
+            info, out_host, _ = tdist.sharded_run_host(sh, rank, world, c["k"], c["f"])
+            pieces = [None] * world
+            dist.all_gather_object(pieces, (info["slice_offset"], out_host[:info["slice_bytes"]].numpy().tobytes()))
+            if rank == 0:
+                image = b"".join(d for _, d in sorted(pieces))
+                assert image == ref, f"multi-GPU host-buffer image differs from the oracle (k={c['k']}, {mode})"
+                print(f"mgpu host-buffer ok: world={world} mode={mode} k={c['k']}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -29,6 +29,15 @@ def _worker(rank, world, port, q):
         # 3. exclusive prefix of (records, stubs)
         before, total = tdist.exclusive_prefix([10 + rank, 1], "cpu")
         assert total == [21, 2] and before == ([0, 0] if rank == 0 else [10, 1])
+        # 4. host-sliced upload + all-gather reassembles the packed genome on every rank (ragged tail)
+        import numpy as np
+        rng = np.random.default_rng(5)
+        codes = rng.integers(0, 2**63, size=1001, dtype=np.uint64)
+        nmask = rng.integers(0, 2**63, size=503, dtype=np.uint64)
+        sh = tdist.host_shard(codes, nmask, 1001 * 32 - 7, None, None, rank, world, pin=False)
+        assert sh.codes.numel() == (501 if rank == 0 else 500) and sh.n_mask.numel() == (252 if rank == 0 else 251)
+        c, m = tdist.upload_allgather(sh, rank, world, "cpu")
+        assert np.array_equal(c.numpy().view(np.uint64), codes) and np.array_equal(m.numpy().view(np.uint64), nmask)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
@@ -47,6 +56,14 @@ def test_dist_helpers_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_shard_bounds_cover_everything():
+    for n, world in ((0, 3), (1, 4), (1001, 2), (8 * 1024 + 8, 8), (7, 8)):
+        b = [tdist.shard_bounds(n, r, world) for r in range(world)]
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
+        assert all(hi - lo <= tdist.shard_chunk(n, world) for lo, hi in b)
 
 
 @pytest.mark.parametrize("npos,world", [(1, 1), (8192, 2), (100_000, 3), (21_700_000_000, 8), (5, 4)])

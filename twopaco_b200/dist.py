@@ -87,3 +87,92 @@ def sharded_run(session, genome, rank: int, world: int, out=None):
     info = dict(junctions=nj, records=trec, stubs=tstub, slice_offset=off, slice_bytes=nb,
                 image_bytes=nb if world == 1 else None)
     return info, out
+
+
+# ---------------------------------------------------------------------------------------------
+# host buffers -> host buffers on N GPUs (the multi-GPU `e2e` region of bench.py)
+# ---------------------------------------------------------------------------------------------
+class HostGenomeShard:
+    """Rank r's 1/world slice of a packed genome (codes and n_mask words [r*chunk, (r+1)*chunk)) in
+    host memory, plus the (small) record table of the whole input.  Every rank uploads only its
+    slice over its own PCIe link; the slices are then all-gathered over NVLink (`upload_allgather`),
+    which replaces the reference's per-stage re-read of the whole FASTA on every worker
+    (vertexenumerator.h:1135-1214)."""
+
+    def __init__(self, codes: torch.Tensor, n_mask: torch.Tensor, code_words: int, mask_words: int, n_positions: int,
+                 rec_start, rec_len):
+        self.codes, self.n_mask = codes, n_mask                  # int64 tensors (pinned when possible)
+        self.code_words, self.mask_words, self.n_positions = int(code_words), int(mask_words), int(n_positions)
+        self.rec_start, self.rec_len = rec_start, rec_len
+
+    @property
+    def nbytes(self) -> int:
+        return (self.codes.numel() + self.n_mask.numel()) * 8
+
+
+def shard_chunk(n_words: int, world: int) -> int:
+    return (n_words + world - 1) // world
+
+
+def shard_bounds(n_words: int, rank: int, world: int) -> tuple[int, int]:
+    c = shard_chunk(n_words, world)
+    return min(n_words, rank * c), min(n_words, (rank + 1) * c)
+
+
+def host_shard(codes, n_mask, n_positions: int, rec_start, rec_len, rank: int, world: int, pin: bool = True) -> HostGenomeShard:
+    """Slice of numpy uint64 arrays `codes` / `n_mask` that rank `rank` uploads."""
+    import numpy as np
+    out = []
+    for arr in (codes, n_mask):
+        lo, hi = shard_bounds(len(arr), rank, world)
+        t = torch.from_numpy(np.ascontiguousarray(arr[lo:hi]).view(np.int64).copy())
+        out.append(t.pin_memory() if pin and torch.cuda.is_available() else t)
+    return HostGenomeShard(out[0], out[1], len(codes), len(n_mask), n_positions, rec_start, rec_len)
+
+
+def upload_allgather(shard: HostGenomeShard, rank: int, world: int, device) -> tuple[torch.Tensor, torch.Tensor]:
+    """-> (codes, n_mask) of the WHOLE genome as int64 tensors on `device`: H2D of this rank's slice,
+    then one all-gather per array (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+    full = []
+    for host, n_words in ((shard.codes, shard.code_words), (shard.n_mask, shard.mask_words)):
+        c = shard_chunk(n_words, world)
+        whole = torch.empty(c * world, dtype=torch.int64, device=device)
+        mine = whole[rank * c:(rank + 1) * c] if world == 1 else torch.zeros(c, dtype=torch.int64, device=device)
+        mine[:host.numel()].copy_(host, non_blocking=True)
+        if host.numel() < c:
+            mine[host.numel():].zero_()
+        if world > 1:
+            dist.all_gather_into_tensor(whole, mine)
+        full.append(whole[:n_words])
+    return full[0], full[1]
+
+
+def sharded_run_host(shard: HostGenomeShard, rank: int, world: int, k: int, filter_bits: int, q: int = 5, rounds: int = 1,
+                     out_host: torch.Tensor | None = None, dev_out=None):
+    """Host buffers in, host buffers out, on `world` GPUs: upload + all-gather of the packed genome,
+    the sharded run, and the device->host copy of this rank's slice of the de_bruijn.bin image into
+    `out_host` (uint8, pinned; bytes [0, slice_bytes) = image bytes [slice_offset, +slice_bytes) --
+    a rank would pwrite() them at that offset).  Returns (info, out_host, dev_out)."""
+    import numpy as np
+    from . import api
+    codes, n_mask = upload_allgather(shard, rank, world, "cuda")
+    s = api.Session(k=k, filter_bits=filter_bits, q=q, rounds=rounds, shard_index=rank, shard_count=world)
+    try:
+        s.set_genome_device(codes.data_ptr(), n_mask.data_ptr(), shard.n_positions, shard.rec_start, shard.rec_len,
+                            keep=(codes, n_mask))
+
+        class _G:  # what sharded_run needs to know about the genome
+            n_positions, rec_len = shard.n_positions, shard.rec_len
+        info, dev_out = sharded_run(s, _G, rank, world, dev_out)
+        nb = info["slice_bytes"]
+        if out_host is None or out_host.numel() < nb:
+            out_host = torch.empty(max(nb, 16), dtype=torch.uint8)
+            if torch.cuda.is_available():
+                out_host = out_host.pin_memory()
+        if nb:
+            out_host[:nb].copy_(api.as_torch(dev_out.ptr, nb, torch.uint8), non_blocking=True)
+        torch.cuda.synchronize()
+        info["stats"] = s.stats()
+    finally:
+        s.close()
+    return info, out_host, dev_out
