@@ -36,15 +36,15 @@ sys.path.insert(0, str(ROOT))
 WORKLOADS = {
     # SURVEY.md 8(d) / BASELINE.json configs[2]: 7 x 24 x 129,166,667 bp, p = 0.001, k = 25, -f 36
     "c3": dict(name="C3: 7 synthetic human-sized genomes (7x24x129166667 bp, 0.1% divergence), k=25 -f 36 -q 5",
-               seed=0x4855, genomes=7, records=24, length=129_166_667, p=0.001, k=25, f=36, q=5, sample_bp=3_000_000),
+               seed=0x4855, genomes=7, records=24, length=129_166_667, p=0.001, k=25, f=36, q=5, sample_bp=20_000_000),
     # configs[1]: 62 x 5 Mbp, p = 0.01, k = 25, -f 32
     "c2": dict(name="C2: 62 synthetic E. coli-like genomes (62x5 Mbp, 1% divergence), k=25 -f 32 -q 5",
                seed=0xEC01, genomes=62, records=1, length=5_000_000, p=0.01, k=25, f=32, q=5, sample_bp=400_000),
     # configs[3]: the same 7-genome set at k = 63 / k = 127 (2 / 4 words per k-mer), -f 37
     "c4k63": dict(name="C4: 7 synthetic human-sized genomes (7x24x129166667 bp, 0.1% divergence), k=63 -f 37 -q 5",
-                  seed=0x4855, genomes=7, records=24, length=129_166_667, p=0.001, k=63, f=37, q=5, sample_bp=3_000_000),
+                  seed=0x4855, genomes=7, records=24, length=129_166_667, p=0.001, k=63, f=37, q=5, sample_bp=20_000_000),
     "c4k127": dict(name="C4: 7 synthetic human-sized genomes (7x24x129166667 bp, 0.1% divergence), k=127 -f 37 -q 5",
-                   seed=0x4855, genomes=7, records=24, length=129_166_667, p=0.001, k=127, f=37, q=5, sample_bp=3_000_000),
+                   seed=0x4855, genomes=7, records=24, length=129_166_667, p=0.001, k=127, f=37, q=5, sample_bp=20_000_000),
     "dev": dict(name="dev: 7x2x4 Mbp, 0.1% divergence, k=25 -f 30 -q 5",
                 seed=0xD0, genomes=7, records=2, length=4_000_000, p=0.001, k=25, f=30, q=5, sample_bp=500_000),
 }
@@ -181,6 +181,10 @@ def main() -> None:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    probe = {}
+    if rank == 0 and not args.sim_world:   # random-access roofline probe while HBM is still empty
+        for mode, name in ((0, "load32B"), (2, "load_condAtomicOr")):
+            probe[name] = round(api.random_access_probe(wl["f"], mode, 1 << 30) / 1e9, 2)
     total_bp = wl["genomes"] * wl["records"] * wl["length"]
     dg = api.synth_family_device(wl["seed"], wl["genomes"], wl["records"], wl["length"], wl["p"], keep_ascii=(rank == 0))
     total_bp = dg.total_bp
@@ -251,7 +255,15 @@ def main() -> None:
     if st.bin_waves:
         waves = st.bin_waves
         passes = 1 if waves == 1 else 2
-        kernels = {"k_bin": (per["ms_bin"], passes * (0.375 * positions + 12.0 * recs)),
+        rounds_local = wl.get("rounds", 1) * max(st.sub_rounds, 1)          # hash sub-ranges this GPU runs in sequence
+        if rounds_local * world > 1:
+            # sharded binning: ONE ownership scan (k_own: stream in, P bit planes out) + per round a k_bin_list pass
+            # (stream + planes in, 12 B per owned record out)
+            planes = max(1, rounds_local.bit_length())
+            bin_bytes = (0.375 + 0.125 * planes) * positions * (1 + passes * rounds_local) + passes * 12.0 * recs
+        else:
+            bin_bytes = passes * (0.375 * positions + 12.0 * recs)
+        kernels = {"k_bin": (per["ms_bin"], bin_bytes),
                    "k_apply_fill": (per["ms_fill"], 8.0 * recs + 2.0 * filter_bytes * waves),
                    "k_apply_query": (per["ms_query"], 8.0 * recs + 8.0 * marks + filter_bytes * waves)}
     else:
@@ -278,6 +290,18 @@ def main() -> None:
                 "filter_touches_per_s_G": {k: round(recs / (v[0] * 1e-3) / 1e9, 2) for k, v in kernels.items()
                                             if v[0] > 0 and k != "k_bin"},
                 "all_filter_kernels": {k: {"ms": round(v[0], 3), "GBps": gbps(*v)} for k, v in kernels.items()}}
+
+    # the north-star's second roofline: uniform random 32-byte sector touches into a table of the filter's size
+    # (k_probe, measured in this run before the workload was generated).  The binned path does not touch HBM at
+    # random any more, so its effective rate (2 touches per owned k-mer over binning + fill + query) may exceed it.
+    t_filter = sum(per[k] for k in ("ms_bin", "ms_fill", "ms_query")) * 1e-3
+    eff = 2.0 * recs / t_filter / 1e9 if t_filter > 0 else None
+    roofline["random_access"] = {
+        "probe_Gtouch_s": probe, "unit": "G sector touches/s", "table_bits": wl["f"],
+        "achieved_Gtouch_s": round(eff, 2) if eff else None,
+        "frac": round(eff / probe["load_condAtomicOr"], 3) if eff and probe.get("load_condAtomicOr") else None,
+        "note": "achieved = (1 fill + 1 query touch per owned k-mer) / (ms_bin + ms_fill + ms_query); "
+                "frac is against the probe's load+conditional-atomicOr rate"}
 
     result = {
         "metric": "input Gbp/s to exact junction set", "value": round(total_bp / (ms_per_step * 1e-3) / 1e9, 4), "unit": "Gbp/s",

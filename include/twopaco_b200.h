@@ -178,7 +178,10 @@ int tpc_session_local_junctions(tpc_session *s, const uint64_t **dev_words, uint
 int tpc_session_set_junctions(tpc_session *s, const uint64_t *dev_words_all, uint64_t count_all);
 
 /* Candidate mask of this shard: 1 bit per position, 32-bit words (bit i of word w = position
- * 32w+i).  Masks of different shards are disjoint; OR (== sum) them before emitting. */
+ * 32w+i).  Masks of different shards are disjoint; OR (== sum) them before emitting.  n_words is
+ * padded (with zero words) to shard_count equal chunks of whole 8192-position tiles, chunk r being
+ * the slice shard r emits: a reduce-scatter of the shards' masks lands each chunk where
+ * tpc_session_emit_count reads it (only the words of the emitted slice have to be complete). */
 int tpc_session_candidate_mask(tpc_session *s, uint32_t **dev_mask, uint64_t *n_words);
 
 /* EdgeConstructionWorker (h:856-993) + JunctionPositionWriter (junctionapi.h:107-137) for the

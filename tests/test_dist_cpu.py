@@ -26,6 +26,11 @@ def _worker(rank, world, port, q):
             m[0], m[2] = 0b1010, 7
         tdist.or_reduce_disjoint_(m)
         assert m.tolist() == [0b1111, -2**31, 7, 0]
+        m2 = torch.zeros(4, dtype=torch.int32)
+        m2[rank * 2] = 5 + rank
+        m2[3 - rank * 2] = 64
+        tdist.or_reduce_scatter_disjoint_(m2, rank, world)
+        assert m2[rank * 2:rank * 2 + 2].tolist() == ([5, 64] if rank == 0 else [6, 64])
         # 3. exclusive prefix of (records, stubs)
         before, total = tdist.exclusive_prefix([10 + rank, 1], "cpu")
         assert total == [21, 2] and before == ([0, 0] if rank == 0 else [10, 1])
@@ -71,4 +76,7 @@ def test_position_cuts(npos, world):
     cuts = tdist.position_cuts(npos, world)
     assert len(cuts) == world + 1 and cuts[0] == 0 and cuts[-1] == npos
     assert all(a <= b for a, b in zip(cuts, cuts[1:]))
-    assert all(c % tdist.TILE_POSITIONS == 0 for c in cuts[:-1])
+    assert all(c % tdist.TILE_POSITIONS == 0 or c == npos for c in cuts[:-1])
+    tiles = (npos + tdist.TILE_POSITIONS - 1) // tdist.TILE_POSITIONS
+    chunk = (tiles + world - 1) // world
+    assert all(b - a <= chunk * tdist.TILE_POSITIONS for a, b in zip(cuts, cuts[1:]))

@@ -240,22 +240,29 @@ k_own(GenomeView g, KParams kp, uint32_t part_base, uint32_t nlocal, uint64_t wo
 constexpr int kBinListMax = kTilePos;
 // R = records per thread per staging round (stage = 256 R records); small R = more CTAs per SM
 constexpr size_t bin_list_smem_bytes(int R) {
-    return kBinMaxBuckets * 8 + kBinMaxBuckets * 4 * 2 + 8 * 4 + 16 + (size_t)kTileThreads * R * (4 * 3 + 1) + kBinListMax * 2 +
-           (kTileCodeWords + kTileMaskWords) * 8;
+    return kBinMaxBuckets * 8 * 2 + kBinMaxBuckets * 4 * 2 + 8 * 4 + 16 + (size_t)kTileThreads * R * (4 * 3 + 1) + kBinListMax * 2 +
+           2 * (kTileCodeWords + kTileMaskWords) * 8;
+}
+
+// 8-byte asynchronous global->shared copy (LDGSTS): the next tile's genome words travel while this
+// tile is being processed
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
 }
 
 template <int W, int R>
-__global__ void __launch_bounds__(kTileThreads, (R <= 8 ? 3 : 2))
+__global__ void __launch_bounds__(kTileThreads, (R <= 8 ? 4 : 2))
 k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_end, uint64_t wave_base, OwnPlanes op) {
     constexpr uint32_t kStage = kTileThreads * R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* gbase = reinterpret_cast<unsigned long long*>(smem_raw);
-    uint64_t* s_codes = reinterpret_cast<uint64_t*>(gbase + kBinMaxBuckets);   // words tw0-1 .. of the tile
-    uint64_t* s_nmask = s_codes + kTileCodeWords;                              // words (tw0-1)/2 .. (64 positions each)
-    uint32_t* hist = reinterpret_cast<uint32_t*>(s_nmask + kTileMaskWords);
+    unsigned long long* gbase = reinterpret_cast<unsigned long long*>(smem_raw);    // records reserved before this chunk, per slice
+    uint32_t** gptr = reinterpret_cast<uint32_t**>(gbase + kBinMaxBuckets);         // where staged record 0 would go, per slice
+    uint64_t* s_stage = reinterpret_cast<uint64_t*>(gptr + kBinMaxBuckets);         // 2 x {code words tw0-1 .., n-mask words (tw0-1)/2 ..}
+    uint32_t* hist = reinterpret_cast<uint32_t*>(s_stage + 2 * (kTileCodeWords + kTileMaskWords));
     uint32_t* pref = hist + kBinMaxBuckets;
     uint32_t* warp_tot = pref + kBinMaxBuckets;
-    uint32_t* list_total = warp_tot + 8;
+    uint32_t* list_total = warp_tot + 8;      // [0] owned positions of the tile, [1] a slice ran over its array in this chunk
     uint32_t* st_a = list_total + 4;
     uint32_t* st_b = st_a + kStage;
     uint32_t* st_c = st_b + kStage;
@@ -263,9 +270,31 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
     uint8_t* st_k = reinterpret_cast<uint8_t*>(list + kBinListMax);           // slice of each staged record
     const uint32_t sib_mask = (1u << bin.sib_bits) - 1u;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t kmask1 = top_mask<1>(kp.k < 32 ? kp.k : 31);              // W == 1 only
+    const uint32_t nxt_shift = 2 * kp.k + 2;                                  // W == 1, k <= 29: next base inside the 32-base window
 
-    for (uint64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
-        uint32_t own = own_word(op, tile * kTileThreads + tid);
+    // Software pipeline over the CTA's tiles: the ownership word and the packed-genome words of tile t+1
+    // are requested (register / cp.async into the other staging buffer) before tile t is processed, so no
+    // HBM latency sits between the barriers of a tile.
+    auto request_tile = [&](uint64_t t, int buf) {
+        const uint64_t w0 = t * kTileThreads, cb = w0 ? w0 - 1 : 0, mb = cb >> 1;
+        uint64_t* sc = s_stage + buf * (kTileCodeWords + kTileMaskWords);
+        uint64_t* sm = sc + kTileCodeWords;
+        for (int j = tid; j < kTileCodeWords; j += kTileThreads) cp_async8(sc + j, g.codes + cb + j);
+        for (int j = tid; j < kTileMaskWords; j += kTileThreads) cp_async8(sm + j, g.nmask + mb + j);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint64_t tile = tile_begin + blockIdx.x;
+    uint32_t own_next = 0;
+    int buf = 0;
+    if (tile < tile_end) {
+        own_next = own_word(op, tile * kTileThreads + tid);
+        request_tile(tile, 0);
+    }
+    for (; tile < tile_end; tile += gridDim.x, buf ^= 1) {
+        uint32_t own = own_next;
+        const uint64_t* s_codes = s_stage + buf * (kTileCodeWords + kTileMaskWords);
+        const uint64_t* s_nmask = s_codes + kTileCodeWords;
         const uint64_t tw0 = tile * kTileThreads;              // first code word of the tile
         const uint64_t cw_base = tw0 ? tw0 - 1 : 0;            // s_codes[0] = word cw_base
         const uint64_t mw_base = cw_base >> 1;                 // s_nmask[0] = word mw_base
@@ -276,30 +305,39 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
             uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        __syncthreads();  // previous tile's readers of list / warp_tot / s_codes are done
+        asm volatile("cp.async.wait_group 0;" ::: "memory");   // this tile's genome words (my copies) have landed
+        __syncthreads();  // ... everybody's; the previous tile's readers of list / warp_tot / the other buffer are done
         if (lane == 31) warp_tot[wid] = incl;
-        // stage the tile's slice of the packed genome (coalesced) for the dense phase
-        for (int j = tid; j < kTileCodeWords; j += kTileThreads) s_codes[j] = __ldg(g.codes + cw_base + j);
-        for (int j = tid; j < kTileMaskWords; j += kTileThreads) s_nmask[j] = __ldg(g.nmask + mw_base + j);
-        __syncthreads();
+        if (tile + gridDim.x < tile_end) {                     // next tile: in flight during this tile's dense phase
+            own_next = own_word(op, (tile + gridDim.x) * kTileThreads + tid);
+            request_tile(tile + gridDim.x, buf ^ 1);
+        }
+        uint64_t n_any = 0;
+        for (int j = tid; j < kTileMaskWords; j += kTileThreads) n_any |= s_nmask[j];
+        // no 'N' anywhere near the tile (all but the tiles holding a record boundary or an N run): the
+        // dense phase then needs no n-mask look-ups at all
+        const bool tile_has_n = __syncthreads_or(n_any != 0) != 0;
         uint32_t off = incl - cnt;
         for (int j = 0; j < wid; ++j) off += warp_tot[j];
-        if (tid == kTileThreads - 1) *list_total = off + cnt;
+        if (tid == kTileThreads - 1) list_total[0] = off + cnt;
         while (own) {
             int i = __ffs(own) - 1;
             own &= own - 1;
             list[off++] = (uint16_t)(tid * 32 + i);
         }
         __syncthreads();
-        const uint32_t total = *list_total;
+        const uint32_t total = list_total[0];
         const uint32_t c_off = (uint32_t)(tw0 - cw_base) * 32;          // tile-local -> s_codes-local position
         const uint32_t m_off = (uint32_t)(tw0 * 32 - mw_base * 64);     // tile-local -> s_nmask-local position
         const uint64_t tile_rel = tile * kTilePos - wave_base;
+        const uint32_t rel_high = (uint32_t)(tile_rel >> 32) << bin.sib_bits;   // a tile never straddles a 2^32 boundary of the wave
+        const uint32_t rel_low = (uint32_t)tile_rel;
 
         // dense processing of the list, kStage records per round
         for (uint32_t c0 = 0; c0 < total; c0 += kStage) {
             const uint32_t n = min(kStage, total - c0);
             hist[tid] = 0;
+            if (tid == 0) list_total[1] = 0;
             __syncthreads();
             uint32_t rm[R], rw[R], rk[R];
 #pragma unroll
@@ -309,19 +347,35 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
                 if (e < n) {
                     const uint32_t tp = list[c0 + e];                // tile-local position (>= 1 when tile 0: position 0 is N)
                     const uint32_t lp = tp + c_off;
-                    Kmer<W> X = extract_kmer_smem<W>(s_codes, lp, kp.k);
-                    Kmer<W> Y = revcomp<W>(X, kp.k);
+                    Kmer<W> X, Y;
+                    uint32_t prv, nxt;
+                    if (W == 1) {
+                        // one unaligned 32-base window starting at the previous base holds prev | k-mer | next (k <= 29)
+                        const uint32_t q0 = lp - 1, wi = q0 >> 5, sh = 2 * (q0 & 31);
+                        const uint64_t lo = s_codes[wi], hi = s_codes[wi + 1];
+                        const uint64_t win = (lo >> sh) | ((hi << 1) << (63 - sh));
+                        prv = (uint32_t)win & 3u;
+                        X.w[0] = (win >> 2) & kmask1;
+                        nxt = (kp.k >= 31 ? (uint32_t)(hi >> sh) : (uint32_t)(win >> nxt_shift)) & 3u;   // k = 31: base 32 of the window
+                    } else {
+                        X = extract_kmer_smem<W>(s_codes, lp, kp.k);
+                        const uint32_t pp = lp - 1, np = lp + kp.k;
+                        prv = (uint32_t)(s_codes[pp >> 5] >> (2 * (pp & 31))) & 3u;
+                        nxt = (uint32_t)(s_codes[np >> 5] >> (2 * (np & 31))) & 3u;
+                    }
+                    Y = revcomp<W>(X, kp.k);
                     const bool fwd = kmer_less<W>(X, Y);
                     const uint64_t h = kmer_hash<W>(kmer_select<W>(fwd, X, Y), kp.seed);
-                    const uint32_t pp = lp - 1, np = lp + kp.k, pm = tp + m_off - 1, nm = tp + m_off + kp.k;
-                    const uint32_t code = occurrence_code(fwd, (uint32_t)(s_codes[pp >> 5] >> (2 * (pp & 31))) & 3u,
-                                                          (uint32_t)(s_codes[np >> 5] >> (2 * (np & 31))) & 3u,
-                                                          (uint32_t)(s_nmask[pm >> 6] >> (pm & 63)) & 1u,
-                                                          (uint32_t)(s_nmask[nm >> 6] >> (nm & 63)) & 1u);
+                    uint32_t pn = 0, nn = 0;
+                    if (tile_has_n) {
+                        const uint32_t pm = tp + m_off - 1, nm = tp + m_off + kp.k;
+                        pn = (uint32_t)(s_nmask[pm >> 6] >> (pm & 63)) & 1u;
+                        nn = (uint32_t)(s_nmask[nm >> 6] >> (nm & 63)) & 1u;
+                    }
+                    const uint32_t code = occurrence_code(fwd, prv, nxt, pn, nn);
                     const uint64_t s = hash_sector(h, kp.sector_shift);
-                    const uint64_t rel64 = tile_rel + tp;
                     rm[j] = mask_seed(h);
-                    rw[j] = ((uint32_t)s & sib_mask) | ((uint32_t)(rel64 >> 32) << bin.sib_bits) | (code << kBinCodeShift);
+                    rw[j] = ((uint32_t)s & sib_mask) | rel_high | (code << kBinCodeShift);
                     const uint32_t bucket = (uint32_t)(s >> bin.sib_bits);
                     rk[j] = (bucket << 16) | atomicAdd(&hist[bucket], 1u);
                 }
@@ -337,8 +391,11 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
             __syncthreads();
             uint32_t base = 0;
             for (int j = 0; j < wid; ++j) base += warp_tot[j];
-            pref[tid] = base + hincl - hc;
-            if (hc) gbase[tid] = atomicAdd(&bin.count[tid], (unsigned long long)hc);
+            const uint32_t my_pref = base + hincl - hc;
+            pref[tid] = my_pref;
+            // thread tid reserves the run of slice tid; the answer is only needed after the scatter below
+            unsigned long long gb = 0;
+            if (hc) gb = atomicAdd(&bin.count[tid], (unsigned long long)hc);
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < R; ++j) {
@@ -346,24 +403,39 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
                     uint32_t idx = pref[rk[j] >> 16] + (rk[j] & 0xFFFFu);
                     st_a[idx] = rm[j];
                     st_b[idx] = rw[j];
-                    st_c[idx] = (uint32_t)(tile_rel + list[c0 + tid + j * kTileThreads]);
+                    st_c[idx] = rel_low + list[c0 + tid + j * kTileThreads];
                     st_k[idx] = (uint8_t)(rk[j] >> 16);
                 }
+            }
+            if (hc) {
+                gbase[tid] = gb;
+                gptr[tid] = bin.rec + (uint64_t)tid * 3 * bin.cap + gb - my_pref;   // + stage index = the record's place
+                if (gb + hc > bin.cap) list_total[1] = 1;
             }
             __syncthreads();
             // copy-out: one thread per staged record (records of a slice are contiguous in the stage, so
             // neighbouring threads write neighbouring words of the slice's arrays)
-            for (uint32_t idx = tid; idx < n; idx += kTileThreads) {
-                const uint32_t b = st_k[idx];
-                const unsigned long long dst = gbase[b] + (idx - pref[b]);
-                if (dst < bin.cap) {
-                    uint32_t* ra = bin.rec + (uint64_t)b * 3 * bin.cap + dst;
+            if (list_total[1] == 0) {
+                const uint64_t cap = bin.cap;
+                for (uint32_t idx = tid; idx < n; idx += kTileThreads) {
+                    uint32_t* ra = gptr[st_k[idx]] + idx;
                     __stcs(ra, st_a[idx]);
-                    __stcs(ra + bin.cap, st_b[idx]);
-                    __stcs(ra + 2 * bin.cap, st_c[idx]);
-                } else {
-                    unsigned long long o = atomicAdd(bin.ov_count, 1ull);
-                    if (o < bin.ov_cap) reinterpret_cast<uint4*>(bin.ov)[o] = make_uint4(st_a[idx], st_b[idx], st_c[idx], b);
+                    __stcs(ra + cap, st_b[idx]);
+                    __stcs(ra + 2 * cap, st_c[idx]);
+                }
+            } else {   // a slice's array is full (repeat-rich input): per-record bound check, overflow list
+                for (uint32_t idx = tid; idx < n; idx += kTileThreads) {
+                    const uint32_t b = st_k[idx];
+                    const unsigned long long dst = gbase[b] + (idx - pref[b]);
+                    if (dst < bin.cap) {
+                        uint32_t* ra = bin.rec + (uint64_t)b * 3 * bin.cap + dst;
+                        __stcs(ra, st_a[idx]);
+                        __stcs(ra + bin.cap, st_b[idx]);
+                        __stcs(ra + 2 * bin.cap, st_c[idx]);
+                    } else {
+                        unsigned long long o = atomicAdd(bin.ov_count, 1ull);
+                        if (o < bin.ov_cap) reinterpret_cast<uint4*>(bin.ov)[o] = make_uint4(st_a[idx], st_b[idx], st_c[idx], b);
+                    }
                 }
             }
             __syncthreads();

@@ -217,24 +217,37 @@ k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t n
     const uint64_t capmask = (1ull << T.log2cap) - 1;
     const uint64_t probe_limit = capmask < 8192 ? capmask : 8192;  // a longer run means the table is too full: host grows it
     unsigned long long claimed = 0;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t w = tile * kTileThreads + threadIdx.x;
-        uint32_t m = mask[w];
+    // this round's marks of a tile (software-pipelined: the next tile's words are requested while this one is processed)
+    auto marks_of = [&](uint64_t t) -> uint32_t {
+        const uint64_t w = t * kTileThreads + threadIdx.x;
+        uint32_t m = __ldcs(mask + w);
         if (op.n) m &= own_word(op, w);
+        return m;
+    };
+    uint64_t tile = blockIdx.x;
+    uint32_t m_next = 0;
+    int buf = 0;
+    if (tile < ntiles) { m_next = marks_of(tile); tile_request(ts, g, tile, 0); }
+    for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const uint32_t m = m_next;
         TileGeom tg;
-        const uint32_t total = tile_compact(ts, g, tile, m, tg);
+        const uint32_t total = tile_compact(ts, tile, buf, m, tg, [&]() {
+            if (tile + gridDim.x < ntiles) { m_next = marks_of(tile + gridDim.x); tile_request(ts, g, tile + gridDim.x, buf ^ 1); }
+        });
+        const uint64_t* s_codes = ts.codes[buf];
+        const uint64_t* s_nmask = ts.nmask[buf];
         for (uint32_t e = threadIdx.x; e < total; e += kTileThreads) {
             const uint32_t tp = ts.list[e];
             const uint64_t p = tile * kTilePos + tp;
             const uint32_t lp = tp + tg.c_off, mp = tp + tg.m_off;
             Occ<W> o;
-            o.X = extract_kmer_smem<W>(ts.codes, lp, kp.k);
+            o.X = extract_kmer_smem<W>(s_codes, lp, kp.k);
             o.Y = revcomp<W>(o.X, kp.k);
             o.fwd = kmer_less<W>(o.X, o.Y);
             const Kmer<W> canon = kmer_select<W>(o.fwd, o.X, o.Y);
             if (!op.n && kp.nparts > 1 && owner_part(owner_fold<W>(canon), kp.nparts) != kp.part) continue;  // marked in another round
             o.h = kmer_hash<W>(canon, kp.seed);
-            Neigh nb = orient(o.fwd, stage_base(ts, lp - 1), stage_base(ts, lp + kp.k), stage_n(ts, mp - 1), stage_n(ts, mp + kp.k));
+            Neigh nb = orient(o.fwd, stage_base(s_codes, lp - 1), stage_base(s_codes, lp + kp.k), stage_n(s_nmask, mp - 1), stage_n(s_nmask, mp + kp.k));
             // neighbour sets in canonical orientation (candidateoccurence.h:25-50; h:778-796)
             unsigned long long want = 0;
             if (!nb.a_n) want |= 1ull << nb.a;

@@ -4,6 +4,7 @@
 #include "tpc_kernels.cuh"
 #include "tpc_launch.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace tpc {
 
@@ -96,9 +97,13 @@ cudaError_t Launch<W>::bin(const LaunchCtx& c, GenomeView g, KParams kp, const B
     if (planes) {
         // dense binning of the owned positions; stage size >= 1.25 x the expected owned positions of a
         // tile (more CTAs per SM when it is small)
-        const uint32_t expect = (uint32_t)(kTilePos / kp.nparts) * 5 / 4;
+        uint32_t expect = (uint32_t)(kTilePos / kp.nparts) * 5 / 4;
+        static const int force_r = getenv("TPC_BIN_R") ? atoi(getenv("TPC_BIN_R")) : 0;   // tuning aid
+        if (force_r) expect = (uint32_t)force_r * kTileThreads;
+        // (a 2048-record stage with 4 CTAs per SM beats a 4096-record stage with 2: the barriers and the global
+        // reservations of one CTA are hidden by the others)
         if (expect <= 4 * kTileThreads) launch_bin_list<W, 4>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
-        else if (expect <= 8 * kTileThreads) launch_bin_list<W, 8>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
+        else if (force_r != 16) launch_bin_list<W, 8>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
         else launch_bin_list<W, 16>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
     } else {
         static bool configured = false;

@@ -604,17 +604,26 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
     return 0;
 }
 
+static uint64_t padded_mask_words(const tpc_session* s) {
+    const uint64_t n = std::max<uint32_t>(s->prm.shard_count, 1);
+    const uint64_t chunk_tiles = (s->ntiles + n - 1) / n;
+    return std::max<uint64_t>(chunk_tiles * n * kTileThreads, 1);
+}
+
 int tpc_session_find_candidates(tpc_session* s) {
     if (!s || !s->g.codes) return set_error("no genome set");
     LaunchCtx lc = s->lctx();
     const uint64_t mask_words = s->ntiles * kTileThreads;
     const uint64_t filter_bytes = (1ull << s->filter_bits_eff) / 8;
     if (!s->d_filter) CK(dev_alloc(&s->d_filter, filter_bytes, s->stream));
+    // the candidate mask is padded to shard_count equal tile-aligned chunks so that the shards' masks can be
+    // reduce-scattered straight into the position slices the GPUs emit (tpc_session_candidate_mask)
+    const uint64_t mask_words_padded = padded_mask_words(s);
     if (!s->d_mask) {
-        CK(dev_alloc(&s->d_mask, std::max<uint64_t>(mask_words, 1) * 4, s->stream));
+        CK(dev_alloc(&s->d_mask, mask_words_padded * 4, s->stream));
         CK(dev_alloc(&s->d_stubmask, std::max<uint64_t>(mask_words, 1) * 4, s->stream));
     }
-    CK(cudaMemsetAsync(s->d_mask, 0, std::max<uint64_t>(mask_words, 1) * 4, s->stream));
+    CK(cudaMemsetAsync(s->d_mask, 0, mask_words_padded * 4, s->stream));
     CK(cudaMemsetAsync(s->d_ctr, 0, sizeof(Counters), s->stream));
     s->local_count = 0;
     s->st = tpc_stats{};
@@ -797,7 +806,7 @@ int tpc_session_set_junctions(tpc_session* s, const uint64_t* dev_words_all, uin
 int tpc_session_candidate_mask(tpc_session* s, uint32_t** dev_mask, uint64_t* n_words) {
     if (!s || !s->d_mask) return set_error("find_candidates has not run");
     if (dev_mask) *dev_mask = s->d_mask;
-    if (n_words) *n_words = s->ntiles * kTileThreads;
+    if (n_words) *n_words = padded_mask_words(s);
     return 0;
 }
 
@@ -805,10 +814,11 @@ int tpc_session_emit_count(tpc_session* s, uint64_t pos_begin, uint64_t pos_end,
     if (!s || !s->have_index || !s->d_mask) return set_error("set_junctions has not run");
     if (pos_end > s->g.npos) pos_end = s->g.npos;
     if (pos_begin > pos_end) pos_begin = pos_end;
-    if (pos_begin % kTilePos) return set_error("emit slice must start at a multiple of %d", kTilePos);
+    if (pos_begin % kTilePos && pos_begin != s->g.npos) return set_error("emit slice must start at a multiple of %d", kTilePos);
     if (pos_end % kTilePos && pos_end != s->g.npos) return set_error("emit slice must end at a multiple of %d", kTilePos);
     LaunchCtx lc = s->lctx();
     uint64_t tb = pos_begin / kTilePos, te = (pos_end + kTilePos - 1) / kTilePos;
+    if (pos_begin >= pos_end) te = tb;   // empty slice (more shards than tiles)
     uint64_t nt = te - tb;
     if (nt + 1 > s->tile_cap) {
         for (void* p : {(void*)s->d_tile_rec, (void*)s->d_tile_stub, (void*)s->d_scan_scratch})

@@ -32,21 +32,41 @@ constexpr int kTileCodeWords = kTileThreads + 8;        // tile + one word befor
 constexpr int kTileMaskWords = kTileThreads / 2 + 4;
 
 struct TileStage {
-    uint64_t codes[kTileCodeWords];   // code words cw_base .. of the tile
-    uint64_t nmask[kTileMaskWords];   // n-mask words mw_base ..
-    uint16_t list[kTilePos];          // tile-local positions of the set bits, in position order
+    uint64_t codes[2][kTileCodeWords];   // double-buffered: code words cw_base .. of the tile
+    uint64_t nmask[2][kTileMaskWords];   // n-mask words mw_base ..
+    uint16_t list[kTilePos];             // tile-local positions of the set bits, in position order
     uint32_t warp_tot[kTileThreads / 32];
     uint32_t total;
 };
 
 struct TileGeom {
-    uint32_t c_off;   // tile-local position -> position inside TileStage::codes
-    uint32_t m_off;   // tile-local position -> position inside TileStage::nmask
+    uint32_t c_off;   // tile-local position -> position inside TileStage::codes[buf]
+    uint32_t m_off;   // tile-local position -> position inside TileStage::nmask[buf]
 };
 
-// All threads of the CTA call this with their 32-position bit word of the tile.  Returns the number of
-// set bits of the tile; ts.list holds them; ts.codes / ts.nmask hold the tile's genome.
-__device__ __forceinline__ uint32_t tile_compact(TileStage& ts, const GenomeView& g, uint64_t tile, uint32_t bits, TileGeom& tg) {
+// 8-byte asynchronous global->shared copy (LDGSTS)
+__device__ __forceinline__ void tile_cp_async8(void* smem, const void* gmem) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+
+// Request the packed-genome words of `tile` into buffer `buf` (all threads of the CTA call this; one
+// cp.async group per call).  tile_compact of that tile waits for them.
+__device__ __forceinline__ void tile_request(TileStage& ts, const GenomeView& g, uint64_t tile, int buf) {
+    const uint64_t tw0 = tile * kTileThreads, cw_base = tw0 ? tw0 - 1 : 0, mw_base = cw_base >> 1;
+    for (int j = threadIdx.x; j < kTileCodeWords; j += kTileThreads) tile_cp_async8(&ts.codes[buf][j], g.codes + cw_base + j);
+    for (int j = threadIdx.x; j < kTileMaskWords; j += kTileThreads) tile_cp_async8(&ts.nmask[buf][j], g.nmask + mw_base + j);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// All threads of the CTA call this with their 32-position bit word of the tile, whose genome words were
+// requested into buffer `buf` before.  `prefetch_next()` is called by every thread once the other buffer
+// is free (the caller loads the next tile's bit word and calls tile_request there), so that the next
+// tile's HBM latency overlaps this tile's work.  Returns the number of set bits of the tile; ts.list
+// holds them; ts.codes[buf] / ts.nmask[buf] hold the tile's genome.
+template <typename Prefetch>
+__device__ __forceinline__ uint32_t tile_compact(TileStage& ts, uint64_t tile, int buf, uint32_t bits, TileGeom& tg,
+                                                 Prefetch prefetch_next) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t tw0 = tile * kTileThreads;              // first code word of the tile
     const uint64_t cw_base = tw0 ? tw0 - 1 : 0;
@@ -59,10 +79,10 @@ __device__ __forceinline__ uint32_t tile_compact(TileStage& ts, const GenomeView
         uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
     }
-    __syncthreads();  // the previous tile's readers of the stage are done
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // my copies of this tile's genome words have landed
+    __syncthreads();  // ... everybody's; the previous tile's readers of the stage are done
     if (lane == 31) ts.warp_tot[wid] = incl;
-    for (int j = tid; j < kTileCodeWords; j += kTileThreads) ts.codes[j] = __ldg(g.codes + cw_base + j);
-    for (int j = tid; j < kTileMaskWords; j += kTileThreads) ts.nmask[j] = __ldg(g.nmask + mw_base + j);
+    prefetch_next();
     __syncthreads();
     uint32_t off = incl - cnt;
     for (int j = 0; j < wid; ++j) off += ts.warp_tot[j];
@@ -91,11 +111,11 @@ __device__ __forceinline__ Kmer<W> extract_kmer_smem(const uint64_t* words, uint
     x.w[W - 1] &= top_mask<W>(k);
     return x;
 }
-__device__ __forceinline__ uint32_t stage_base(const TileStage& ts, uint32_t lp) {   // lp: position inside ts.codes
-    return (uint32_t)(ts.codes[lp >> 5] >> (2 * (lp & 31))) & 3u;
+__device__ __forceinline__ uint32_t stage_base(const uint64_t* codes, uint32_t lp) {   // lp: position inside the staged codes
+    return (uint32_t)(codes[lp >> 5] >> (2 * (lp & 31))) & 3u;
 }
-__device__ __forceinline__ uint32_t stage_n(const TileStage& ts, uint32_t mp) {      // mp: position inside ts.nmask
-    return (uint32_t)(ts.nmask[mp >> 6] >> (mp & 63)) & 1u;
+__device__ __forceinline__ uint32_t stage_n(const uint64_t* nmask, uint32_t mp) {      // mp: position inside the staged n-mask
+    return (uint32_t)(nmask[mp >> 6] >> (mp & 63)) & 1u;
 }
 
 }  // namespace tpc

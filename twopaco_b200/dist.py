@@ -4,7 +4,7 @@ The exchanges of DESIGN.md section 4 ("Multi-GPU"), written against torch.distri
 over NCCL on GPUs and over gloo on CPU (tests/test_dist_cpu.py):
 
   1. all-gather of the shards' junction words (variable length)      -> identical global id index
-  2. OR-reduce of the disjoint candidate masks (sum == or)
+  2. OR-reduce-scatter of the disjoint candidate masks (sum == or) into the position slices
   3. exclusive prefix of (records, stubs) over the position slices    -> ordered, position-sharded emit
 """
 from __future__ import annotations
@@ -17,9 +17,11 @@ TILE_POSITIONS = 8192
 
 def position_cuts(n_positions: int, world: int) -> list[int]:
     """Slice boundaries (multiples of the 8192-position tile, last = n_positions): rank r emits
-    positions [cuts[r], cuts[r+1])."""
+    positions [cuts[r], cuts[r+1]).  The slices are `world` equal chunks of whole tiles (the last ones
+    may be short or empty) -- the chunks of the padded candidate mask (tpc_session_candidate_mask)."""
     tiles = (n_positions + TILE_POSITIONS - 1) // TILE_POSITIONS
-    return [min(n_positions, (tiles * r // world) * TILE_POSITIONS) for r in range(world)] + [n_positions]
+    chunk = (tiles + world - 1) // world
+    return [min(n_positions, r * chunk * TILE_POSITIONS) for r in range(world)] + [n_positions]
 
 
 def allgather_varlen(local: torch.Tensor) -> torch.Tensor:
@@ -41,6 +43,22 @@ def or_reduce_disjoint_(mask_words: torch.Tensor) -> torch.Tensor:
     """In-place OR over ranks of bit masks whose set bits are disjoint between ranks (each position's
     k-mer belongs to exactly one hash range, vertexenumerator.h:638), so integer sum == OR."""
     dist.all_reduce(mask_words, op=dist.ReduceOp.SUM)
+    return mask_words
+
+
+def or_reduce_scatter_disjoint_(mask_words: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Like or_reduce_disjoint_, but only chunk `rank` of the (padded, world equal chunks) mask is
+    completed on this rank -- all the position-sharded emit reads.  NCCL: one reduce-scatter, which
+    moves half the bytes of the all-reduce; gloo (CPU tests) has no reduce-scatter: all-reduce."""
+    n = mask_words.numel()
+    assert n % world == 0, (n, world)
+    c = n // world
+    if dist.get_backend() == "nccl":
+        mine = torch.empty(c, dtype=mask_words.dtype, device=mask_words.device)
+        dist.reduce_scatter_tensor(mine, mask_words, op=dist.ReduceOp.SUM)
+        mask_words[rank * c:(rank + 1) * c].copy_(mine)
+    else:
+        dist.all_reduce(mask_words, op=dist.ReduceOp.SUM)
     return mask_words
 
 
@@ -75,7 +93,7 @@ def sharded_run(session, genome, rank: int, world: int, out=None):
         allj = allgather_varlen(api.as_torch(ptr, n, torch.int64))            # exchange 1
         s.set_junctions(allj.data_ptr(), allj.numel())
         mptr, mw = s.candidate_mask()
-        or_reduce_disjoint_(api.as_torch(mptr, mw, torch.int32))               # exchange 2
+        or_reduce_scatter_disjoint_(api.as_torch(mptr, mw, torch.int32), rank, world)   # exchange 2
         cut = position_cuts(genome.n_positions, world)
         nrec, nstub = s.emit_count(cut[rank], cut[rank + 1])
         (rb, sb), (trec, tstub) = exclusive_prefix([nrec, nstub], "cuda")     # exchange 3
