@@ -14,6 +14,8 @@ struct LaunchCtx {
     cudaStream_t stream;
     int sm_count;
     uint32_t* launches;  // incremented per kernel launch
+    int bin_ctas = 0;    // cap on resident CTAs per SM of the binning kernels (0 = what fits): two kernels bound by
+    int apply_ctas = 0;  //   different pipes share the SMs when the rounds are pipelined; same for the apply kernels
 };
 
 template <int W>

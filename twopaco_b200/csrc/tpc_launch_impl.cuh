@@ -64,6 +64,7 @@ static void launch_bin_list(const LaunchCtx& c, GenomeView g, KParams kp, const 
     }
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_list<W, R>, kTileThreads, smem);
+    if (c.bin_ctas > 0 && per_sm > c.bin_ctas) per_sm = c.bin_ctas;
     uint64_t grid = std::min<uint64_t>((uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count, tile_end - tile_begin);
     k_bin_list<W, R><<<(int)grid, kTileThreads, smem, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base, op);
 }

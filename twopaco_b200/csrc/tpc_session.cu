@@ -114,7 +114,7 @@ cudaError_t launch_scan_exclusive(const LaunchCtx& c, unsigned long long* data, 
     return cudaGetLastError();
 }
 
-static int apply_grid(const LaunchCtx& c) { return c.sm_count * 4; }
+static int apply_grid(const LaunchCtx& c) { return c.sm_count * (c.apply_ctas > 0 && c.apply_ctas < 4 ? c.apply_ctas : 4); }
 
 #define TPC_APPLY_Q_SWITCH(q, ...)                             \
     switch (q) {                                               \
@@ -245,7 +245,8 @@ struct tpc_session {
 
     bool allow_inline = true;      // env TPC_INLINE_KEYS=0 forces position-identified slots for every k
     uint32_t inline_keys() const { return (allow_inline && W == 1 && prm.abundance == ~0ull) ? 1u : 0u; }
-    LaunchCtx lctx() { return LaunchCtx{stream, sm_count, &launches}; }
+    int bin_ctas = 0, apply_ctas = 0;   // env TPC_BIN_CTAS / TPC_APPLY_CTAS (tuning aids)
+    LaunchCtx lctx() { return LaunchCtx{stream, sm_count, &launches, bin_ctas, apply_ctas}; }
     KParams kparams(uint32_t part) const {
         KParams kp{};
         kp.k = prm.k;
@@ -312,6 +313,8 @@ int tpc_session_create(const tpc_params* params, void* stream, tpc_session** out
     if (const char* e = getenv("TPC_SLICE_LOG2")) s->slice_log2 = std::min(31, std::max(8, atoi(e)));
     if (const char* e = getenv("TPC_BIN_BUFFER_MB")) s->bin_budget_bytes = (uint64_t)atoll(e) << 20;
     if (const char* e = getenv("TPC_SUBROUNDS")) s->sub_rounds_env = std::min(64, std::max(0, atoi(e)));
+    if (const char* e = getenv("TPC_BIN_CTAS")) s->bin_ctas = atoi(e);
+    if (const char* e = getenv("TPC_APPLY_CTAS")) s->apply_ctas = atoi(e);
     s->rounds_eff = params->rounds;
     cudaGetDevice(&s->device);
     configure_pool(s->device);
@@ -650,18 +653,24 @@ int tpc_session_find_candidates(tpc_session* s) {
             s->own.n = 1;
         }
     }
+    // Sub-rounds of ONE user round share the exact pass: their candidates are disjoint hash ranges of the
+    // same input, the mask only holds this GPU's marks, so one k_insert scan over the marks of all of them
+    // (one table, sized from the HyperLogLog sketch accumulated over the sub-rounds) replaces one scan per
+    // sub-round.  With -r > 1 the table stays per round, as in the reference (h:337-338).
+    const bool merge_insert = s->prm.rounds == 1 && s->sub_rounds > 1;
     for (uint32_t r = 0; r < s->rounds_eff; ++r) {
         KParams kp = s->kparams(s->prm.shard_index * s->rounds_eff + r);
+        const Counters round_start = cur;
         CK(cudaEventRecord(s->ev[0], s->stream));
         CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));  // h:257: zero-filled each round
-        CK(cudaMemsetAsync(s->d_hll, 0, 4u << kHllBits, s->stream));
+        if (!merge_insert || r == 0) CK(cudaMemsetAsync(s->d_hll, 0, 4u << kHllBits, s->stream));
         float b_bin = 0, b_fill = 0, b_query = 0;
         int brc = filter_passes_binned(s, kp, &b_bin, &b_fill, &b_query);
         if (brc > 0) return brc;
         if (brc == -2) {  // redo this round from scratch; marks already set are true marks and may stay
             CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));
-            CK(cudaMemcpyAsync(s->d_ctr, &prev, sizeof prev, cudaMemcpyHostToDevice, s->stream));
-            CK(cudaMemsetAsync(s->d_hll, 0, 4u << kHllBits, s->stream));
+            CK(cudaMemcpyAsync(s->d_ctr, &round_start, sizeof round_start, cudaMemcpyHostToDevice, s->stream));
+            if (!merge_insert) CK(cudaMemsetAsync(s->d_hll, 0, 4u << kHllBits, s->stream));
             CK(cudaEventRecord(s->ev[0], s->stream));
         }
         if (int wrc = wait_genome(s, s->ntiles)) return wrc;
@@ -675,6 +684,16 @@ int tpc_session_find_candidates(tpc_session* s) {
         CK(cudaEventRecord(s->ev[2], s->stream));
         CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
+        {
+            float t;
+            if (brc < 0) {
+                cudaEventElapsedTime(&t, s->ev[0], s->ev[1]); ms_fill += t;
+                cudaEventElapsedTime(&t, s->ev[1], s->ev[2]); ms_query += t;
+            } else {
+                ms_bin += b_bin; ms_fill += b_fill; ms_query += b_query;
+            }
+        }
+        if (merge_insert && r + 1 < s->rounds_eff) continue;   // exact pass after the last sub-round
         uint64_t marks_r = cur.marks - prev.marks;
 
         // exact set of this round's candidates, sized from the HyperLogLog estimate of their number
@@ -708,8 +727,10 @@ int tpc_session_find_candidates(tpc_session* s) {
             // ownership planes (valid for every tile once a binned round has run) pick this round's marks
             OwnPlanes iop = s->own;
             iop.id = kp.part - s->prm.shard_index * s->rounds_eff + 1;
-            const bool planes_ok = brc == 0 && s->own_shared && kp.nparts > 1 && s->own_done_tiles >= s->ntiles;
-            CK(W_DISPATCH(s, insert(lc, s->g, s->d_mask, kp, s->ntiles, TableView{s->d_T, lg, s->inline_keys()}, s->d_ctr,
+            const bool planes_ok = !merge_insert && brc == 0 && s->own_shared && kp.nparts > 1 && s->own_done_tiles >= s->ntiles;
+            KParams kpi = kp;
+            if (merge_insert) kpi.nparts = 1;   // every mark in the mask belongs to this pass
+            CK(W_DISPATCH(s, insert(lc, s->g, s->d_mask, kpi, s->ntiles, TableView{s->d_T, lg, s->inline_keys()}, s->d_ctr,
                                     planes_ok ? &iop : nullptr)));
             CK(cudaEventRecord(s->ev[3], s->stream));
             CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
@@ -740,12 +761,6 @@ int tpc_session_find_candidates(tpc_session* s) {
         CK(cudaStreamSynchronize(s->stream));
         s->local_count = cur.junctions;
         float t;
-        if (brc < 0) {
-            cudaEventElapsedTime(&t, s->ev[0], s->ev[1]); ms_fill += t;
-            cudaEventElapsedTime(&t, s->ev[1], s->ev[2]); ms_query += t;
-        } else {
-            ms_bin += b_bin; ms_fill += b_fill; ms_query += b_query;
-        }
         cudaEventElapsedTime(&t, s->ev[10], s->ev[3]); ms_insert += t;
         cudaEventElapsedTime(&t, s->ev[3], s->ev[4]); ms_classify += t;
         prev = cur;

@@ -83,6 +83,7 @@ def sharded_run(session, genome, rank: int, world: int, out=None):
     s = session
     s.find_candidates()
     ptr, n = s.local_junctions()
+    ms_x = {}
     if world == 1:
         s.set_junctions(ptr, n)
         cut = [0, genome.n_positions]
@@ -90,20 +91,28 @@ def sharded_run(session, genome, rank: int, world: int, out=None):
         rb = sb = 0
         trec, tstub, nj = nrec, nstub, n
     else:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if torch.cuda.is_available() else None
+        if ev: ev[0].record()
         allj = allgather_varlen(api.as_torch(ptr, n, torch.int64))            # exchange 1
+        if ev: ev[1].record()
         s.set_junctions(allj.data_ptr(), allj.numel())
         mptr, mw = s.candidate_mask()
+        if ev: ev[2].record()
         or_reduce_scatter_disjoint_(api.as_torch(mptr, mw, torch.int32), rank, world)   # exchange 2
+        if ev: ev[3].record()
         cut = position_cuts(genome.n_positions, world)
         nrec, nstub = s.emit_count(cut[rank], cut[rank + 1])
         (rb, sb), (trec, tstub) = exclusive_prefix([nrec, nstub], "cuda")     # exchange 3
         nj = allj.numel()
+        if ev:   # (emit_count has synchronised the stream)
+            ms_x = {"ms_allgather_junctions": round(ev[0].elapsed_time(ev[1]), 3),
+                    "ms_reduce_scatter_masks": round(ev[2].elapsed_time(ev[3]), 3)}
     need = 12 * (nrec + len(genome.rec_len)) + 16
     if out is None or out.nbytes < need:
         out = api.DeviceBuffer(need)
     off, nb = s.emit_write(rb, sb, out.ptr, out.nbytes)
     info = dict(junctions=nj, records=trec, stubs=tstub, slice_offset=off, slice_bytes=nb,
-                image_bytes=nb if world == 1 else None)
+                image_bytes=nb if world == 1 else None, **ms_x)
     return info, out
 
 
