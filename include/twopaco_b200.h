@@ -67,7 +67,8 @@ typedef struct tpc_stats {
                                     fill and query); 0 = direct path                             */
     uint32_t sub_rounds;         /* hash sub-ranges per -r round chosen so that one round's records
                                     fit HBM in one wave (1 = none); unobservable in the output    */
-    uint32_t reserved0;
+    float ms_bin_overlapped;     /* pipelined rounds: binning of round r+1 that ran beside the fill of round r
+                                    (not part of ms_bin / ms_total) */
 } tpc_stats;
 
 /* ------------------------------------------------------------------------------------------

@@ -374,6 +374,12 @@ def test_sub_rounds_share_one_ownership_scan(name, sub, user_rounds, golden, mon
     img, st = api.junctions_host(api.pack_records(recs), k=spec["k"], filter_bits=20, q=4, rounds=user_rounds)
     assert st.ms_bin > 0 and st.sub_rounds == sub
     assert canon_md5(bytes(img)) == g["canon_md5"] and st.junctions == g["distinct_junctions"]
+    # rounds <= 15 per GPU are pipelined (round r+1 binned on a second stream beside the fill of round r) ...
+    assert (st.ms_bin_overlapped > 0) == (sub * user_rounds <= 15)
+    # ... unless switched off: same result from the one-scratch path
+    monkeypatch.setenv("TPC_PIPELINE", "0")
+    img2, st2 = api.junctions_host(api.pack_records(recs), k=spec["k"], filter_bits=20, q=4, rounds=user_rounds)
+    assert st2.ms_bin_overlapped == 0 and bytes(img2) == bytes(img)
 
 
 def test_sub_rounds_direct_path_and_shards(monkeypatch, golden):

@@ -37,7 +37,7 @@ class Stats(C.Structure):
                 ("ms_bin", C.c_float), ("ms_fill", C.c_float), ("ms_query", C.c_float), ("ms_insert", C.c_float), ("ms_classify", C.c_float),
                 ("ms_index", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float),
                 ("kernel_launches", C.c_uint32), ("bin_waves", C.c_uint32), ("sub_rounds", C.c_uint32),
-                ("reserved0", C.c_uint32)]
+                ("ms_bin_overlapped", C.c_float)]
 
     def asdict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

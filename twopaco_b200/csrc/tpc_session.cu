@@ -222,6 +222,20 @@ struct tpc_session {
     bool bin_ready = false;
     bool used_binned = false;
     bool T_in_scratch = false;
+    // Pipelined rounds: the record scratch is split in two halves; while round r is FILLED from one half
+    // (apply kernels: bound by L2 / L1-tag traffic, few instructions) round r+1 is BINNED into the other
+    // on a second stream (k_bin_list: bound by the integer pipes, little memory traffic), each kernel
+    // capped to a share of the SM so that both are resident.  The query of round r runs alone afterwards.
+    int pipe_env = 1;               // env TPC_PIPELINE=0 disables
+    // CTAs per SM while both run (the register file holds four 256-thread CTAs of these kernels).  Measured at C3
+    // on one GPU: 2+2 gains nothing (both kernels also share the LSU / L1 data path: binning 355 ms instead of
+    // 226 ms alone), 3+1 turns 640 ms per step into 593 ms.
+    int pipe_bin_ctas = 3, pipe_fill_ctas = 1;   // env TPC_PIPE_BIN_CTAS / TPC_PIPE_FILL_CTAS
+    bool pipe = false;
+    cudaStream_t bin_stream = nullptr;
+    BinView pipe_view[2]{};
+    long long pipe_round[2] = {-1, -1};   // round whose records a half holds
+    cudaEvent_t pipe_ev[6]{};       // [0,1] half binned  [2] main-stream marker  [3,4] bin start/stop (timing)
 
     // hash sub-ranges processed in sequence by this GPU: the user's -r times the sub-rounds chosen so
     // that one round's records fit HBM in one wave (choose_sub_rounds); ownership planes of all of
@@ -313,6 +327,9 @@ int tpc_session_create(const tpc_params* params, void* stream, tpc_session** out
     if (const char* e = getenv("TPC_SLICE_LOG2")) s->slice_log2 = std::min(31, std::max(8, atoi(e)));
     if (const char* e = getenv("TPC_BIN_BUFFER_MB")) s->bin_budget_bytes = (uint64_t)atoll(e) << 20;
     if (const char* e = getenv("TPC_SUBROUNDS")) s->sub_rounds_env = std::min(64, std::max(0, atoi(e)));
+    if (const char* e = getenv("TPC_PIPELINE")) s->pipe_env = atoi(e);
+    if (const char* e = getenv("TPC_PIPE_BIN_CTAS")) s->pipe_bin_ctas = std::max(1, atoi(e));
+    if (const char* e = getenv("TPC_PIPE_FILL_CTAS")) s->pipe_fill_ctas = std::max(1, atoi(e));
     if (const char* e = getenv("TPC_BIN_CTAS")) s->bin_ctas = atoi(e);
     if (const char* e = getenv("TPC_APPLY_CTAS")) s->apply_ctas = atoi(e);
     s->rounds_eff = params->rounds;
@@ -344,6 +361,9 @@ void tpc_session_destroy(tpc_session* s) {
     for (auto& ev : s->up_ev)
         if (ev) cudaEventDestroy(ev);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+    if (s->bin_stream) { cudaStreamSynchronize(s->bin_stream); cudaStreamDestroy(s->bin_stream); }
+    for (auto& ev : s->pipe_ev)
+        if (ev) cudaEventDestroy(ev);
     delete s;
 }
 
@@ -456,19 +476,33 @@ static uint32_t own_planes_for(uint32_t rounds_local) {  // bits needed for ids 
 // for both filter passes, and its filter holds 1/S of the vertices, so Bloom false positives (the
 // marks pass 2 has to remove) drop steeply.  -r and -f keep their meaning; like -r, the split is
 // unobservable in the output.
-static uint32_t choose_sub_rounds(const tpc_session* s) {
-    if (s->sub_rounds_env) return (uint32_t)s->sub_rounds_env;
-    if (s->bin_budget_bytes || !binned_applies(s, nullptr)) return 1;
+static uint32_t choose_sub_rounds(tpc_session* s) {
+    s->pipe = false;
+    const bool can_pipe = s->pipe_env && binned_applies(s, nullptr) && !s->bin_budget_bytes;
     const uint64_t avail = available_bytes(s->device);
     const uint64_t plane_bytes = s->ntiles * kTileThreads * 4;
     const uint64_t base = (uint64_t)s->prm.rounds * s->prm.shard_count;
-    for (uint32_t S = 1; S <= 8; ++S) {
+    // does the record scratch of one round (x2 when two rounds are in flight) fit with S sub-rounds?
+    auto fits = [&](uint32_t S, int scratches) {
         uint32_t planes = own_planes_for(s->prm.rounds * S);
         uint64_t extra = planes > 1 ? (planes - 1) * plane_bytes : 0;
-        if (avail <= extra) break;
-        if ((double)(s->g.npos / (base * S)) * 14.0 <= (double)(avail - extra) * 0.88) return S;  // (binning takes 92 %)
+        if (avail <= extra) return false;
+        return (double)(s->g.npos / (base * S)) * 14.0 * scratches <= (double)(avail - extra) * 0.88;  // (binning takes 92 %)
+    };
+    if (s->sub_rounds_env) {
+        const uint32_t S = (uint32_t)s->sub_rounds_env;
+        s->pipe = can_pipe && s->prm.rounds * S >= 2 && own_planes_for(s->prm.rounds * S) > 0 && fits(S, 2);
+        return S;
     }
-    return 8;
+    if (s->bin_budget_bytes || !binned_applies(s, nullptr)) return 1;
+    uint32_t S1 = 8;
+    for (uint32_t S = 1; S <= 8; ++S)
+        if (fits(S, 1)) { S1 = S; break; }
+    if (can_pipe && s->prm.rounds * S1 >= 2) {   // several rounds anyway: overlap them, with two half-size scratches
+        for (uint32_t S = S1; S <= 2 * S1 && S <= 12; ++S)
+            if (own_planes_for(s->prm.rounds * S) > 0 && fits(S, 2)) { s->pipe = true; return S; }
+    }
+    return S1;
 }
 
 // first tile boundary in (from, to] at which another upload chunk has to be waited for
@@ -501,23 +535,43 @@ static int binned_setup(tpc_session* s, const KParams& kp) {
         uint64_t est = wave_tiles * kTilePos / kp.nparts;
         bv.cap = ((uint64_t)(est / buckets * 1.08) + 8192 + 31) / 32 * 32;
         bv.ov_cap = std::max<uint64_t>(1 << 16, est / 64);
-        s->bin_rec_bytes = (uint64_t)buckets * 3 * bv.cap * 4;
+        if (s->pipe && nwaves > 1) s->pipe = false;   // (cannot happen with the sub-rounds chosen for it, but stay safe)
+        const uint32_t halves = s->pipe ? 2 : 1;
+        s->bin_rec_bytes = (uint64_t)halves * buckets * 3 * bv.cap * 4;
         cudaError_t e = dev_alloc(&s->d_bin_rec, s->bin_rec_bytes, s->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
         if (e == cudaErrorMemoryAllocation && attempt < 4 && !s->bin_budget_bytes) {
-            cudaGetLastError();  // not enough contiguous memory after all: smaller waves
+            cudaGetLastError();  // not enough contiguous memory after all: one scratch, then smaller waves
             s->d_bin_rec = nullptr;
             s->bin_rec_bytes = 0;
-            budget = budget * 6 / 10;
+            if (s->pipe) s->pipe = false;
+            else budget = budget * 6 / 10;
             continue;
         }
         CK(e);
         break;
     }
-    CK(dev_alloc(&s->d_bin_count, (buckets + 1) * 8, s->stream));
-    CK(dev_alloc(&s->d_bin_ov, bv.ov_cap * 16, s->stream));
+    const uint32_t halves = s->pipe ? 2 : 1;
+    CK(dev_alloc(&s->d_bin_count, (uint64_t)halves * (buckets + 1) * 8, s->stream));
+    CK(dev_alloc(&s->d_bin_ov, (uint64_t)halves * bv.ov_cap * 16, s->stream));
     bv.rec = s->d_bin_rec; bv.count = s->d_bin_count; bv.ov_count = s->d_bin_count + buckets; bv.ov = s->d_bin_ov;
     s->bin_view = bv;
+    for (uint32_t h = 0; h < 2; ++h) {
+        BinView hv = bv;
+        if (h < halves) {
+            hv.rec = s->d_bin_rec + (uint64_t)h * buckets * 3 * bv.cap;
+            hv.count = s->d_bin_count + (uint64_t)h * (buckets + 1);
+            hv.ov_count = hv.count + buckets;
+            hv.ov = s->d_bin_ov + (uint64_t)h * bv.ov_cap * 4;
+        }
+        s->pipe_view[h] = hv;
+        s->pipe_round[h] = -1;
+    }
+    if (s->pipe) {
+        if (!s->bin_stream) CK(cudaStreamCreateWithFlags(&s->bin_stream, cudaStreamNonBlocking));
+        for (auto& ev : s->pipe_ev)
+            if (!ev) CK(cudaEventCreate(&ev));
+    }
     s->bin_wave_tiles = wave_tiles;
     s->bin_nwaves = nwaves;
     s->bin_ready = true;
@@ -607,6 +661,86 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
     return 0;
 }
 
+// Bin round `part` (ownership id `id`) into the half scratch `bv` on stream `lc.stream`.
+static int bin_whole_round(tpc_session* s, const LaunchCtx& lc, const KParams& kp, const BinView& bv) {
+    const uint32_t buckets = 1u << bv.bucket_bits;
+    const uint32_t part_base = s->prm.shard_index * s->rounds_eff;
+    OwnPlanes op = s->own;
+    op.id = kp.part - part_base + 1;
+    CK(cudaMemsetAsync(bv.count, 0, (buckets + 1) * 8, lc.stream));
+    for (uint64_t a = 0; a < s->ntiles;) {   // (cuts only while the genome is still being uploaded: first round, main stream)
+        const uint64_t b = lc.stream == s->stream ? next_cut(s, a, s->ntiles) : s->ntiles;
+        if (lc.stream == s->stream)
+            if (int wrc = wait_genome(s, b)) return wrc;
+        if (s->own_done_tiles < b) {
+            CK(W_DISPATCH(s, own(lc, s->g, kp, part_base, s->rounds_eff, s->own_done_tiles, b, s->own)));
+            s->own_done_tiles = b;
+        }
+        CK(W_DISPATCH(s, bin(lc, s->g, kp, bv, a, b, 0, &op)));
+        a = b;
+    }
+    return 0;
+}
+
+// Filter passes of round r (of rounds_eff) with the next round's binning overlapped (see tpc_session::pipe).
+// Same return convention as filter_passes_binned.
+static int filter_passes_pipelined(tpc_session* s, uint32_t r, const KParams& kp, float* ms_bin, float* ms_fill, float* ms_query) {
+    if (int rc = binned_setup(s, kp)) return rc;
+    if (!s->pipe) return -3;   // the scratch could not be split after all: caller uses the one-scratch path
+    const int h = (int)(r & 1);
+    const BinView bv = s->pipe_view[h];
+    const uint32_t buckets = 1u << bv.bucket_bits;
+    const bool has_next = r + 1 < s->rounds_eff;
+    LaunchCtx lc = s->lctx();
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    float t_bin_ahead = 0;
+    CK(cudaEventRecord(e0, s->stream));
+    if (s->pipe_round[h] != (long long)r) {   // first round of the call (or after a fallback): bin here, nothing to overlap with
+        if (int rc = bin_whole_round(s, lc, kp, bv)) return rc;
+        s->pipe_round[h] = r;
+    } else {
+        CK(cudaStreamWaitEvent(s->stream, s->pipe_ev[h], 0));
+    }
+    CK(cudaEventRecord(e1, s->stream));
+    if (has_next) {
+        // everything enqueued on the main stream so far (ownership planes, the genome upload, the previous round's
+        // readers of the other half) precedes the next round's binning
+        if (int wrc = wait_genome(s, s->ntiles)) return wrc;
+        CK(cudaEventRecord(s->pipe_ev[2], s->stream));
+        CK(cudaStreamWaitEvent(s->bin_stream, s->pipe_ev[2], 0));
+        LaunchCtx lb{s->bin_stream, s->sm_count, &s->launches, s->pipe_bin_ctas, 0};
+        KParams kn = s->kparams(kp.part + 1);
+        CK(cudaEventRecord(s->pipe_ev[3], s->bin_stream));
+        if (int rc = bin_whole_round(s, lb, kn, s->pipe_view[h ^ 1])) return rc;
+        CK(cudaEventRecord(s->pipe_ev[4], s->bin_stream));
+        CK(cudaEventRecord(s->pipe_ev[h ^ 1], s->bin_stream));
+        s->pipe_round[h ^ 1] = r + 1;
+        lc.apply_ctas = s->pipe_fill_ctas;   // share the SMs with the binning kernel
+    }
+    for (uint32_t b = 0; b < buckets; ++b) CK(launch_apply_fill(lc, s->d_filter, bv, b, s->d_ctr));
+    CK(launch_apply_overflow(lc, s->d_filter, bv, 0, s->d_mask, 0, s->d_ctr, s->d_hll));
+    CK(cudaEventRecord(e2, s->stream));
+    if (has_next) CK(cudaStreamWaitEvent(s->stream, s->pipe_ev[h ^ 1], 0));   // the query runs alone, at full occupancy
+    lc.apply_ctas = s->apply_ctas;
+    for (uint32_t b = 0; b < buckets; ++b) CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, 0, s->d_ctr, s->d_hll));
+    CK(launch_apply_overflow(lc, s->d_filter, bv, 1, s->d_mask, 0, s->d_ctr, s->d_hll));
+    CK(cudaEventRecord(e3, s->stream));
+    unsigned long long ov_now = 0;
+    CK(cudaMemcpyAsync(&ov_now, bv.ov_count, 8, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1); *ms_bin += t;       // binning done here (first round) or the wait for the overlapped one
+    cudaEventElapsedTime(&t, e1, e2); *ms_fill += t;      // (overlapped with the next round's binning)
+    cudaEventElapsedTime(&t, e2, e3); *ms_query += t;     // (includes waiting for that binning to end)
+    if (has_next && cudaEventElapsedTime(&t_bin_ahead, s->pipe_ev[3], s->pipe_ev[4]) == cudaSuccess) s->st.ms_bin_overlapped += t_bin_ahead;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    if (ov_now > bv.ov_cap) return -2;
+    s->used_binned = true;
+    s->st.bin_waves = 1;
+    return 0;
+}
+
 static uint64_t padded_mask_words(const tpc_session* s) {
     const uint64_t n = std::max<uint32_t>(s->prm.shard_count, 1);
     const uint64_t chunk_tiles = (s->ntiles + n - 1) / n;
@@ -665,7 +799,8 @@ int tpc_session_find_candidates(tpc_session* s) {
         CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));  // h:257: zero-filled each round
         if (!merge_insert || r == 0) CK(cudaMemsetAsync(s->d_hll, 0, 4u << kHllBits, s->stream));
         float b_bin = 0, b_fill = 0, b_query = 0;
-        int brc = filter_passes_binned(s, kp, &b_bin, &b_fill, &b_query);
+        int brc = s->pipe ? filter_passes_pipelined(s, r, kp, &b_bin, &b_fill, &b_query) : -3;
+        if (brc == -3) brc = filter_passes_binned(s, kp, &b_bin, &b_fill, &b_query);
         if (brc > 0) return brc;
         if (brc == -2) {  // redo this round from scratch; marks already set are true marks and may stay
             CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));
@@ -711,9 +846,14 @@ int tpc_session_find_candidates(tpc_session* s) {
                 s->d_T = nullptr; s->T_bytes = 0; s->T_in_scratch = false;
             }
             if (!s->d_T) {
-                if (s->d_bin_rec && need <= s->bin_rec_bytes) {   // the record waves of this round are spent
-                    s->d_T = reinterpret_cast<Slot*>(s->d_bin_rec);
-                    s->T_bytes = s->bin_rec_bytes;
+                // the record waves of this round are spent (pipelined rounds: only this round's half is, unless
+                // this is the last round)
+                uint32_t* spent = s->d_bin_rec;
+                uint64_t spent_bytes = s->bin_rec_bytes;
+                if (s->pipe && r + 1 < s->rounds_eff) { spent = s->pipe_view[r & 1].rec; spent_bytes = s->bin_rec_bytes / 2; }
+                if (s->d_bin_rec && need <= spent_bytes) {
+                    s->d_T = reinterpret_cast<Slot*>(spent);
+                    s->T_bytes = spent_bytes;
                     s->T_in_scratch = true;
                 } else {
                     if (need > available_bytes(s->device)) return set_error("candidate table of 2^%u slots does not fit in device memory", lg);
