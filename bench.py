@@ -344,18 +344,16 @@ def main() -> None:
                          "api": "tpc_junctions_host (pinned host genome -> pinned host de_bruijn.bin image)"}
     elif not args.no_e2e:
         # N GPUs, host buffers in / host buffers out (twopaco_b200.dist.sharded_run_host): every rank uploads
-        # 1/N of the packed genome from pinned host memory, NCCL all-gathers it over NVLink, runs its shard,
-        # and copies its slice of the image back to pinned host memory.  Wall clock between barriers, max over ranks.
+        # 1/N of the packed genome from pinned host memory, chunk by chunk, NCCL all-gathers the chunks over
+        # NVLink while the first pass already runs on those that have arrived, runs its shard, and copies its
+        # slice of the image back to pinned host memory.  Wall clock between barriers, max over ranks.
         from twopaco_b200 import dist as tdist
         runner.session.close()
         runner.out = None
         L = api.lib()
         cw, mw = L.tpc_code_words(dg.n_positions), L.tpc_mask_words(dg.n_positions)
-        (c_lo, c_hi), (m_lo, m_hi) = tdist.shard_bounds(cw, rank, world), tdist.shard_bounds(mw, rank, world)
-        shard = tdist.HostGenomeShard(
-            torch.from_numpy(dg.codes.to_host((c_hi - c_lo) * 8, c_lo * 8).view(np.int64)).pin_memory(),
-            torch.from_numpy(dg.n_mask.to_host((m_hi - m_lo) * 8, m_lo * 8).view(np.int64)).pin_memory(),
-            cw, mw, dg.n_positions, dg.rec_start, dg.rec_len)
+        shard = tdist.host_shard(cw, mw, dg.n_positions, dg.rec_start, dg.rec_len, rank, world, n_chunks=16,
+                                 fetch=lambda a, lo, hi: (dg.codes if a == 0 else dg.n_mask).to_host((hi - lo) * 8, lo * 8).view(np.uint64))
         dg.codes.close(); dg.n_mask.close()                     # the e2e region starts from HOST buffers only
         out_host, dev_out, times = None, None, []
         for i in range(1 + max(1, min(args.steps, 3))):

@@ -164,6 +164,15 @@ void tpc_session_destroy(tpc_session *s);
 int tpc_session_set_genome_host(tpc_session *s, const tpc_genome *host_genome);
 int tpc_session_set_genome_device(tpc_session *s, const tpc_genome *genome_with_device_arrays);
 
+/* A device-resident genome handed to tpc_session_set_genome_device may still be arriving (multi-GPU:
+ * every GPU uploads 1/N of it and the parts are all-gathered chunk by chunk over NVLink).  Declare
+ * its chunks: tiles (8192 positions) from tile_begin up to the next chunk's tile_begin are complete
+ * once `cuda_event` (a cudaEvent_t, recorded by the producer on its stream) has completed.  Chunks are
+ * added in ascending order, the first at tile 0, before tpc_session_find_candidates; the first pass
+ * over the genome then starts on the chunks that have arrived.  The events stay owned by the caller
+ * and must outlive the session's use of the genome. */
+int tpc_session_add_genome_event(tpc_session *s, uint64_t tile_begin, void *cuda_event);
+
 /* Pass 1 + pass 2 for this shard (reference stages 1a, 1b, 2: FilterFillerWorker h:995-1105,
  * CandidateCheckingWorker h:586-704, CandidateFinalFilteringWorker h:708-829), `rounds` times
  * over disjoint hash sub-ranges. */

@@ -34,15 +34,17 @@ def _worker(rank, world, port, q):
         # 3. exclusive prefix of (records, stubs)
         before, total = tdist.exclusive_prefix([10 + rank, 1], "cpu")
         assert total == [21, 2] and before == ([0, 0] if rank == 0 else [10, 1])
-        # 4. host-sliced upload + all-gather reassembles the packed genome on every rank (ragged tail)
+        # 4. chunk-interleaved host shards + chunked all-gather reassemble the packed genome on every rank
         import numpy as np
         rng = np.random.default_rng(5)
-        codes = rng.integers(0, 2**63, size=1001, dtype=np.uint64)
-        nmask = rng.integers(0, 2**63, size=503, dtype=np.uint64)
-        sh = tdist.host_shard(codes, nmask, 1001 * 32 - 7, None, None, rank, world, pin=False)
-        assert sh.codes.numel() == (501 if rank == 0 else 500) and sh.n_mask.numel() == (252 if rank == 0 else 251)
-        c, m = tdist.upload_allgather(sh, rank, world, "cpu")
-        assert np.array_equal(c.numpy().view(np.uint64), codes) and np.array_equal(m.numpy().view(np.uint64), nmask)
+        npos = 5 * 8192 + 100                                  # 6 tiles -> 3 chunks of 2 tiles (world 2)
+        codes = rng.integers(0, 2**63, size=6 * 256 + 8, dtype=np.uint64)
+        nmask = rng.integers(0, 2**63, size=6 * 128 + 8, dtype=np.uint64)
+        sh = tdist.host_shard(codes, nmask, npos, None, None, rank, world, pin=False, n_chunks=3)
+        assert sh.plan.tile_begin == [0, 2, 4] and sh.codes.numel() == 256 + 256 + 260
+        c, m, ev = tdist.upload_allgather(sh, rank, world, "cpu")
+        assert ev == [] and np.array_equal(c.numpy().view(np.uint64)[:len(codes)], codes)
+        assert np.array_equal(m.numpy().view(np.uint64)[:len(nmask)], nmask)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
@@ -63,12 +65,23 @@ def test_dist_helpers_gloo_world2():
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
 
 
-def test_shard_bounds_cover_everything():
-    for n, world in ((0, 3), (1, 4), (1001, 2), (8 * 1024 + 8, 8), (7, 8)):
-        b = [tdist.shard_bounds(n, r, world) for r in range(world)]
-        assert b[0][0] == 0 and b[-1][1] == n
-        assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
-        assert all(hi - lo <= tdist.shard_chunk(n, world) for lo, hi in b)
+@pytest.mark.parametrize("npos,world,chunks", [(1, 1, 8), (8192 * 7 + 5, 2, 3), (100_000, 3, 8), (21_700_000_000, 8, 16), (5, 4, 2)])
+def test_chunk_plan_covers_everything(npos, world, chunks):
+    tiles = (npos + 8191) // 8192
+    cw, mw = tiles * 256 + 8, tiles * 128 + 8
+    plan = tdist.ChunkPlan(npos, cw, mw, world, chunks)
+    assert plan.tile_begin[0] == 0 and plan.n_chunks <= max(chunks, 1)
+    assert all(t % world == 0 for t in plan.tile_begin)
+    for a, total in enumerate((cw, mw)):
+        covered = 0
+        for c in range(plan.n_chunks):
+            for r in range(world):
+                lo, hi = plan.part_bounds(a, c, r)
+                assert lo == min(total, covered) and hi - lo <= plan.arrays[a][1][c][1]
+                covered = max(covered, hi) if hi > lo else covered
+            start, part = plan.arrays[a][1][c]
+            covered = min(total, start + part * world)
+        assert covered == total and plan.device_words(a) >= total
 
 
 @pytest.mark.parametrize("npos,world", [(1, 1), (8192, 2), (100_000, 3), (21_700_000_000, 8), (5, 4)])

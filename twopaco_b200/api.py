@@ -72,6 +72,7 @@ SIGNATURES = {
     "tpc_session_destroy": (None, [C.c_void_p]),
     "tpc_session_set_genome_host": (C.c_int, [C.c_void_p, C.POINTER(Genome)]),
     "tpc_session_set_genome_device": (C.c_int, [C.c_void_p, C.POINTER(Genome)]),
+    "tpc_session_add_genome_event": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "tpc_session_find_candidates": (C.c_int, [C.c_void_p]),
     "tpc_session_local_junctions": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "tpc_session_set_junctions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -273,6 +274,11 @@ class Session:
         self._keep = (keep, rec_start, rec_len)
         g = Genome(codes_ptr, n_mask_ptr, n_positions, rec_start.ctypes.data, rec_len.ctypes.data, len(rec_len))
         _check(lib().tpc_session_set_genome_device(self._s, C.byref(g)))
+
+    def add_genome_event(self, tile_begin: int, cuda_event: int, keep=None) -> None:
+        """Tiles from tile_begin on (up to the next event's tile) are complete once the CUDA event has completed."""
+        self._events = getattr(self, "_events", []) + [keep]
+        _check(lib().tpc_session_add_genome_event(self._s, tile_begin, C.c_void_p(cuda_event)))
 
     def find_candidates(self) -> None:
         _check(lib().tpc_session_find_candidates(self._s))

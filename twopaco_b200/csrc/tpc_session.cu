@@ -249,6 +249,7 @@ struct tpc_session {
 
     // host->device upload of the genome overlapped with the first binning pass (set_genome_host)
     cudaStream_t copy_stream = nullptr;
+    bool up_ev_owned = true;                 // false: events handed in by tpc_session_add_genome_event
     std::vector<cudaEvent_t> up_ev;          // upload chunk c is complete
     std::vector<uint64_t> up_tile_begin;     // first tile of chunk c
     size_t up_waited = 0;                    // chunks the compute stream already waits for
@@ -358,8 +359,9 @@ void tpc_session_destroy(tpc_session* s) {
     cudaStreamSynchronize(s->stream);
     for (auto& ev : s->ev)
         if (ev) cudaEventDestroy(ev);
-    for (auto& ev : s->up_ev)
-        if (ev) cudaEventDestroy(ev);
+    if (s->up_ev_owned)
+        for (auto& ev : s->up_ev)
+            if (ev) cudaEventDestroy(ev);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
     if (s->bin_stream) { cudaStreamSynchronize(s->bin_stream); cudaStreamDestroy(s->bin_stream); }
     for (auto& ev : s->pipe_ev)
@@ -443,6 +445,18 @@ int tpc_session_set_genome_device(tpc_session* s, const tpc_genome* g) {
     return adopt_records(s, g);
 }
 
+int tpc_session_add_genome_event(tpc_session* s, uint64_t tile_begin, void* cuda_event) {
+    if (!s || !s->g.codes || !cuda_event) return set_error("set_genome_device first");
+    if (s->d_codes) return set_error("the genome was uploaded by the session itself");
+    if (s->have_candidates || s->up_waited) return set_error("genome events must be added before find_candidates");
+    if (s->up_ev.empty() ? tile_begin != 0 : tile_begin <= s->up_tile_begin.back())
+        return set_error("genome events must be added in ascending tile order, starting at tile 0");
+    s->up_ev_owned = false;
+    s->up_ev.push_back((cudaEvent_t)cuda_event);
+    s->up_tile_begin.push_back(tile_begin);
+    return 0;
+}
+
 static double hll_estimate(const std::vector<uint32_t>& reg) {
     const double m = (double)reg.size();
     double sum = 0;
@@ -499,8 +513,11 @@ static uint32_t choose_sub_rounds(tpc_session* s) {
     for (uint32_t S = 1; S <= 8; ++S)
         if (fits(S, 1)) { S1 = S; break; }
     if (can_pipe && s->prm.rounds * S1 >= 2) {   // several rounds anyway: overlap them, with two half-size scratches
+        // Only with >= 4 rounds: the first binning and the last fill are not overlapped, the overlapped fill runs at
+        // a quarter of the SM, and every extra sub-round is one more scan of the ownership planes.  Measured at C3:
+        // 1 GPU (3 -> 5 sub-rounds) 640 -> 593 ms; 2 GPUs (2 -> 3 sub-rounds) 321 -> 344 ms, hence the threshold.
         for (uint32_t S = S1; S <= 2 * S1 && S <= 12; ++S)
-            if (own_planes_for(s->prm.rounds * S) > 0 && fits(S, 2)) { s->pipe = true; return S; }
+            if (s->prm.rounds * S >= 4 && own_planes_for(s->prm.rounds * S) > 0 && fits(S, 2)) { s->pipe = true; return S; }
     }
     return S1;
 }

@@ -119,74 +119,137 @@ def sharded_run(session, genome, rank: int, world: int, out=None):
 # ---------------------------------------------------------------------------------------------
 # host buffers -> host buffers on N GPUs (the multi-GPU `e2e` region of bench.py)
 # ---------------------------------------------------------------------------------------------
-class HostGenomeShard:
-    """Rank r's 1/world slice of a packed genome (codes and n_mask words [r*chunk, (r+1)*chunk)) in
-    host memory, plus the (small) record table of the whole input.  Every rank uploads only its
-    slice over its own PCIe link; the slices are then all-gathered over NVLink (`upload_allgather`),
-    which replaces the reference's per-stage re-read of the whole FASTA on every worker
-    (vertexenumerator.h:1135-1214)."""
+CODE_WORDS_PER_TILE = 256      # 8192 positions x 2 bits / 64
+MASK_WORDS_PER_TILE = 128
 
-    def __init__(self, codes: torch.Tensor, n_mask: torch.Tensor, code_words: int, mask_words: int, n_positions: int,
-                 rec_start, rec_len):
-        self.codes, self.n_mask = codes, n_mask                  # int64 tensors (pinned when possible)
-        self.code_words, self.mask_words, self.n_positions = int(code_words), int(mask_words), int(n_positions)
-        self.rec_start, self.rec_len = rec_start, rec_len
+
+class ChunkPlan:
+    """Geometry of the chunked multi-GPU upload of a packed genome of `code_words` / `mask_words` 64-bit
+    words: the tiles are cut into (at most) `n_chunks` chunks of a multiple of `world` tiles; every chunk of
+    both arrays is `world` equal parts, part r held (and uploaded) by rank r.  One all-gather per chunk and
+    array then lands the chunk contiguously, in place, in every GPU's copy of the genome -- chunk by chunk in
+    position order, so the first pass over the genome can start on the chunks that have arrived
+    (tpc_session_add_genome_event).  The last chunk also carries the arrays' read-ahead padding words and is
+    padded to a multiple of `world` words (the device arrays are allocated that much longer)."""
+
+    def __init__(self, n_positions: int, code_words: int, mask_words: int, world: int, n_chunks: int = 8):
+        self.world = world
+        self.tiles = (n_positions + TILE_POSITIONS - 1) // TILE_POSITIONS
+        per = max(1, -(-self.tiles // max(n_chunks, 1)))
+        per = -(-per // world) * world                       # tiles per chunk: a multiple of world
+        self.tile_begin = list(range(0, max(self.tiles, 1), per))
+        self.n_chunks = len(self.tile_begin)
+        self.arrays = []                                     # per array: (total words, [(start, part_words)] per chunk)
+        for total, wpt in ((code_words, CODE_WORDS_PER_TILE), (mask_words, MASK_WORDS_PER_TILE)):
+            chunks = []
+            for c, tb in enumerate(self.tile_begin):
+                start = tb * wpt
+                end = total if c + 1 == self.n_chunks else self.tile_begin[c + 1] * wpt
+                chunks.append((start, -(-(end - start) // world)))
+            self.arrays.append((total, chunks))
+
+    def device_words(self, a: int) -> int:
+        start, part = self.arrays[a][1][-1]
+        return start + part * self.world
+
+    def part_bounds(self, a: int, c: int, rank: int) -> tuple[int, int]:
+        """Word range [lo, hi) of array a that rank `rank` holds of chunk c (clipped to the array)."""
+        total, chunks = self.arrays[a]
+        start, part = chunks[c]
+        return min(total, start + rank * part), min(total, start + (rank + 1) * part)
+
+    def host_words(self, a: int) -> int:
+        """Length of a rank's host buffer for array a: its (padded) parts of all chunks, back to back."""
+        return sum(part for _, part in self.arrays[a][1])
+
+
+class HostGenomeShard:
+    """What rank r holds of a packed genome in (pinned) host memory: for every chunk of the ChunkPlan its
+    1/world part of the codes and of the n_mask, back to back, plus the (small) record table of the whole
+    input.  Every rank uploads only this over its own PCIe link; the parts are all-gathered over NVLink
+    (`upload_allgather`), which replaces the reference's per-stage re-read of the whole FASTA by every
+    worker (vertexenumerator.h:1135-1214)."""
+
+    def __init__(self, plan: ChunkPlan, codes: torch.Tensor, n_mask: torch.Tensor, n_positions: int, rec_start, rec_len):
+        self.plan, self.codes, self.n_mask = plan, codes, n_mask           # int64 tensors (pinned when possible)
+        self.n_positions, self.rec_start, self.rec_len = int(n_positions), rec_start, rec_len
 
     @property
     def nbytes(self) -> int:
         return (self.codes.numel() + self.n_mask.numel()) * 8
 
 
-def shard_chunk(n_words: int, world: int) -> int:
-    return (n_words + world - 1) // world
-
-
-def shard_bounds(n_words: int, rank: int, world: int) -> tuple[int, int]:
-    c = shard_chunk(n_words, world)
-    return min(n_words, rank * c), min(n_words, (rank + 1) * c)
-
-
-def host_shard(codes, n_mask, n_positions: int, rec_start, rec_len, rank: int, world: int, pin: bool = True) -> HostGenomeShard:
-    """Slice of numpy uint64 arrays `codes` / `n_mask` that rank `rank` uploads."""
+def host_shard(codes, n_mask, n_positions: int, rec_start, rec_len, rank: int, world: int, pin: bool = True,
+               n_chunks: int = 8, fetch=None) -> HostGenomeShard:
+    """Rank `rank`'s shard of numpy uint64 arrays `codes` / `n_mask` (or of any source `fetch(a, lo, hi)` ->
+    numpy uint64 words [lo, hi) of array a, e.g. a device-resident genome)."""
     import numpy as np
+    plan = ChunkPlan(n_positions, len(codes) if fetch is None else codes, len(n_mask) if fetch is None else n_mask, world, n_chunks)
+    if fetch is None:
+        src = (codes, n_mask)
+        fetch = lambda a, lo, hi: src[a][lo:hi]
     out = []
-    for arr in (codes, n_mask):
-        lo, hi = shard_bounds(len(arr), rank, world)
-        t = torch.from_numpy(np.ascontiguousarray(arr[lo:hi]).view(np.int64).copy())
+    for a in range(2):
+        buf = np.zeros(plan.host_words(a), dtype=np.uint64)
+        off = 0
+        for c in range(plan.n_chunks):
+            lo, hi = plan.part_bounds(a, c, rank)
+            buf[off:off + hi - lo] = fetch(a, lo, hi)
+            off += plan.arrays[a][1][c][1]
+        t = torch.from_numpy(buf.view(np.int64))
         out.append(t.pin_memory() if pin and torch.cuda.is_available() else t)
-    return HostGenomeShard(out[0], out[1], len(codes), len(n_mask), n_positions, rec_start, rec_len)
+    return HostGenomeShard(plan, out[0], out[1], n_positions, rec_start, rec_len)
 
 
-def upload_allgather(shard: HostGenomeShard, rank: int, world: int, device) -> tuple[torch.Tensor, torch.Tensor]:
-    """-> (codes, n_mask) of the WHOLE genome as int64 tensors on `device`: H2D of this rank's slice,
-    then one all-gather per array (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
-    full = []
-    for host, n_words in ((shard.codes, shard.code_words), (shard.n_mask, shard.mask_words)):
-        c = shard_chunk(n_words, world)
-        whole = torch.empty(c * world, dtype=torch.int64, device=device)
-        mine = whole[rank * c:(rank + 1) * c] if world == 1 else torch.zeros(c, dtype=torch.int64, device=device)
-        mine[:host.numel()].copy_(host, non_blocking=True)
-        if host.numel() < c:
-            mine[host.numel():].zero_()
-        if world > 1:
-            dist.all_gather_into_tensor(whole, mine)
-        full.append(whole[:n_words])
-    return full[0], full[1]
+def upload_allgather(shard: HostGenomeShard, rank: int, world: int, device):
+    """-> (codes, n_mask, events): the WHOLE genome as int64 tensors on `device`, produced chunk by chunk
+    on a side stream: H2D of this rank's part of the chunk, then one all-gather per array (NCCL over NVLink
+    on GPUs, gloo in the CPU tests) straight into place.  events[c] = (first tile of chunk c, CUDA event
+    recorded when chunk c is complete) -- empty on CPU, where everything is synchronous."""
+    plan = shard.plan
+    on_gpu = torch.device(device).type == "cuda"
+    full = [torch.empty(plan.device_words(a), dtype=torch.int64, device=device) for a in range(2)]
+    stage = [torch.empty(max(p for _, p in plan.arrays[a][1]), dtype=torch.int64, device=device) for a in range(2)]
+    events = []
+    side = torch.cuda.Stream() if on_gpu else None
+    if on_gpu:
+        side.wait_stream(torch.cuda.current_stream())      # the allocations above
+    import contextlib
+    with (torch.cuda.stream(side) if on_gpu else contextlib.nullcontext()):
+        offs = [0, 0]
+        for c in range(plan.n_chunks):
+            for a, host in enumerate((shard.codes, shard.n_mask)):
+                start, part = plan.arrays[a][1][c]
+                mine = full[a][start + rank * part:start + (rank + 1) * part] if world == 1 else stage[a][:part]
+                mine.copy_(host[offs[a]:offs[a] + part], non_blocking=True)
+                offs[a] += part
+                if world > 1:
+                    dist.all_gather_into_tensor(full[a][start:start + part * world], mine)
+            if on_gpu:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                events.append((plan.tile_begin[c], ev))
+    for t in full + stage:
+        if on_gpu:
+            t.record_stream(side)
+    return full[0], full[1], events
 
 
 def sharded_run_host(shard: HostGenomeShard, rank: int, world: int, k: int, filter_bits: int, q: int = 5, rounds: int = 1,
                      out_host: torch.Tensor | None = None, dev_out=None):
-    """Host buffers in, host buffers out, on `world` GPUs: upload + all-gather of the packed genome,
-    the sharded run, and the device->host copy of this rank's slice of the de_bruijn.bin image into
-    `out_host` (uint8, pinned; bytes [0, slice_bytes) = image bytes [slice_offset, +slice_bytes) --
-    a rank would pwrite() them at that offset).  Returns (info, out_host, dev_out)."""
-    import numpy as np
+    """Host buffers in, host buffers out, on `world` GPUs: chunked upload + all-gather of the packed genome
+    (overlapped with the first pass over it), the sharded run, and the device->host copy of this rank's
+    slice of the de_bruijn.bin image into `out_host` (uint8, pinned; bytes [0, slice_bytes) = image bytes
+    [slice_offset, +slice_bytes) -- a rank would pwrite() them at that offset).
+    Returns (info, out_host, dev_out)."""
     from . import api
-    codes, n_mask = upload_allgather(shard, rank, world, "cuda")
+    codes, n_mask, events = upload_allgather(shard, rank, world, "cuda")
     s = api.Session(k=k, filter_bits=filter_bits, q=q, rounds=rounds, shard_index=rank, shard_count=world)
     try:
         s.set_genome_device(codes.data_ptr(), n_mask.data_ptr(), shard.n_positions, shard.rec_start, shard.rec_len,
                             keep=(codes, n_mask))
+        for tile_begin, ev in events:
+            s.add_genome_event(tile_begin, ev.cuda_event, keep=ev)
 
         class _G:  # what sharded_run needs to know about the genome
             n_positions, rec_len = shard.n_positions, shard.rec_len
