@@ -158,8 +158,9 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
 
 
 // ---- sharded variant (nparts > 1): ownership is sparse (1/nparts of the positions).
-// k_own decides ownership of EVERY position with as few instructions as possible (cheap fold of
-// the canonical k-mer, high occupancy); k_bin_list compacts the owned positions of a tile into a
+// k_own decides ownership of EVERY position with as few instructions as possible (the strand-symmetric
+// middle-11-mer key of owner_fold, by constant funnel shifts -- no rolling chain, the same cost for
+// every k >= 11; high occupancy); k_bin_list compacts the owned positions of a tile into a
 // CTA-wide list and runs the expensive part (64-bit hash, record, counting sort by slice) densely
 // on it.  One scan serves all the rounds of this GPU: the local round that owns a position
 // (1 + round, 0 = none / not a definite k-mer) is written as P bit planes of 1 bit per position.
@@ -172,17 +173,7 @@ k_own(GenomeView g, KParams kp, uint32_t part_base, uint32_t nlocal, uint64_t wo
 #pragma unroll
         for (int j = 0; j < P; ++j) pl[j] = 0;
         if (w * 32 < g.npos) {
-            if (W == 1) {
-                // k <= 31: every k-mer of this thread lies inside two code words; extract both strands
-                // with constant shifts (no rolling dependency chain between positions)
-                const uint64_t c0 = __ldg(g.codes + w), c1 = __ldg(g.codes + w + 1);
-                const uint32_t k2 = 2 * kp.k;
-                const uint64_t kmask = (~0ull) >> (64 - k2);
-                // reverse complement of the 128-bit window, pre-shifted so that position i's reverse
-                // complement is the low 2k bits of (r >> (64 - 2i))
-                const uint64_t rh = pairrev64(~c0), rl = pairrev64(~c1);
-                const uint32_t s0 = 64 - k2;  // 2..62
-                const uint64_t r_lo = (rl >> s0) | (rh << (64 - s0)), r_hi = rh >> s0;
+            {
                 uint32_t valid = ~0u;
                 if (w == 0 || any_n(g.nmask, w * 32, 32 + kp.k)) {
                     valid = 0;
@@ -195,13 +186,49 @@ k_own(GenomeView g, KParams kp, uint32_t part_base, uint32_t nlocal, uint64_t wo
                         if (run >= kp.k) valid |= 1u << i;
                     }
                 }
+                if (kp.k >= kOwnMid) {
+                    // ownership key = canonical middle 11-mer (owner_fold): A = the 64-base window shifted to the
+                    // middle of position 0's k-mer, B = its reverse complement; position i's middle 11-mer is bases
+                    // i.. of A and its reverse complement bases 53-i.. of B -- one constant funnel shift each
+                    // (any k >= 11, one to four words per k-mer: only the three code words around the middle are read)
+                    const uint32_t off = (kp.k - kOwnMid) >> 1, off2 = 2 * (off & 31);
+                    const uint64_t* cw = g.codes + w + (off >> 5);
+                    const uint64_t c0 = __ldg(cw), c1 = __ldg(cw + 1), c2 = __ldg(cw + 2);
+                    const uint64_t a0 = off2 ? (c0 >> off2) | (c1 << (64 - off2)) : c0;
+                    const uint64_t a1 = off2 ? (c1 >> off2) | (c2 << (64 - off2)) : c1;
+                    const uint64_t b0 = pairrev64(~a1), b1 = pairrev64(~a0);
+                    const uint32_t A[4] = {(uint32_t)a0, (uint32_t)(a0 >> 32), (uint32_t)a1, (uint32_t)(a1 >> 32)};
+                    const uint32_t B[5] = {(uint32_t)b0, (uint32_t)(b0 >> 32), (uint32_t)b1, (uint32_t)(b1 >> 32), 0u};
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        constexpr int kTop = 32 - 2 * (int)kOwnMid;
+                        const int sa = 2 * i, sb = 2 * (53 - i);
+                        const uint32_t m = __funnelshift_r(A[sa >> 5], A[(sa >> 5) + 1], sa & 31) << kTop;
+                        const uint32_t y = __funnelshift_r(B[sb >> 5], B[(sb >> 5) + 1], sb & 31) << kTop;
+                        const uint32_t local = owner_part(owner_fold_mid(m, y), kp.nparts) - part_base;
+                        if (P == 1) pl[0] |= (local < nlocal ? 1u : 0u) << i;
+                        else {
+                            const uint32_t id = local < nlocal ? local + 1u : 0u;
+#pragma unroll
+                            for (int j = 0; j < P; ++j) pl[j] |= ((id >> j) & 1u) << i;
+                        }
+                    }
+                } else {
+                // k < 11 (one word per k-mer): both strands of every position by constant shifts out of two code
+                // words and their reverse complement, multiplicative fold of the canonical k-mer
+                const uint64_t c0 = __ldg(g.codes + w), c1 = __ldg(g.codes + w + 1);
+                const uint32_t k2 = 2 * kp.k;
+                const uint64_t kmask = (~0ull) >> (64 - k2);
+                const uint64_t rh = pairrev64(~c0), rl = pairrev64(~c1);
+                const uint32_t s0 = 64 - k2;
+                const uint64_t r_lo = (rl >> s0) | (rh << (64 - s0)), r_hi = rh >> s0;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const uint64_t x = (i ? ((c0 >> (2 * i)) | (c1 << (64 - 2 * i))) : c0) & kmask;
                     const uint64_t y = (i ? ((r_lo >> (64 - 2 * i)) | (r_hi << (2 * i))) : r_hi) & kmask;
                     Kmer<1> canon;
                     canon.w[0] = x < y ? x : y;
-                    const uint32_t local = owner_part(owner_fold<1>(canon), kp.nparts) - part_base;
+                    const uint32_t local = owner_part(owner_fold<1>(canon, kp.k), kp.nparts) - part_base;
                     if (P == 1) pl[0] |= (local < nlocal ? 1u : 0u) << i;
                     else {
                         const uint32_t id = local < nlocal ? local + 1u : 0u;
@@ -209,27 +236,9 @@ k_own(GenomeView g, KParams kp, uint32_t part_base, uint32_t nlocal, uint64_t wo
                         for (int j = 0; j < P; ++j) pl[j] |= ((id >> j) & 1u) << i;
                     }
                 }
+                }
 #pragma unroll
                 for (int j = 0; j < P; ++j) pl[j] &= valid;
-            } else {
-                Window<W> win;
-                win.load(g, w, kp.k);
-                if (win.valid) {
-                    uint64_t nf = win.next_feed;
-#pragma unroll 4
-                    for (int i = 0; i < 32; ++i) {
-                        uint32_t nxt = (uint32_t)nf & 3u;
-                        nf >>= 2;
-                        if ((win.valid >> i) & 1u) {
-                            bool fwd = kmer_less<W>(win.X, win.Y);
-                            const uint32_t local = owner_part(owner_fold<W>(kmer_select<W>(fwd, win.X, win.Y)), kp.nparts) - part_base;
-                            const uint32_t id = local < nlocal ? local + 1u : 0u;
-#pragma unroll
-                            for (int j = 0; j < P; ++j) pl[j] |= ((id >> j) & 1u) << i;
-                        }
-                        roll<W>(win.X, win.Y, nxt, kp.k);
-                    }
-                }
             }
         }
 #pragma unroll

@@ -194,11 +194,38 @@ __device__ __forceinline__ uint64_t kmer_hash(const Kmer<W>& c, uint64_t seed) {
     return h;
 }
 
-// ---- hash-range ownership (rounds x GPUs): a cheap multiplicative fold of the canonical k-mer,
-// evaluated for EVERY position on every GPU, so it must cost little; the full 64-bit hash is
-// only needed for the positions a GPU owns.  Uniform to ~0.3 % over 8 parts on genomic k-mers.
+// ---- hash-range ownership (rounds x GPUs).  It is evaluated for EVERY position on every GPU (k_own), so it
+// must cost little; the full 64-bit hash is only needed for the positions a GPU owns.  Any function of the
+// vertex that is the same for both strands will do.  k is odd, so the middle 11 bases of the reverse
+// complement are the reverse complement of the middle 11 bases: the key is the smaller of the two 22-bit
+// values, multiplied by a constant -- two funnel shifts, a min and a multiply per position instead of
+// building, comparing and folding both 2k-bit strands.  4^11 / 2 classes spread evenly over any sensible number
+// of parts (uniform to a fraction of a per cent on the synthetic sets; all copies of a low-complexity k-mer go
+// to one owner under any scheme).  k < 11: multiplicative fold of the whole canonical k-mer.
+constexpr uint32_t kOwnMid = 11;
+constexpr uint32_t kOwnMidMask = (1u << (2 * kOwnMid)) - 1u;
+__device__ __forceinline__ uint32_t pairrev32(uint32_t x) {
+    x = __brev(x);
+    return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+}
+// m, y: the middle 11-mer and its reverse complement, top-aligned (<< 10) -- both in any order
+__device__ __forceinline__ uint32_t owner_fold_mid(uint32_t m_top, uint32_t y_top) {
+    return min(m_top, y_top) * 0x9E3779B1u;
+}
 template <int W>
-__device__ __forceinline__ uint32_t owner_fold(const Kmer<W>& canon) {
+__device__ __forceinline__ uint32_t owner_fold(const Kmer<W>& canon, uint32_t k) {
+    if (k >= kOwnMid) {
+        const uint32_t bit = 2 * ((k - kOwnMid) >> 1), wi = bit >> 6, sh = bit & 63;
+        uint64_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            if (j == (int)wi) lo = canon.w[j];
+            if (j == (int)wi + 1) hi = canon.w[j];
+        }
+        const uint32_t m = (uint32_t)((lo >> sh) | ((hi << 1) << (63 - sh))) & kOwnMidMask;
+        const uint32_t y = pairrev32(~m) >> (32 - 2 * kOwnMid);   // reverse complement of the 11 bases
+        return owner_fold_mid(m << (32 - 2 * kOwnMid), y << (32 - 2 * kOwnMid));
+    }
     uint32_t f = 0;
 #pragma unroll
     for (int j = 0; j < W; ++j) {

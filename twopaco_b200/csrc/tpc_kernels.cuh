@@ -114,7 +114,7 @@ k_fill(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t ntiles,
             if ((win.valid >> i) & 1u) {
                 bool fwd = kmer_less<W>(win.X, win.Y);
                 Kmer<W> canon = kmer_select<W>(fwd, win.X, win.Y);
-                if (kp.nparts == 1 || owner_part(owner_fold<W>(canon), kp.nparts) == kp.part) {
+                if (kp.nparts == 1 || owner_part(owner_fold<W>(canon, kp.k), kp.nparts) == kp.part) {
                     uint64_t h = kmer_hash<W>(canon, kp.seed);
                     uint32_t code = occurrence_code(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
                     uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
@@ -152,7 +152,7 @@ k_query(GenomeView g, const uint32_t* __restrict__ filter, KParams kp, uint64_t 
                 if ((win.valid >> i) & 1u) {
                     bool fwd = kmer_less<W>(win.X, win.Y);
                     Kmer<W> canon = kmer_select<W>(fwd, win.X, win.Y);
-                    if (kp.nparts == 1 || owner_part(owner_fold<W>(canon), kp.nparts) == kp.part) {
+                    if (kp.nparts == 1 || owner_part(owner_fold<W>(canon, kp.k), kp.nparts) == kp.part) {
                         uint64_t h = kmer_hash<W>(canon, kp.seed);
                         const uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
                         uint32_t vm = vertex_mask<Q>(h);
@@ -192,7 +192,7 @@ __device__ __forceinline__ Occ<W> occurrence_at(const GenomeView& g, uint64_t p,
     o.Y = revcomp<W>(o.X, kp.k);
     o.fwd = kmer_less<W>(o.X, o.Y);
     Kmer<W> canon = kmer_select<W>(o.fwd, o.X, o.Y);
-    o.fold = owner_fold<W>(canon);
+    o.fold = owner_fold<W>(canon, kp.k);
     o.h = kmer_hash<W>(canon, kp.seed);
     return o;
 }
@@ -245,7 +245,7 @@ k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t n
             o.Y = revcomp<W>(o.X, kp.k);
             o.fwd = kmer_less<W>(o.X, o.Y);
             const Kmer<W> canon = kmer_select<W>(o.fwd, o.X, o.Y);
-            if (!op.n && kp.nparts > 1 && owner_part(owner_fold<W>(canon), kp.nparts) != kp.part) continue;  // marked in another round
+            if (!op.n && kp.nparts > 1 && owner_part(owner_fold<W>(canon, kp.k), kp.nparts) != kp.part) continue;  // marked in another round
             o.h = kmer_hash<W>(canon, kp.seed);
             Neigh nb = orient(o.fwd, stage_base(s_codes, lp - 1), stage_base(s_codes, lp + kp.k), stage_n(s_nmask, mp - 1), stage_n(s_nmask, mp + kp.k));
             // neighbour sets in canonical orientation (candidateoccurence.h:25-50; h:778-796)
