@@ -513,11 +513,20 @@ static uint32_t choose_sub_rounds(tpc_session* s) {
     for (uint32_t S = 1; S <= 8; ++S)
         if (fits(S, 1)) { S1 = S; break; }
     if (can_pipe && s->prm.rounds * S1 >= 2) {   // several rounds anyway: overlap them, with two half-size scratches
-        // Only with >= 4 rounds: the first binning and the last fill are not overlapped, the overlapped fill runs at
-        // a quarter of the SM, and every extra sub-round is one more scan of the ownership planes.  Measured at C3:
-        // 1 GPU (3 -> 5 sub-rounds) 640 -> 593 ms; 2 GPUs (2 -> 3 sub-rounds) 321 -> 344 ms, hence the threshold.
-        for (uint32_t S = S1; S <= 2 * S1 && S <= 12; ++S)
-            if (s->prm.rounds * S >= 4 && own_planes_for(s->prm.rounds * S) > 0 && fits(S, 2)) { s->pipe = true; return S; }
+        // Pipelining hides the fill of all rounds but the last behind the binning, and pays for it with extra
+        // sub-rounds (two scratches must fit), each one more pass of k_bin_list over the ownership planes and the
+        // genome of ALL positions, whatever share of them the GPU owns.  Per position, measured at C3 (k = 25):
+        // fill 7.8 ps per owned record, one k_bin_list pass 1.9 ps.  1 GPU (3 -> 5 sub-rounds): 640 -> 586 ms per
+        // step; 2 GPUs (2 -> 3 or 4 sub-rounds): 321 -> 344 / 350 ms -- so only when the model predicts a clear gain.
+        for (uint32_t S = S1; S <= 2 * S1 && S <= 12; ++S) {
+            const double rounds_now = (double)s->prm.rounds * S;
+            const double hidden = 7.8 / s->prm.shard_count * (rounds_now - 1.0) / rounds_now;
+            const double extra = 1.9 * s->prm.rounds * (double)(S - S1);
+            if (rounds_now >= 3 && hidden - extra > 1.0 && own_planes_for(s->prm.rounds * S) > 0 && fits(S, 2)) {
+                s->pipe = true;
+                return S;
+            }
+        }
     }
     return S1;
 }

@@ -209,29 +209,46 @@ def upload_allgather(shard: HostGenomeShard, rank: int, world: int, device):
     plan = shard.plan
     on_gpu = torch.device(device).type == "cuda"
     full = [torch.empty(plan.device_words(a), dtype=torch.int64, device=device) for a in range(2)]
-    stage = [torch.empty(max(p for _, p in plan.arrays[a][1]), dtype=torch.int64, device=device) for a in range(2)]
+    # two staging buffers per array: the H2D copy of chunk c+1 (copy engine, PCIe) runs beside the all-gather of
+    # chunk c (NVLink), each on its own side stream
+    stage = [[torch.empty(max(p for _, p in plan.arrays[a][1]), dtype=torch.int64, device=device) for _ in range(2)] for a in range(2)]
     events = []
-    side = torch.cuda.Stream() if on_gpu else None
-    if on_gpu:
-        side.wait_stream(torch.cuda.current_stream())      # the allocations above
     import contextlib
-    with (torch.cuda.stream(side) if on_gpu else contextlib.nullcontext()):
-        offs = [0, 0]
-        for c in range(plan.n_chunks):
-            for a, host in enumerate((shard.codes, shard.n_mask)):
-                start, part = plan.arrays[a][1][c]
-                mine = full[a][start + rank * part:start + (rank + 1) * part] if world == 1 else stage[a][:part]
+    h2d = torch.cuda.Stream() if on_gpu else None
+    ag = torch.cuda.Stream() if on_gpu else None
+    on = lambda st: torch.cuda.stream(st) if on_gpu else contextlib.nullcontext()
+    if on_gpu:
+        h2d.wait_stream(torch.cuda.current_stream())       # the allocations above
+        ag.wait_stream(torch.cuda.current_stream())
+    gathered = [[None, None], [None, None]]                # all-gather that last read staging buffer [a][b]
+    offs = [0, 0]
+    for c in range(plan.n_chunks):
+        for a, host in enumerate((shard.codes, shard.n_mask)):
+            start, part = plan.arrays[a][1][c]
+            b = c & 1
+            with on(h2d):
+                if on_gpu and gathered[a][b] is not None:
+                    h2d.wait_event(gathered[a][b])
+                mine = full[a][start + rank * part:start + (rank + 1) * part] if world == 1 else stage[a][b][:part]
                 mine.copy_(host[offs[a]:offs[a] + part], non_blocking=True)
                 offs[a] += part
+                if on_gpu:
+                    copied = torch.cuda.Event()
+                    copied.record(h2d)
+            with on(ag):
+                if on_gpu:
+                    ag.wait_event(copied)
                 if world > 1:
                     dist.all_gather_into_tensor(full[a][start:start + part * world], mine)
-            if on_gpu:
-                ev = torch.cuda.Event()
-                ev.record(side)
-                events.append((plan.tile_begin[c], ev))
-    for t in full + stage:
+                if on_gpu:
+                    gathered[a][b] = torch.cuda.Event()
+                    gathered[a][b].record(ag)
         if on_gpu:
-            t.record_stream(side)
+            events.append((plan.tile_begin[c], gathered[1][c & 1]))   # n_mask of chunk c is gathered last
+    if on_gpu:
+        for t in full + stage[0] + stage[1]:
+            t.record_stream(h2d)
+            t.record_stream(ag)
     return full[0], full[1], events
 
 
