@@ -406,6 +406,46 @@ def test_sub_rounds_direct_path_and_shards(monkeypatch, golden):
     assert total == g["distinct_junctions"]
 
 
+@pytest.mark.parametrize("mode", ["direct", "binned"])
+def test_host_buffer_run_with_chunked_upload(mode, monkeypatch):
+    """The multi-GPU host-buffer entry point (dist.sharded_run_host) on ONE GPU: the packed genome is uploaded
+    chunk by chunk on side streams and the session starts on the chunks that have arrived
+    (tpc_session_add_genome_event).  The image must be byte-identical to the oracle's."""
+    from twopaco_b200 import dist as tdist
+    monkeypatch.setenv("TPC_FILTER_MODE", mode)
+    monkeypatch.setenv("TPC_SLICE_LOG2", "12")
+    recs = synth.founder_family(seed=77, genomes=5, records_per_genome=3, record_len=40_000, p=0.01, n_runs=2) + [b"ACGTACG", b""]
+    g = api.pack_records(recs)
+    ref, nj, nm = O.find_junctions(recs, 25)
+    for n_chunks in (1, 5, 64):
+        sh = tdist.host_shard(g.codes, g.n_mask, g.n_positions, g.rec_start, g.rec_len, 0, 1, n_chunks=n_chunks)
+        assert 1 <= sh.plan.n_chunks <= n_chunks and (n_chunks == 1 or sh.plan.n_chunks > 1)
+        info, out_host, _ = tdist.sharded_run_host(sh, 0, 1, 25, 22)
+        assert info["junctions"] == nj and info["records"] == nm and info["slice_offset"] == 0
+        assert out_host[:info["slice_bytes"]].numpy().tobytes() == ref
+
+
+def test_genome_events_are_validated():
+    recs = [b"ACGTTGCATGCATGCATTTGACCA" * 50]
+    g = api.pack_records(recs)
+    import torch
+    codes = torch.from_numpy(g.codes.view(np.int64)).cuda()
+    nmask = torch.from_numpy(g.n_mask.view(np.int64)).cuda()
+    ev = torch.cuda.Event()
+    ev.record()
+    s = api.Session(k=11, filter_bits=20)
+    with pytest.raises(api.TpcError):
+        s.add_genome_event(0, ev.cuda_event)                  # no genome yet
+    s.set_genome_device(codes.data_ptr(), nmask.data_ptr(), g.n_positions, g.rec_start, g.rec_len, keep=(codes, nmask))
+    with pytest.raises(api.TpcError):
+        s.add_genome_event(3, ev.cuda_event)                  # the first chunk starts at tile 0
+    s.add_genome_event(0, ev.cuda_event, keep=ev)
+    with pytest.raises(api.TpcError):
+        s.add_genome_event(0, ev.cuda_event)                  # ascending tile order
+    s.find_candidates()
+    s.close()
+
+
 def test_multi_gpu_torchrun():
     """N > 1: hash-range shards over NCCL (skipped on single-GPU boxes)."""
     import subprocess
