@@ -292,6 +292,9 @@ def main() -> None:
                 "filter_touches_per_s_G": {k: round(recs / (v[0] * 1e-3) / 1e9, 2) for k, v in kernels.items()
                                             if v[0] > 0 and k != "k_bin"},
                 "all_filter_kernels": {k: {"ms": round(v[0], 3), "GBps": gbps(*v)} for k, v in kernels.items()}}
+    if per.get("ms_bin_overlapped", 0) > 0:
+        roofline["overlap"] = ("pipelined rounds: k_bin_list of round r+1 (3 CTAs/SM) runs beside k_apply_fill of round r (1 CTA/SM) on two "
+                               "streams; k_bin's time is ms_bin + ms_bin_overlapped, the fill's time is what it takes while sharing the SMs")
 
     # the north-star's second roofline: uniform random 32-byte sector touches into a table of the filter's size
     # (k_probe, measured in this run before the workload was generated).  The binned path does not touch HBM at
@@ -313,6 +316,7 @@ def main() -> None:
                    "parallelism": f"hash-range shards x{world}" if world > 1 else "single GPU",
                    "l2_hygiene": "inputs (packed genome + 2^f-bit filter) are far larger than the 126 MB L2"},
         "stages_ms": {k: round(v / args.steps, 3) for k, v in stage_ms.items()},
+        "untimed_ms": round(ms_per_step - sum(v for k, v in stage_ms.items() if k != "ms_bin_overlapped") / args.steps, 3),
         "result": {**runner.last, "candidate_marks": st.candidate_marks, "candidate_kmers": st.candidate_kmers},
         "gpu_launches": launches, "roofline": roofline,
     }
