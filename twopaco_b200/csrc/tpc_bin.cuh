@@ -253,13 +253,6 @@ constexpr size_t bin_list_smem_bytes(int R) {
            2 * (kTileCodeWords + kTileMaskWords) * 8;
 }
 
-// 8-byte asynchronous global->shared copy (LDGSTS): the next tile's genome words travel while this
-// tile is being processed
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
-}
-
 template <int W, int R>
 __global__ void __launch_bounds__(kTileThreads, (R <= 8 ? 4 : 2))
 k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_end, uint64_t wave_base, OwnPlanes op) {
@@ -289,8 +282,8 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
         const uint64_t w0 = t * kTileThreads, cb = w0 ? w0 - 1 : 0, mb = cb >> 1;
         uint64_t* sc = s_stage + buf * (kTileCodeWords + kTileMaskWords);
         uint64_t* sm = sc + kTileCodeWords;
-        for (int j = tid; j < kTileCodeWords; j += kTileThreads) cp_async8(sc + j, g.codes + cb + j);
-        for (int j = tid; j < kTileMaskWords; j += kTileThreads) cp_async8(sm + j, g.nmask + mb + j);
+        for (int j = tid; j < kTileCodeWords; j += kTileThreads) tile_cp_async8(sc + j, g.codes + cb + j);
+        for (int j = tid; j < kTileMaskWords; j += kTileThreads) tile_cp_async8(sm + j, g.nmask + mb + j);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     uint64_t tile = tile_begin + blockIdx.x;
