@@ -137,3 +137,40 @@ def test_ingest_errors_and_odd_framing(tmp_path):
     e.write_bytes(b"")
     layout, npos, rs, rl = api.ingest_fasta([str(e), str(f)])
     assert layout == b"NACGTNTTNN"
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_ingest_fuzz_against_the_scalar_parsers(seed, tmp_path, monkeypatch):
+    """The 32-byte-at-a-time (AVX2) classification of tpc_ingest_fasta against tpc_read_fasta (scalar,
+    streamfastaparser.cpp:29-133) and the oracle's parser on random files: every letter of the alphabet in both
+    cases, all whitespace kinds anywhere in the sequence text, ragged lines, records shorter than a SIMD block,
+    '>' inside headers, no trailing newline; pieces of odd sizes so that blocks straddle piece seams."""
+    import random
+    rnd = random.Random(seed)
+    alphabet = "ACGTURYKMSWBDHWNXV"
+    letters = alphabet + alphabet.lower() + "ACGTacgt" * 6
+    blanks = [" ", "\t", "\n", "\r\n", "\v", "\f", "\n\n"]
+    text = []
+    for r in range(rnd.randint(1, 7)):
+        text.append(">r%d some >text\t here" % r + rnd.choice(["\n", "\r\n"]))
+        for _ in range(rnd.choice([0, 1, 3, 40, 400])):
+            n = rnd.choice([0, 1, 5, 31, 32, 33, 63, 64, 80, 80, 80, 200])
+            text.append("".join(rnd.choice(letters) for _ in range(n)))
+            text.append(rnd.choice(blanks) if rnd.random() < 0.9 else "")
+    body = "".join(text)
+    if rnd.random() < 0.5:
+        body = body.rstrip()
+    f = tmp_path / "fuzz.fa"
+    f.write_bytes(body.encode())
+    ref = O.parse_fasta(str(f))
+    assert api.read_fasta([str(f)]) == ref
+    for piece in (0, 37, 64, 1001):
+        if piece:
+            monkeypatch.setenv("TPC_INGEST_PIECE", str(piece))
+        layout, npos, rec_start, rec_len = api.ingest_fasta([str(f)], threads=3)
+        assert layout == b"N" + b"".join(x + b"N" for x in ref), (seed, piece)
+    # an invalid character inside a block, between valid ones
+    bad = body.replace("\n", "\n", 1).encode() + b"\n>z\n" + b"ACGT" * 20 + b"!" + b"ACGT" * 20 + b"\n"
+    f.write_bytes(bad)
+    with pytest.raises(api.TpcError, match="invalid character '!' in sequence z"):
+        api.ingest_fasta([str(f)], threads=2)

@@ -25,7 +25,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
-#include <cuda_runtime_api.h>
+#include <immintrin.h>
 
 #include "tpc_ingest.h"
 #include "tpc_internal.h"
@@ -51,6 +51,76 @@ struct Tables {
     }
 };
 const Tables kT;
+
+// ---- byte classification, 32 bytes at a time (AVX2, chosen at run time; the scalar loops remain for tails and
+// for hosts without AVX2).  A byte is a sequence letter iff (lo_lut[low nibble] & hi_lut[high nibble]) has bit 0 or 1:
+//   bit 0: high nibble 4/6 with low nibble of A B C D G H K M N      bit 1: high nibble 5/7 with low nibble of R S T U V W X Y
+//   bit 2: high nibble 0 with 9..D (\t \n \v \f \r)                  bit 3: 0x20 (space)          0: invalid character
+// -- exactly the classes of Tables::cls (dnachar.cpp:11 alphabet, either case; isspace() in the C locale).
+#define TPC_AVX2 __attribute__((target("avx2,popcnt")))
+TPC_AVX2 inline __m256i classify32(__m256i v) {
+    const __m256i lo_lut = _mm256_setr_epi8(8, 1, 3, 3, 3, 2, 2, 3, 3, 6, 4, 5, 4, 5, 1, 0, 8, 1, 3, 3, 3, 2, 2, 3, 3, 6, 4, 5, 4, 5, 1, 0);
+    const __m256i hi_lut = _mm256_setr_epi8(4, 0, 8, 0, 1, 2, 1, 2, 0, 0, 0, 0, 0, 0, 0, 0, 4, 0, 8, 0, 1, 2, 1, 2, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i nib = _mm256_set1_epi8(0x0F);
+    const __m256i lo = _mm256_shuffle_epi8(lo_lut, _mm256_and_si256(v, nib));
+    const __m256i hi = _mm256_shuffle_epi8(hi_lut, _mm256_and_si256(_mm256_srli_epi16(v, 4), nib));
+    return _mm256_and_si256(lo, hi);
+}
+
+// bases and validity of p[0, n): returns the number of whole 32-byte blocks consumed
+TPC_AVX2 size_t count_avx2(const unsigned char* p, size_t n, uint64_t* bases, bool* bad) {
+    const __m256i zero = _mm256_setzero_si256(), three = _mm256_set1_epi8(3);
+    uint64_t cnt = 0;
+    uint32_t invalid = 0;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i t = classify32(_mm256_loadu_si256((const __m256i*)(p + i)));
+        const uint32_t not_letter = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_and_si256(t, three), zero));
+        invalid |= (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(t, zero));
+        cnt += (uint64_t)__builtin_popcount(~not_letter);
+    }
+    *bases += cnt;
+    *bad |= invalid != 0;
+    return i;
+}
+
+// normalised letters of p[0, n) appended at dst (whitespace and anything else skipped, like the scalar loop):
+// returns the whole blocks consumed, *dst_io advanced.  Never writes a byte beyond the letters it appends.
+TPC_AVX2 size_t emit_avx2(const unsigned char* p, size_t n, uint8_t** dst_io) {
+    const __m256i zero = _mm256_setzero_si256(), three = _mm256_set1_epi8(3), upper = _mm256_set1_epi8((char)0xDF);
+    const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'), cT = _mm256_set1_epi8('T'),
+                  cN = _mm256_set1_epi8('N');
+    uint8_t* dst = *dst_io;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i v = _mm256_loadu_si256((const __m256i*)(p + i));
+        const __m256i t = classify32(v);
+        uint32_t keep = ~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_and_si256(t, three), zero));
+        const __m256i u = _mm256_and_si256(v, upper);
+        const __m256i acgt = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, cA), _mm256_cmpeq_epi8(u, cC)),
+                                             _mm256_or_si256(_mm256_cmpeq_epi8(u, cG), _mm256_cmpeq_epi8(u, cT)));
+        const __m256i out = _mm256_blendv_epi8(cN, u, acgt);
+        if (keep == 0xFFFFFFFFu) {
+            _mm256_storeu_si256((__m256i*)dst, out);
+            dst += 32;
+            continue;
+        }
+        alignas(32) uint8_t tmp[32];
+        _mm256_store_si256((__m256i*)tmp, out);
+        while (keep) {   // runs of letters between the skipped bytes (normally: one line break per block at most)
+            const uint32_t s = (uint32_t)__builtin_ctz(keep);
+            const uint32_t rest = keep >> s;
+            const uint32_t len = rest == (0xFFFFFFFFu >> s) ? 32 - s : (uint32_t)__builtin_ctz(~rest);
+            memcpy(dst, tmp + s, len);
+            dst += len;
+            keep = s + len >= 32 ? 0u : keep & (0xFFFFFFFFu << (s + len));
+        }
+    }
+    *dst_io = dst;
+    return i;
+}
+
+const bool kHaveAvx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt") && !getenv("TPC_INGEST_SCALAR");
 
 struct Mapped {
     const unsigned char* p = nullptr;
@@ -165,7 +235,9 @@ int ingest_plan(const char* const* paths, size_t n_files, uint32_t threads, Inge
         const unsigned char* p = files[pc.file].p;
         uint64_t n = 0;
         bool bad = false;
-        for (size_t b = pc.lo; b < pc.hi; ++b) {
+        size_t b = pc.lo;
+        if (kHaveAvx2) b += count_avx2(p + b, pc.hi - b, &n, &bad);
+        for (; b < pc.hi; ++b) {
             uint8_t c = kT.cls[p[b]];
             n += c <= 4;
             bad |= c == 6;
@@ -238,7 +310,9 @@ int ingest_emit(const IngestPlan& plan, uint32_t threads, uint64_t span_bytes, I
             const Piece& pc = pieces[i + t];
             const unsigned char* p = files[pc.file].p;
             uint8_t* dst = buf + (dest_lo(pc) - span_lo);
-            for (size_t b = pc.lo; b < pc.hi; ++b) {
+            size_t b = pc.lo;
+            if (kHaveAvx2) b += emit_avx2(p + b, pc.hi - b, &dst);
+            for (; b < pc.hi; ++b) {
                 unsigned char ch = p[b];
                 if (kT.cls[ch] <= 4) *dst++ = (uint8_t)kT.norm[ch];
             }
