@@ -344,6 +344,21 @@ def test_binned_filter_passes_match_golden(name, slice_log2, buffer_mb, golden, 
     assert st.junctions == g["distinct_junctions"]
 
 
+@pytest.mark.parametrize("name", ["family_k29", "family_k33", "family_k65", "family_k75", "family_k97"])
+def test_kmer_word_count_boundaries_on_the_sharded_binned_path(name, golden, monkeypatch):
+    """k at the word-count boundaries of the packed k-mer (and at the limits of the one-window extraction of
+    k_bin_list / the ownership window of k_own) through k_own + k_bin_list + the apply kernels, 3 sub-rounds."""
+    spec, g = CASES[name], golden[name]
+    monkeypatch.setenv("TPC_FILTER_MODE", "binned")
+    monkeypatch.setenv("TPC_SLICE_LOG2", "12")
+    monkeypatch.setenv("TPC_SUBROUNDS", "3")
+    with case_files(spec) as (paths, _, _):
+        recs = api.read_fasta(paths)
+    img, st = api.junctions_host(api.pack_records(recs), k=spec["k"], filter_bits=21, q=4)
+    assert st.ms_bin > 0 and st.sub_rounds == 3
+    assert canon_md5(bytes(img)) == g["canon_md5"] and st.junctions == g["distinct_junctions"]
+
+
 def test_binned_rounds_and_shards(monkeypatch, golden):
     monkeypatch.setenv("TPC_FILTER_MODE", "binned")
     monkeypatch.setenv("TPC_SLICE_LOG2", "12")
