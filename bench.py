@@ -50,6 +50,13 @@ WORKLOADS = {
 }
 
 
+# (junctions, records, stubs) of the synthetic workloads: identical in every run of round 1 -- direct and binned filter
+# passes, 1 / 2 / 4 / 8 GPUs, with and without sub-rounds and pipelining.  A run that deviates has lost or invented
+# junctions (small parity tests can stay green while a race only shows at this scale), so the bench line says so.
+EXPECTED_COUNTS = {"c3": (36118333, 248411004, 8), "c2": (3310265, 150000784, 22),
+                   "c4k63": (34766769, 232728501, 19), "c4k127": (32624952, 208872372, 32)}
+
+
 # ---------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------
@@ -317,7 +324,10 @@ def main() -> None:
                    "l2_hygiene": "inputs (packed genome + 2^f-bit filter) are far larger than the 126 MB L2"},
         "stages_ms": {k: round(v / args.steps, 3) for k, v in stage_ms.items()},
         "untimed_ms": round(ms_per_step - sum(v for k, v in stage_ms.items() if k != "ms_bin_overlapped") / args.steps, 3),
-        "result": {**runner.last, "candidate_marks": st.candidate_marks, "candidate_kmers": st.candidate_kmers},
+        "result": {**runner.last, "candidate_marks": st.candidate_marks, "candidate_kmers": st.candidate_kmers,
+                   "counts_match_round1": (None if args.workload not in EXPECTED_COUNTS else
+                                           (runner.last.get("junctions"), runner.last.get("records"), runner.last.get("stubs"))
+                                           == EXPECTED_COUNTS[args.workload])},
         "gpu_launches": launches, "roofline": roofline,
     }
     if rank == 0:
