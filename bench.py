@@ -9,7 +9,14 @@ exact pass, id index, ordered emit) over one synthetic genome set.
 * value      : whole-job throughput, packed genome already resident in HBM, image left in HBM.
 * e2e        : same metric through the C-ABI call with HOST buffers (tpc_junctions_host):
                H2D of the packed genome and D2H of the de_bruijn.bin image inside the timed region.
-* roofline   : the dominant kernel (candidate query), algorithmic bytes / CUDA-event time.
+* roofline   : the dominant filter kernel: algorithmic HBM bytes / CUDA-event time against the measured HBM
+               peak, plus `l2_random` -- the apply kernels' sector touches/s against a probe of the same access
+               pattern (random 32-byte sectors inside one L2-resident slice, record stream beside it), and
+               `hbm_random` -- the direct kernels' bound (random sectors in a 2^f-bit table in HBM).
+* parity     : `result.image_digest` = position-keyed digest of the de_bruijn.bin image (sum over ranks of the
+               slices' digests, tpc_image_digest_device): identical at N = 1/2/4/8, and compared inside every run
+               with the digest of one untimed step through the DIRECT filter kernels (a different code path) and
+               with tests/golden/workload_digests.json (provenance recorded there).
 * cpu_baseline: the UNMODIFIED reference (oracle/_ref/twopaco) on a bounded sample of the same
                workload with all host cores; the sample's output is also compared (canonical
                stream) with ours -- that, not the oracle, is what `parity_on_sample` reports.
@@ -50,11 +57,12 @@ WORKLOADS = {
 }
 
 
-# (junctions, records, stubs) of the synthetic workloads: identical in every run of round 1 -- direct and binned filter
-# passes, 1 / 2 / 4 / 8 GPUs, with and without sub-rounds and pipelining.  A run that deviates has lost or invented
-# junctions (small parity tests can stay green while a race only shows at this scale), so the bench line says so.
-EXPECTED_COUNTS = {"c3": (36118333, 248411004, 8), "c2": (3310265, 150000784, 22),
-                   "c4k63": (34766769, 232728501, 19), "c4k127": (32624952, 208872372, 32)}
+def golden_digest(workload: str):
+    """Digest / counts of a workload's image recorded in tests/golden/workload_digests.json (with provenance)."""
+    try:
+        return json.loads((ROOT / "tests" / "golden" / "workload_digests.json").read_text()).get(workload)
+    except OSError:
+        return None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -98,12 +106,25 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the unmodified reference on a bounded sample
 # ---------------------------------------------------------------------------------------------
-def sample_records(dg, wl) -> list[bytes]:
-    """Bounded sample of the workload: the first sample_bp bases of the first record of every genome."""
-    return [dg.record_ascii(g * wl["records"], wl["sample_bp"]) for g in range(wl["genomes"])]
+def sample_records(wl) -> list[bytes]:
+    """Bounded sample of the workload: the first sample_bp bases of the first record of every genome, from the
+    numpy restatement of the on-device generator (same bases; checked by tests/test_gpu_parity.py)."""
+    from tools.benchutil import hostsynth
+    return [hostsynth.record_prefix(wl["seed"], wl["records"], wl["p"], g, 0, wl["sample_bp"], wl["length"])
+            for g in range(wl["genomes"])]
 
 
-def run_reference_on(records: list[bytes], wl: dict, threads: int):
+def reference_filter_bits(wl) -> int:
+    """-f of the reference run: the workload's, unless the host cannot hold a 2^f-bit filter comfortably."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    return wl["f"] if avail > 3 * (1 << wl["f"]) // 8 else min(wl["f"], 32)
+
+
+def run_reference_on(records: list[bytes], wl: dict, threads: int, f: int):
     from oracle import oracle as O
     with tempfile.TemporaryDirectory(prefix="tpc_bench_") as d:
         paths = []
@@ -112,7 +133,7 @@ def run_reference_on(records: list[bytes], wl: dict, threads: int):
             O.write_fasta(p, [r], names=[f"g{i}_c0"])
             paths.append(p)
         t0 = time.perf_counter()
-        img, log = O.run_reference(paths, wl["k"], min(wl["f"], 32), q=wl["q"], r=1, t=threads)
+        img, log = O.run_reference(paths, wl["k"], f, q=wl["q"], r=1, t=threads)
         dt = time.perf_counter() - t0
     return img, dt
 
@@ -124,11 +145,12 @@ def cpu_baseline(recs: list[bytes], wl: dict) -> dict:
         return {"value": None, "unit": "Gbp/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/twopaco missing"}
     cores = os.cpu_count() or 1
     bp = sum(len(r) for r in recs)
-    ref_img, dt = run_reference_on(recs, wl, cores)
-    ours, _ = api.junctions_host(api.pack_records(recs), k=wl["k"], filter_bits=min(wl["f"], 32), q=wl["q"])
+    f = reference_filter_bits(wl)
+    ref_img, dt = run_reference_on(recs, wl, cores, f)
+    ours, _ = api.junctions_host(api.pack_records(recs), k=wl["k"], filter_bits=f, q=wl["q"])
     return {"value": bp / dt / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "reference",
             "sample": f"first {wl['sample_bp']} bp of record 0 of each of the {wl['genomes']} genomes ({bp} bp), "
-                      f"-k {wl['k']} -f {min(wl['f'], 32)} -q {wl['q']} -t {cores}, wall {dt:.2f} s incl. FASTA parsing",
+                      f"-k {wl['k']} -f {f} -q {wl['q']} -t {cores}, wall {dt:.2f} s incl. FASTA parsing",
             "parity_on_sample": bool(O.canon_equal(bytes(ours), ref_img))}
 
 
@@ -155,6 +177,16 @@ class Runner:
         dg.attach(s)
         self.last, self.out = tdist.sharded_run(s, dg, self.rank, self.world, self.out)
 
+    def digest(self):
+        """Digest of the whole image = sum over ranks of the digests of the slices they hold (device-side)."""
+        torch, api = self.torch, self.api
+        d = api.image_digest_device(self.out.ptr, self.last["slice_bytes"], self.last["slice_offset"])
+        if self.world > 1:
+            t = torch.tensor([x - (1 << 64) if x >= (1 << 63) else x for x in d], dtype=torch.int64, device="cuda")
+            torch.distributed.all_reduce(t)                      # int64 sums wrap mod 2^64, as the digest does
+            d = tuple(int(x) & (2**64 - 1) for x in t.tolist())
+        return [f"{d[0]:016x}", f"{d[1]:016x}"]
+
 
 def main() -> None:
     ap = argparse.ArgumentParser()
@@ -167,6 +199,10 @@ def main() -> None:
     ap.add_argument("--sim-world", type=int, default=0,
                     help="kernel tuning aid: time only pass 1+2 of shard 0 of N on ONE GPU (not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the untimed direct-path step whose image digest is compared")
+    ap.add_argument("--no-probe", action="store_true", help="skip the roofline probes")
+    ap.add_argument("--filter-mode", default=os.environ.get("TPC_FILTER_MODE", "auto"), choices=["auto", "direct", "binned"],
+                    help="filter passes of the timed steps (default: the session's own choice)")
     ap.add_argument("--rounds", type=int, default=0, help="-r of the run (default: the workload's, 1)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -182,23 +218,28 @@ def main() -> None:
         return
 
     import torch
+    from tools import benchutil
     from twopaco_b200 import api
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.filter_mode != "auto":
+        os.environ["TPC_FILTER_MODE"] = args.filter_mode
+    else:
+        os.environ.pop("TPC_FILTER_MODE", None)
 
-    probe = {}
-    if rank == 0 and not args.sim_world:   # random-access roofline probe while HBM is still empty
+    probe, slice_probe = {}, {}
+    if rank == 0 and not args.sim_world and not args.no_probe:   # roofline probes while HBM is still empty
         for mode, name in ((0, "load32B"), (2, "load_condAtomicOr")):
-            probe[name] = round(api.random_access_probe(wl["f"], mode, 1 << 30) / 1e9, 2)
-    total_bp = wl["genomes"] * wl["records"] * wl["length"]
-    dg = api.synth_family_device(wl["seed"], wl["genomes"], wl["records"], wl["length"], wl["p"], keep_ascii=(rank == 0))
+            probe[name] = round(benchutil.random_access_probe(wl["f"], mode, 1 << 30) / 1e9, 2)
+        slice_log2 = int(os.environ.get("TPC_SLICE_LOG2", "26"))
+        for mode, name in ((1, "query"), (2, "fill")):
+            # best over the launch shapes the apply kernels may use; 7-fold duplicated k-mers as in the workload
+            slice_probe[name] = round(max(benchutil.slice_probe(slice_log2, 6, 32 << 20, wl["genomes"], mode, U, c)
+                                          for U, c in ((4, 4), (8, 2), (4, 8))) / 1e9, 2)
+    dg = benchutil.synth_family_device(wl["seed"], wl["genomes"], wl["records"], wl["length"], wl["p"], keep_ascii=False)
     total_bp = dg.total_bp
-    sample = sample_records(dg, wl) if rank == 0 else None   # bounded sample for the reference arm / parity check
-    if dg.ascii is not None:                                  # the 1 byte/bp generator output is not an input of the path
-        dg.ascii.close()
-        dg.ascii = None
 
     if args.sim_world:
         for i in range(args.warmup + args.steps):
@@ -208,8 +249,8 @@ def main() -> None:
             st = s.stats()
             s.close()
         print(json.dumps({"sim_world": args.sim_world, "workload": args.workload,
-                          "stages_ms": {k: round(getattr(st, k), 3) for k in ("ms_bin", "ms_bin_overlapped", "ms_fill", "ms_query", "ms_insert", "ms_classify")},
-                          "bin_waves": st.bin_waves, "marks": st.candidate_marks, "candidate_kmers": st.candidate_kmers}))
+                          "stages_ms": {k: round(getattr(st, k), 3) for k in ("ms_bin", "ms_bin_overlapped", "ms_fill", "ms_query", "ms_insert", "ms_classify", "ms_wall_candidates")},
+                          "bin_waves": st.bin_waves, "sub_rounds": st.sub_rounds, "marks": st.candidate_marks, "candidate_kmers": st.candidate_kmers}))
         return
 
     runner = Runner(wl, dg, rank, world)
@@ -223,7 +264,9 @@ def main() -> None:
         runner.step()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms = {k: 0.0 for k in ("ms_bin", "ms_bin_overlapped", "ms_fill", "ms_query", "ms_insert", "ms_classify", "ms_index", "ms_emit")}
+    stage_keys = ("ms_bin", "ms_bin_overlapped", "ms_fill", "ms_query", "ms_insert", "ms_classify", "ms_index", "ms_emit")
+    wall_keys = ("ms_wall_candidates", "ms_wall_index", "ms_wall_emit")
+    stage_ms = {k: 0.0 for k in stage_keys + wall_keys}
     launches = 0
     with ClockSampler(local_rank) as clocks:
         ev0.record()
@@ -242,14 +285,32 @@ def main() -> None:
         ms = float(t.item())
     ms_per_step = ms / args.steps
     st = runner.session.stats()
+    digest = runner.digest()
+    timed_result = dict(runner.last)
+
+    # ---- parity of the timed code path (untimed): one more step through the DIRECT filter kernels (k_fill / k_query:
+    # no binning, no sub-round pipeline, no L2-resident slices) must produce the same image, byte for byte
+    verify = None
+    if not args.no_verify and st.bin_waves:
+        os.environ["TPC_FILTER_MODE"] = "direct"
+        runner.step()
+        st_d = runner.session.stats()
+        d_direct = runner.digest()
+        verify = {"direct_path_digest": d_direct, "binned_equals_direct": d_direct == digest and st_d.bin_waves == 0,
+                  "direct_ms": {k: round(getattr(st_d, k), 3) for k in ("ms_fill", "ms_query")}}
+        if args.filter_mode != "auto":
+            os.environ["TPC_FILTER_MODE"] = args.filter_mode
+        else:
+            os.environ.pop("TPC_FILTER_MODE", None)
+    gold = golden_digest(args.workload) if wl.get("rounds", 1) >= 1 else None
 
     # ---- roofline of the dominant filter-pass kernel ---------------------------
     # algorithmic HBM bytes, summed over the kernel's launches of one step:
     #   direct : k_fill  = 32 B (one filter sector) x owned k-mers + 0.375 B x positions (packed stream)
     #            k_query = the same + 1 bit/position of candidate mask
-    #   binned : k_bin         = 0.375 B x positions + 12 B x records written        (per binning pass)
-    #            k_apply_fill  = 8 B x records read + filter read once and written back once per wave
-    #            k_apply_query = 8 B x records + 8 B x marks (position word + mask word) + filter read per wave
+    #   binned : binning       = 0.375 B x positions (+ planes) per pass + 12 B x records written
+    #            k_apply_fill  = 8 B x records read + the filter read once and written back once per (sub-)round
+    #            k_apply_query = 8 B x records + 8 B x marks (position word + mask word) + the filter read once per (sub-)round
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -259,10 +320,11 @@ def main() -> None:
     positions, recs, marks = st.positions, total_bp / world, st.candidate_marks
     filter_bytes = (1 << wl["f"]) / 8
     per = {k: v / args.steps for k, v in stage_ms.items()}
+    rounds_local = wl.get("rounds", 1) * max(st.sub_rounds, 1)              # hash sub-ranges this GPU runs in sequence
     if st.bin_waves:
         waves = st.bin_waves
         passes = 1 if waves == 1 else 2
-        rounds_local = wl.get("rounds", 1) * max(st.sub_rounds, 1)          # hash sub-ranges this GPU runs in sequence
+        filter_sweeps = waves * rounds_local                                 # every (sub-)round has the whole filter to itself
         if rounds_local * world > 1:
             # sharded binning: ONE ownership scan (k_own: stream in, P bit planes out) + per round a k_bin_list pass
             # (stream + planes in, 12 B per owned record out)
@@ -273,48 +335,60 @@ def main() -> None:
         # pipelined rounds: the binning of round r+1 runs beside the fill of round r (ms_bin_overlapped, CUDA events on
         # its own stream); the binning kernels' time is the sum, the step only pays ms_bin for them
         kernels = {"k_bin": (per["ms_bin"] + per["ms_bin_overlapped"], bin_bytes),
-                   "k_apply_fill": (per["ms_fill"], 8.0 * recs + 2.0 * filter_bytes * waves),
-                   "k_apply_query": (per["ms_query"], 8.0 * recs + 8.0 * marks + filter_bytes * waves)}
+                   "k_apply_fill": (per["ms_fill"], 8.0 * recs + 2.0 * filter_bytes * filter_sweeps),
+                   "k_apply_query": (per["ms_query"], 8.0 * recs + 8.0 * marks + filter_bytes * filter_sweeps)}
     else:
-        kernels = {"k_fill": (per["ms_fill"], 32.0 * recs + 0.375 * positions),
-                   "k_query": (per["ms_query"], 32.0 * recs + 0.5 * positions)}
+        kernels = {"k_fill": (per["ms_fill"], 32.0 * recs + 0.375 * positions * rounds_local),
+                   "k_query": (per["ms_query"], 32.0 * recs + 0.5 * positions * rounds_local)}
     dom = max(kernels, key=lambda k: kernels[k][0])
     dom_ms, dom_bytes = kernels[dom]
     gbps = lambda ms, nbytes: round(nbytes / (ms * 1e-3) / 1e9, 1) if ms > 0 else None
     achieved = gbps(dom_ms, dom_bytes) or 0.0
-    # DRAM traffic of that kernel: measured once per round with `ncu --set full` on the C2 workload
-    # (profiles/r*_traffic_c2.json: dram__bytes_read.sum + dram__bytes_write.sum per launch); reported here as
-    # measured-traffic/algorithmic-bytes ratio of that capture x this run's algorithmic bytes.
+    # DRAM traffic of that kernel: `ncu --set full` capture of this workload when one is committed
+    # (profiles/r*_traffic_<workload>.json: dram__bytes_read.sum + dram__bytes_write.sum over the kernel's launches of a
+    # step), else the measured-traffic / algorithmic-bytes ratio of the C2 capture x this run's algorithmic bytes
     traffic, traffic_src = None, None
-    for f in sorted((ROOT / "profiles").glob("r*_traffic_c2.json"), reverse=True):
-        ratio = json.loads(f.read_text())["kernels"].get(dom, {}).get("traffic_over_algorithmic")
-        if ratio:
-            traffic, traffic_src = ratio * dom_bytes, f"{f.name}: ncu DRAM bytes / algorithmic bytes = {ratio} (C2 capture), scaled to this workload"
-        break
+    for pattern, scaled in ((f"r*_traffic_{args.workload}.json", False), ("r*_traffic_c2.json", True)):
+        for f in sorted((ROOT / "profiles").glob(pattern), reverse=True):
+            entry = json.loads(f.read_text())["kernels"].get(dom, {})
+            if not scaled and entry.get("dram_bytes_per_step") and entry.get("n_gpus", 1) == world:
+                traffic, traffic_src = entry["dram_bytes_per_step"], f"{f.name}: ncu dram__bytes_read.sum + dram__bytes_write.sum over the launches of one step"
+            elif scaled and entry.get("traffic_over_algorithmic"):
+                ratio = entry["traffic_over_algorithmic"]
+                traffic, traffic_src = ratio * dom_bytes, f"{f.name}: ncu DRAM bytes / algorithmic bytes = {ratio} (C2 capture), scaled to this workload"
+            break
+        if traffic:
+            break
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "peak_source": "measured" if peaks else "fallback", "traffic": traffic,
                 "traffic_source": traffic_src,
                 "algorithmic_bytes_per_step": dom_bytes, "ms_per_step": round(dom_ms, 3),
                 "filter_path": "binned (L2-resident slices)" if st.bin_waves else "direct (random HBM sectors)",
-                "filter_touches_per_s_G": {k: round(recs / (v[0] * 1e-3) / 1e9, 2) for k, v in kernels.items()
-                                            if v[0] > 0 and k != "k_bin"},
-                "all_filter_kernels": {k: {"ms": round(v[0], 3), "GBps": gbps(*v)} for k, v in kernels.items()}}
+                "all_filter_kernels": {k: {"ms": round(v[0], 3), "GBps": gbps(*v), "frac_of_hbm_peak": round((gbps(*v) or 0) / peak, 4)}
+                                       for k, v in kernels.items()}}
     if per.get("ms_bin_overlapped", 0) > 0:
-        roofline["overlap"] = ("pipelined rounds: k_bin_list of round r+1 (3 CTAs/SM) runs beside k_apply_fill of round r (1 CTA/SM) on two "
-                               "streams; k_bin's time is ms_bin + ms_bin_overlapped, the fill's time is what it takes while sharing the SMs")
+        roofline["overlap"] = ("pipelined rounds: the binning of round r+1 runs beside the fill of round r on a second stream; "
+                               "k_bin's time is ms_bin + ms_bin_overlapped, the fill's time is what it takes while sharing the SMs")
+    touches = {k: round(recs / (v[0] * 1e-3) / 1e9, 2) for k, v in kernels.items() if v[0] > 0 and k != "k_bin"}
+    if st.bin_waves:
+        # the binned apply kernels touch one random 32-byte sector per record INSIDE an L2-resident slice: their bound is
+        # the probe of exactly that pattern (tpcb_slice_probe), not a random-HBM probe
+        roofline["l2_random"] = {
+            "unit": "G sector touches/s", "slice_bytes": 1 << int(os.environ.get("TPC_SLICE_LOG2", "26")),
+            "probe": slice_probe, "achieved": {k: touches.get(k) for k in ("k_apply_fill", "k_apply_query")},
+            "frac": {k: (round(touches[k] / slice_probe[n], 3) if touches.get(k) and slice_probe.get(n) else None)
+                     for k, n in (("k_apply_fill", "fill"), ("k_apply_query", "query"))},
+            "note": "probe = random 256-bit sector loads (+ the fill's conditional atomicOr) inside one slice with the 8-byte record "
+                    "stream read beside it, best launch shape; pipelined rounds: the fill shares the SMs with the binning kernel"}
+        roofline["hbm_random"] = {"probe_Gtouch_s": probe, "note": "bound of the DIRECT kernels only (bench.py --filter-mode direct)"}
+    else:
+        roofline["hbm_random"] = {
+            "unit": "G sector touches/s", "table_bits": wl["f"], "probe_Gtouch_s": probe, "achieved": touches,
+            "frac": {"k_fill": round(touches["k_fill"] / probe["load_condAtomicOr"], 3) if probe.get("load_condAtomicOr") and touches.get("k_fill") else None,
+                     "k_query": round(touches["k_query"] / probe["load32B"], 3) if probe.get("load32B") and touches.get("k_query") else None},
+            "note": "one random 32-byte sector per owned k-mer and pass; probe = k_probe (uniform random sectors of a 2^f-bit table)"}
 
-    # the north-star's second roofline: uniform random 32-byte sector touches into a table of the filter's size
-    # (k_probe, measured in this run before the workload was generated).  The binned path does not touch HBM at
-    # random any more, so its effective rate (2 touches per owned k-mer over binning + fill + query) may exceed it.
-    t_filter = sum(per[k] for k in ("ms_bin", "ms_fill", "ms_query")) * 1e-3
-    eff = 2.0 * recs / t_filter / 1e9 if t_filter > 0 else None
-    roofline["random_access"] = {
-        "probe_Gtouch_s": probe, "unit": "G sector touches/s", "table_bits": wl["f"],
-        "achieved_Gtouch_s": round(eff, 2) if eff else None,
-        "frac": round(eff / probe["load_condAtomicOr"], 3) if eff and probe.get("load_condAtomicOr") else None,
-        "note": "achieved = (1 fill + 1 query touch per owned k-mer) / (ms_bin + ms_fill + ms_query); "
-                "frac is against the probe's load+conditional-atomicOr rate"}
-
+    timed_stage_sum = sum(v for k, v in stage_ms.items() if k in stage_keys and k != "ms_bin_overlapped") / args.steps
     result = {
         "metric": "input Gbp/s to exact junction set", "value": round(total_bp / (ms_per_step * 1e-3) / 1e9, 4), "unit": "Gbp/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
@@ -323,11 +397,15 @@ def main() -> None:
                    "parallelism": f"hash-range shards x{world}" if world > 1 else "single GPU",
                    "l2_hygiene": "inputs (packed genome + 2^f-bit filter) are far larger than the 126 MB L2"},
         "stages_ms": {k: round(v / args.steps, 3) for k, v in stage_ms.items()},
-        "untimed_ms": round(ms_per_step - sum(v for k, v in stage_ms.items() if k != "ms_bin_overlapped") / args.steps, 3),
-        "result": {**runner.last, "candidate_marks": st.candidate_marks, "candidate_kmers": st.candidate_kmers,
-                   "counts_match_round1": (None if args.workload not in EXPECTED_COUNTS else
-                                           (runner.last.get("junctions"), runner.last.get("records"), runner.last.get("stubs"))
-                                           == EXPECTED_COUNTS[args.workload])},
+        "untimed_ms": round(ms_per_step - timed_stage_sum, 3),
+        "sub_rounds": st.sub_rounds,
+        "result": {**timed_result, "candidate_marks": st.candidate_marks, "candidate_kmers": st.candidate_kmers,
+                   "image_digest": digest, "verify": verify,
+                   "golden": (None if not gold else
+                              {"digest_matches": gold.get("digest") == digest,
+                               "counts_match": [gold.get("junctions"), gold.get("records"), gold.get("stubs")]
+                                               == [timed_result.get("junctions"), timed_result.get("records"), timed_result.get("stubs")],
+                               "provenance": gold.get("provenance")})},
         "gpu_launches": launches, "roofline": roofline,
     }
     if rank == 0:
@@ -341,7 +419,7 @@ def main() -> None:
         nmask = torch.from_numpy(host.n_mask.view(np.int64)).pin_memory()
         pinned = api.PackedGenome(codes.numpy().view(np.uint64), nmask.numpy().view(np.uint64), host.n_positions,
                                   host.rec_start, host.rec_len)
-        out = torch.empty(runner.last["image_bytes"] + 4096, dtype=torch.uint8).pin_memory()
+        out = torch.empty(timed_result["image_bytes"] + 4096, dtype=torch.uint8).pin_memory()
         out_np = out.numpy()
         times = []
         for i in range(1 + max(1, min(args.steps, 3))):
@@ -352,10 +430,12 @@ def main() -> None:
             if i:
                 times.append(time.perf_counter() - t0)
         e2e_s = float(np.mean(times))
+        d_host = api.image_digest_host(img)
         result["e2e"] = {"value": round(total_bp / e2e_s / 1e9, 4), "unit": "Gbp/s",
                          "h2d_bytes_per_step": int(pinned.codes.nbytes + pinned.n_mask.nbytes),
                          "d2h_bytes_per_step": int(len(img)), "ms_per_step": round(e2e_s * 1e3, 3),
-                         "api": "tpc_junctions_host (pinned host genome -> pinned host de_bruijn.bin image)"}
+                         "api": "tpc_junctions_host (pinned host genome -> pinned host de_bruijn.bin image)",
+                         "image_digest_equals_device_run": [f"{d_host[0]:016x}", f"{d_host[1]:016x}"] == digest}
     elif not args.no_e2e:
         # N GPUs, host buffers in / host buffers out (twopaco_b200.dist.sharded_run_host): every rank uploads
         # 1/N of the packed genome from pinned host memory, chunk by chunk, NCCL all-gathers the chunks over
@@ -378,6 +458,10 @@ def main() -> None:
             barrier()
             if i:
                 times.append(time.perf_counter() - t0)
+        d_host = api.image_digest_host(out_host[:info["slice_bytes"]].numpy(), info["slice_offset"])
+        dt = torch.tensor([x - (1 << 64) if x >= (1 << 63) else x for x in d_host], dtype=torch.int64, device="cuda")
+        torch.distributed.all_reduce(dt)
+        d_all = [f"{int(x) & (2**64 - 1):016x}" for x in dt.tolist()]
         t = torch.tensor([float(np.mean(times)), float(shard.nbytes), float(info["slice_bytes"])], dtype=torch.float64, device="cuda")
         tmax = t.clone()
         torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
@@ -388,10 +472,11 @@ def main() -> None:
                          "ms_per_step": round(e2e_s * 1e3, 3),
                          "api": "twopaco_b200.dist.sharded_run_host (each rank: pinned 1/N of the packed genome -> NCCL all-gather -> "
                                 "shard run -> its slice of the de_bruijn.bin image in pinned host memory)",
-                         "junctions": info["junctions"], "records": info["records"]}
+                         "junctions": info["junctions"], "records": info["records"],
+                         "image_digest_equals_device_run": d_all == digest}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        result["cpu_baseline"] = cpu_baseline(sample, wl)
+        result["cpu_baseline"] = cpu_baseline(sample_records(wl), wl)
     if rank == 0:
         print(json.dumps(result))
     if world > 1:
@@ -399,31 +484,32 @@ def main() -> None:
 
 
 def reference_arm(args, wl, world) -> None:
-    """--impl reference: the unmodified reference CPU implementation on a bounded sample of the
-    same workload (rank 0 only), all host cores."""
+    """--impl reference: the unmodified reference CPU implementation (oracle/_ref/twopaco, all host cores) on a bounded
+    sample of the same workload, rank 0 only.  The sample comes from the numpy restatement of the generator: this arm
+    needs no GPU and loads none of this repository's libraries."""
     from oracle import oracle as O
-    from twopaco_b200 import api
     if not O.have_reference():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/twopaco was not built (no /root/reference at build time)"}))
         return
     cores = os.cpu_count() or 1
-    dg = api.synth_family_device(wl["seed"], wl["genomes"], wl["records"], min(wl["length"], wl["sample_bp"] * 2), wl["p"])
-    recs = sample_records(dg, wl)
+    recs = sample_records(wl)
     bp = sum(len(r) for r in recs)
+    f = reference_filter_bits(wl)
     times = []
     for i in range(args.warmup + args.steps):
-        _, dt = run_reference_on(recs, wl, cores)
+        _, dt = run_reference_on(recs, wl, cores, f)
         if i >= args.warmup:
             times.append(dt)
     ms = float(np.mean(times)) * 1e3
     v = bp / (ms * 1e-3) / 1e9
-    sample = (f"first {wl['sample_bp']} bp of record 0 of each of the {wl['genomes']} genomes ({bp} bp), "
-              f"-t {cores}, wall incl. FASTA parsing")
+    total_bp = wl["genomes"] * wl["records"] * wl["length"]
+    sample = (f"first {wl['sample_bp']} bp of record 0 of each of the {wl['genomes']} genomes ({bp} bp of the workload's ~{total_bp} bp), "
+              f"-k {wl['k']} -f {f} -q {wl['q']} -t {cores}, wall incl. FASTA parsing; Gbp/s of the sample, i.e. a linear extrapolation to the workload")
     print(json.dumps({
         "impl": "reference", "metric": "input Gbp/s to exact junction set", "value": round(v, 6), "unit": "Gbp/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": wl["name"], "k": wl["k"], "filter_bits": min(wl["f"], 32), "q": wl["q"]},
+        "config": {"workload": wl["name"], "k": wl["k"], "filter_bits": wl["f"], "q": wl["q"], "reference_filter_bits": f},
         "cpu_baseline": {"value": round(v, 6), "unit": "Gbp/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": round(v, 6), "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TPC_ABI_VERSION 2
+#define TPC_ABI_VERSION 3
 #define TPC_INVALID_VERTEX INT64_MAX          /* src/graphconstructor/common.cpp:5 */
 #define TPC_SEPARATOR_POS 0xFFFFFFFFu         /* src/common/junctionapi.h:36-37 */
 #define TPC_MAX_K 127                         /* 4 x 64-bit words per packed k-mer in this build
@@ -69,6 +69,9 @@ typedef struct tpc_stats {
                                     fit HBM in one wave (1 = none); unobservable in the output    */
     float ms_bin_overlapped;     /* pipelined rounds: binning of round r+1 that ran beside the fill of round r
                                     (not part of ms_bin / ms_total) */
+    float ms_wall_candidates;    /* host wall clock of tpc_session_find_candidates (kernels + memsets + allocations +
+                                    host synchronisations), so that time outside the CUDA-event stage times is visible */
+    float ms_wall_index, ms_wall_emit;   /* the same for set_junctions and emit_count + emit_write */
 } tpc_stats;
 
 /* ------------------------------------------------------------------------------------------
@@ -209,11 +212,6 @@ int tpc_session_emit_write(tpc_session *s, uint64_t records_before, uint64_t stu
 int tpc_session_get_id(tpc_session *s, const char *kmer, int64_t *id);
 int tpc_session_stats(tpc_session *s, tpc_stats *out);   /* synchronises the stream */
 
-/* Random-access roofline probe: uniform random 32-byte sector touches into a
- * 2^filter_bits-bit table on the current device. mode 0 = 32-byte loads, 1 = 4-byte atomicOr,
- * 2 = load + conditional atomicOr (the fill pattern).  Returns sector touches per second. */
-int tpc_random_access_probe(uint32_t filter_bits, uint32_t mode, uint64_t touches, double *touches_per_s);
-
 /* ------------------------------------------------------------------------------------------
  * K0: ASCII -> 2-bit codes + N mask on the device.  dev_ascii holds one byte per position in
  * the layout of tpc_genome ('N' or any non-ACGT byte at separators; case folded; the alphabet
@@ -223,15 +221,14 @@ int tpc_random_access_probe(uint32_t filter_bits, uint32_t mode, uint64_t touche
 int tpc_pack_ascii_device(const uint8_t *dev_ascii, uint64_t n_positions, uint64_t *dev_codes,
                           uint64_t *dev_nmask, void *stream);
 
-/* Synthetic founder-family genome set generated ON the device: genome 0 is an
- * i.i.d. uniform founder of records_per_genome x record_len bases; every other genome mutates
- * each founder base with probability p (80 % SNP, 10 % 1-bp insertion, 10 % 1-bp deletion).
- * Records are ordered genome-major.  Returns a device ASCII buffer in the tpc_genome layout
- * (release with tpc_device_free) and fills the HOST arrays rec_start / rec_len
- * (genomes * records_per_genome entries each). */
-int tpc_synth_family_device(uint64_t seed, uint32_t genomes, uint32_t records_per_genome,
-                            uint64_t record_len, double p, uint8_t **dev_ascii,
-                            uint64_t *n_positions, uint64_t *rec_start, uint64_t *rec_len);
+/* Position-keyed digest of (a slice of) a de_bruijn.bin image in device memory: two 64-bit sums over the
+ * image's 32-bit words of mix(global word index, word).  The digests of disjoint slices of one image add up
+ * (mod 2^64) to the digest of the whole image, so N GPUs that each hold a slice (tpc_session_emit_write:
+ * image_offset / image_bytes) can prove byte-identity with a single-GPU run without gathering the image.
+ * nbytes and image_offset are multiples of 4.  Synchronises `stream`. */
+int tpc_image_digest_device(const uint8_t *dev_image, uint64_t nbytes, uint64_t image_offset, void *stream,
+                            uint64_t digest[2]);
+
 int tpc_device_alloc(uint64_t bytes, void **out);
 void tpc_device_free(void *p);
 int tpc_copy_to_host(void *host_dst, const void *dev_src, uint64_t bytes);

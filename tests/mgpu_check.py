@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Multi-GPU parity check, run under torchrun on a box with >= 2 GPUs:
+"""Multi-GPU parity check, run under torchrun on a box with >= 2 GPUs (or, with TPC_MGPU_BACKEND=gloo, with several
+ranks sharing one GPU and exchanging over gloo):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tests/mgpu_check.py
 
@@ -24,8 +25,13 @@ from twopaco_b200 import dist as tdist  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    backend = os.environ.get("TPC_MGPU_BACKEND", "nccl")
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:   # ranks share the GPUs there are (one-GPU box: all on cuda:0) and exchange over gloo
+        torch.cuda.set_device(local % torch.cuda.device_count())
+        dist.init_process_group("gloo")
     cases = [dict(k=25, f=24, recs=synth.founder_family(91, 6, 3, 60_000, 0.01, n_runs=2) + [b"ACG", b""]),
              dict(k=63, f=22, recs=synth.founder_family(92, 4, 2, 50_000, 0.02, n_runs=1)),
              dict(k=9, f=20, recs=synth.reference_selftest_set(93))]

@@ -10,6 +10,7 @@ import pytest
 from oracle import oracle as O
 from tests.cases import CASES
 from tests.util import canon_md5, case_files, oracle_on_paths
+from tools import benchutil
 from twopaco_b200 import api, synth
 
 pytestmark = pytest.mark.gpu
@@ -237,8 +238,8 @@ def test_k0_pack_ascii_device_matches_host_packer():
 
 def test_synth_family_device_generator():
     """On-device founder-family generator: deterministic, right shape, right divergence."""
-    a = api.synth_family_device(0x4855, 4, 3, 200_000, 0.01)
-    b = api.synth_family_device(0x4855, 4, 3, 200_000, 0.01)
+    a = benchutil.synth_family_device(0x4855, 4, 3, 200_000, 0.01)
+    b = benchutil.synth_family_device(0x4855, 4, 3, 200_000, 0.01)
     assert a.n_positions == b.n_positions and np.array_equal(a.codes.to_host(), b.codes.to_host())
     assert len(a.rec_len) == 12 and np.all(a.rec_len[:3] == 200_000)
     assert int(a.rec_start[0]) == 1 and a.n_positions == 1 + int((a.rec_len + 1).sum())
@@ -461,20 +462,105 @@ def test_genome_events_are_validated():
     s.close()
 
 
-def test_multi_gpu_torchrun():
-    """N > 1: hash-range shards over NCCL (skipped on single-GPU boxes)."""
+def _run_mgpu_check(nproc: int, port: int, backend: str):
     import subprocess
     import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "mgpu_check.py")],
+                       capture_output=True, text=True, timeout=900, env={**os.environ, "TPC_MGPU_BACKEND": backend})
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("mgpu ok") == 6 and r.stdout.count("mgpu host-buffer ok") == 6, r.stdout[-3000:]
+
+
+def test_multi_gpu_torchrun():
+    """N > 1: hash-range shards over NCCL (skipped on single-GPU boxes)."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "mgpu_check.py")],
-                       capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("mgpu ok") == 6
+    _run_mgpu_check(min(n, 4), 29533, "nccl")
+
+
+def test_multi_rank_run_on_one_gpu_over_gloo():
+    """The SAME multi-rank code (twopaco_b200.dist.sharded_run / sharded_run_host under torchrun: hash-range shards,
+    all-gather of the junction words, OR-reduce of the candidate masks, position-sharded emit, chunked host upload +
+    all-gather of the genome) with 3 ranks that share ONE GPU and exchange over gloo -- NCCL needs one GPU per rank,
+    the exchanged bytes are the same.  Device-resident and host-buffer entry points, direct and binned filter passes,
+    k = 9 / 25 / 63, byte-identical to the oracle."""
+    _run_mgpu_check(3, 29534, "gloo")
+
+
+def test_image_digest_device_matches_host_and_adds_over_slices():
+    """tpc_image_digest_device: equal to the numpy restatement, and the digests of disjoint slices add up to the digest of
+    the whole image (what lets N GPUs prove byte-identity with one GPU without gathering the image)."""
+    import torch
+    recs = synth.founder_family(5150, 6, 2, 60_000, 0.01, n_runs=2)
+    img, _ = api.junctions_host(api.pack_records(recs), k=25, filter_bits=24)
+    img = bytes(img)
+    dev = torch.frombuffer(bytearray(img), dtype=torch.uint8).cuda()
+    whole = api.image_digest_device(dev.data_ptr(), len(img), 0)
+    assert whole == api.image_digest_host(img)
+    cut = (len(img) // 36) * 12
+    parts = [api.image_digest_device(dev.data_ptr(), cut, 0), api.image_digest_device(dev.data_ptr() + cut, len(img) - cut, cut)]
+    assert api.add_digests(*parts) == whole
+    assert api.image_digest_device(dev.data_ptr(), 0, 0) == (0, 0)
+    flipped = bytearray(img)
+    flipped[len(img) // 2] ^= 1
+    assert api.image_digest_host(bytes(flipped)) != whole
+    swapped = img[12:24] + img[:12] + img[24:]
+    assert swapped == img or api.image_digest_host(swapped) != whole
+
+
+def test_host_generator_matches_device_generator():
+    """tools/benchutil/hostsynth.py (the sample source of `bench.py --impl reference`) == the on-device generator."""
+    from tools.benchutil import hostsynth
+    dg = benchutil.synth_family_device(0x4855, 3, 2, 300_000, 0.01)
+    for g, c in ((0, 0), (1, 0), (2, 1)):
+        want = dg.record_ascii(g * 2 + c, 120_000)
+        assert hostsynth.record_prefix(0x4855, 2, 0.01, g, c, 120_000, 300_000) == want
+    full = dg.record_ascii(3)
+    assert hostsynth.record_prefix(0x4855, 2, 0.01, 1, 1, 10**9, 300_000) == full
+
+
+def test_headline_code_path_at_100mbp_against_the_live_reference(tmp_path, monkeypatch):
+    """The code path of the benchmark's headline number (C3 on one GPU: k_own with 3 ownership planes, five pipelined
+    sub-rounds of k_bin_list beside k_apply_fill, 64 MiB slices, merged exact pass) on 105 Mbp of the same kind of input
+    (7 genomes, 0.1 % divergence, k = 25), against the UNMODIFIED reference run here with all host cores (the C oracle when
+    the reference binary did not travel); then the direct kernels must give the same bytes."""
+    dg = benchutil.synth_family_device(0x4855, 7, 1, 15_000_000, 0.001)
+    recs = [dg.record_ascii(r) for r in range(7)]
+    host = dg.to_host()
+    monkeypatch.setenv("TPC_SUBROUNDS", "5")
+    monkeypatch.setenv("TPC_FILTER_MODE", "binned")
+    img, st = api.junctions_host(host, k=25, filter_bits=30, q=5)
+    assert st.sub_rounds == 5 and st.ms_bin_overlapped > 0 and st.bin_waves == 1, "not the pipelined sub-round path"
+    img = bytes(img)
+    if O.have_reference():
+        paths = []
+        for i, r in enumerate(recs):
+            p = str(tmp_path / f"g{i}.fa")
+            O.write_fasta(p, [r], names=[f"g{i}_c0"])
+            paths.append(p)
+        ref, _ = O.run_reference(paths, 25, 30, q=5, r=1, t=os.cpu_count() or 1)
+    else:
+        ref, _, _ = O.find_junctions(recs, 25)
+    assert len(img) == len(ref) and O.canon_equal(img, ref), "pipelined sub-round path differs from the reference"
+    monkeypatch.setenv("TPC_SUBROUNDS", "0")
+    monkeypatch.setenv("TPC_FILTER_MODE", "direct")
+    img_d, st_d = api.junctions_host(host, k=25, filter_bits=30, q=5)
+    assert st_d.bin_waves == 0 and bytes(img_d) == img
+    # sharded sessions (what GPUs 0 and 3 of 4 would run: k_own + one k_bin_list pass, no sub-rounds): junction counts add up
+    monkeypatch.setenv("TPC_FILTER_MODE", "binned")
+    total = 0
+    for i in range(4):
+        s = api.Session(k=25, filter_bits=30, shard_index=i, shard_count=4)
+        dg.attach(s)
+        s.find_candidates()
+        total += s.local_junctions()[1]
+        assert s.stats().bin_waves == 1
+        s.close()
+    assert total == st.junctions
 
 
 @pytest.mark.parametrize("name", ["family_k25", "selftest_s1_k9", "edge_mixed_k11", "family_k11_collisions"])

@@ -16,13 +16,14 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 from bench import WORKLOADS  # noqa: E402
 from oracle import oracle as O  # noqa: E402
+from tools import benchutil  # noqa: E402
 from twopaco_b200 import api  # noqa: E402
 
 
 def main():
     wl = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "c2"]
     cores = os.cpu_count() or 1
-    dg = api.synth_family_device(wl["seed"], wl["genomes"], wl["records"], wl["length"], wl["p"])
+    dg = benchutil.synth_family_device(wl["seed"], wl["genomes"], wl["records"], wl["length"], wl["p"])
     with tempfile.TemporaryDirectory(prefix="tpc_cli_") as d:
         paths = []
         for g in range(wl["genomes"]):

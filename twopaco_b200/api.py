@@ -37,7 +37,8 @@ class Stats(C.Structure):
                 ("ms_bin", C.c_float), ("ms_fill", C.c_float), ("ms_query", C.c_float), ("ms_insert", C.c_float), ("ms_classify", C.c_float),
                 ("ms_index", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float),
                 ("kernel_launches", C.c_uint32), ("bin_waves", C.c_uint32), ("sub_rounds", C.c_uint32),
-                ("ms_bin_overlapped", C.c_float)]
+                ("ms_bin_overlapped", C.c_float), ("ms_wall_candidates", C.c_float), ("ms_wall_index", C.c_float),
+                ("ms_wall_emit", C.c_float)]
 
     def asdict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -81,10 +82,8 @@ SIGNATURES = {
     "tpc_session_emit_write": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tpc_session_get_id": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "tpc_session_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
-    "tpc_random_access_probe": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_double)]),
     "tpc_pack_ascii_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "tpc_synth_family_device": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_double, C.POINTER(C.c_void_p),
-                                          C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]),
+    "tpc_image_digest_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64 * 2)]),
     "tpc_device_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
     "tpc_device_free": (None, [C.c_void_p]),
     "tpc_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -329,10 +328,34 @@ class Session:
             pass
 
 
-def random_access_probe(filter_bits: int, mode: int, touches: int = 1 << 30) -> float:
-    v = C.c_double()
-    _check(lib().tpc_random_access_probe(filter_bits, mode, touches, C.byref(v)))
-    return v.value
+def image_digest_device(dev_ptr: int, nbytes: int, image_offset: int = 0, stream: int = 0) -> tuple[int, int]:
+    """Position-keyed digest of an image slice in device memory (slices' digests add up mod 2^64)."""
+    d = (C.c_uint64 * 2)()
+    _check(lib().tpc_image_digest_device(C.c_void_p(dev_ptr), nbytes, image_offset, C.c_void_p(stream), C.byref(d)))
+    return int(d[0]), int(d[1])
+
+
+def _fmix64(x: np.ndarray) -> np.ndarray:
+    x = x ^ (x >> np.uint64(33)); x = x * np.uint64(0xff51afd7ed558ccd)
+    x = x ^ (x >> np.uint64(33)); x = x * np.uint64(0xc4ceb9fe1a85ec53)
+    return x ^ (x >> np.uint64(33))
+
+
+def image_digest_host(image, image_offset: int = 0) -> tuple[int, int]:
+    """The same digest computed with numpy from image bytes in host memory."""
+    w = np.frombuffer(bytes(image), dtype="<u4").astype(np.uint64)
+    a = b = 0
+    with np.errstate(over="ignore"):
+        for lo in range(0, len(w), 1 << 24):
+            part = w[lo:lo + (1 << 24)]
+            gi = np.arange(image_offset // 4 + lo + 1, image_offset // 4 + lo + 1 + len(part), dtype=np.uint64)
+            a = (a + int(_fmix64((gi * np.uint64(0x9E3779B97F4A7C15)) ^ part).sum(dtype=np.uint64))) & (2**64 - 1)
+            b = (b + int(_fmix64(gi * np.uint64(0xC2B2AE3D27D4EB4F) + part * np.uint64(0x165667B19E3779F9)).sum(dtype=np.uint64))) & (2**64 - 1)
+    return a, b
+
+
+def add_digests(*ds: tuple[int, int]) -> tuple[int, int]:
+    return (sum(d[0] for d in ds) & (2**64 - 1), sum(d[1] for d in ds) & (2**64 - 1))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -412,20 +435,6 @@ def pack_ascii_device(ascii_buf: DeviceBuffer, n_positions: int, rec_start: np.n
     if not keep_ascii:
         ascii_buf.close()
     return g
-
-
-def synth_family_device(seed: int, genomes: int, records_per_genome: int, record_len: int, p: float,
-                        keep_ascii: bool = True) -> DeviceGenome:
-    """Founder-family genome set generated and packed on the device."""
-    L = lib()
-    n = genomes * records_per_genome
-    rec_start = np.empty(n, dtype=np.uint64)
-    rec_len = np.empty(n, dtype=np.uint64)
-    ptr, npos = C.c_void_p(), C.c_uint64()
-    _check(L.tpc_synth_family_device(seed, genomes, records_per_genome, record_len, p, C.byref(ptr), C.byref(npos),
-                                     rec_start.ctypes.data, rec_len.ctypes.data))
-    buf = DeviceBuffer.adopt(ptr.value, (npos.value + 63) // 64 * 64 + 64)
-    return pack_ascii_device(buf, npos.value, rec_start, rec_len, keep_ascii=keep_ascii)
 
 
 class _DevArray:

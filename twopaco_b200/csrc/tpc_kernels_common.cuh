@@ -17,21 +17,24 @@ __global__ void __launch_bounds__(256)
 k_classify(TableView T, uint64_t abundance, uint32_t use_abundance, unsigned long long* __restrict__ out,
            uint64_t out_cap, Counters* ctr) {
     uint64_t cap = 1ull << T.log2cap;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-        ulonglong2 v = *reinterpret_cast<const ulonglong2*>(T.slots + i);
+    const int lane = threadIdx.x & 31;
+    // whole warps iterate together (the bound is rounded up to a warp), so every shuffle below is full-mask
+    const uint64_t cap_w = (cap + 31) & ~31ull;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap_w; i += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2 v = make_ulonglong2(0ull, 0ull);
+        if (i < cap) v = *reinterpret_cast<const ulonglong2*>(T.slots + i);
         bool j = v.x != 0 && meta_is_junction(v.y);
         bool drop = j && use_abundance && (v.y >> kMetaCountShift) > abundance;
         if (drop) atomicAdd(&ctr->dropped, 1ull);
         bool take = j && !drop;
-        // warp-aggregated append
-        unsigned ballot = __ballot_sync(__activemask(), take);
+        // warp-aggregated append: one atomicAdd per warp, the base handed out by a full-mask shuffle
+        const unsigned ballot = __ballot_sync(0xffffffffu, take);
+        if (ballot == 0) continue;
+        const int leader = __ffs(ballot) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(&ctr->junctions, (unsigned long long)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, leader);
         if (take) {
-            unsigned act = __activemask();
-            int lane = threadIdx.x & 31;
-            int leader = __ffs(ballot) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(&ctr->junctions, (unsigned long long)__popc(ballot));
-            base = __shfl_sync(act, base, leader);
             unsigned long long at = base + __popc(ballot & ((1u << lane) - 1));
             if (at < out_cap) out[at] = T.inline_keys ? (v.y >> kInlinePosShift) : (v.x & kPosMask);
         }
@@ -85,33 +88,6 @@ k_scan_apply(unsigned long long* __restrict__ data, uint64_t n, const unsigned l
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// random-access roofline probe: uniform random sector touches
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_probe(uint32_t* __restrict__ table, uint32_t sector_bits, uint32_t mode, uint64_t per_thread, unsigned long long* sink) {
-    uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    uint64_t x = fmix64(tid + 0x1234567ull);
-    uint32_t acc = 0;
-    for (uint64_t i = 0; i < per_thread; ++i) {
-        x = x * 6364136223846793005ull + 1442695040888963407ull;
-        uint64_t h = fmix64(x);
-        uint32_t* sec = table + ((h >> (64 - sector_bits)) << 3);
-        if (mode == 0) {
-            Sector v = ld_sector_nc(sec);
-            acc += v.w[0] ^ v.w[1] ^ v.w[2] ^ v.w[3] ^ v.w[4] ^ v.w[5] ^ v.w[6] ^ v.w[7];
-        } else if (mode == 1) {
-            atomicOr(sec + (h & 7), 1u << ((h >> 3) & 31));
-        } else {
-            uint32_t m = 1u << ((h >> 3) & 31);
-            uint32_t cur = __ldcg(sec + (h & 7));
-            if ((cur & m) != m) atomicOr(sec + (h & 7), m);
-            acc += cur;
-        }
-    }
-    if (acc == 0x9e3779b9u) atomicAdd(sink, 1ull);
-}
-
 // ---- apply: one launch per slice; the slice stays in L2 ------------------------------------------
 // A thread takes kApplyU consecutive records per iteration: the record words come in as 128-bit
 // streaming loads, then all kApplyU sector loads (one 256-bit load each, random inside the
@@ -154,7 +130,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 struct ApplyStream {   // per-thread state of the record prefetcher
     const uint4* sd;
     const uint4* w1;
-    uint32_t next, nvec, gsize;
+    uint64_t next, nvec;            // 64-bit: a slice may hold more than 2^32 records (small -f, huge inputs)
+    uint32_t gsize;
     uint64_t policy;
     int slot;
     __device__ __forceinline__ void issue(ApplyRing& ring, int d) {
@@ -165,7 +142,7 @@ struct ApplyStream {   // per-thread state of the record prefetcher
         cp_async_commit();
         next += gsize;
     }
-    __device__ __forceinline__ void start(ApplyRing& ring, const uint32_t* rec, const uint32_t* rec_b, uint32_t gtid, uint32_t gs, uint32_t nv) {
+    __device__ __forceinline__ void start(ApplyRing& ring, const uint32_t* rec, const uint32_t* rec_b, uint32_t gtid, uint32_t gs, uint64_t nv) {
         sd = reinterpret_cast<const uint4*>(rec); w1 = reinterpret_cast<const uint4*>(rec_b);
         next = gtid; nvec = nv; gsize = gs; slot = 0;
         policy = l2_evict_first_policy();
@@ -191,15 +168,15 @@ k_apply_fill(uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, con
     __shared__ unsigned long long red[8];
     __shared__ ApplyRing ring;
     unsigned long long n64 = *count;
-    const uint32_t n = (uint32_t)(n64 > cap ? cap : n64);
+    const uint64_t n = n64 > cap ? cap : n64;
     const uint32_t* __restrict__ rec_b = rec + cap;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
     uint32_t fresh = 0;
-    const uint32_t nvec = n / kApplyU;
+    const uint64_t nvec = n / kApplyU;
     ApplyStream st;
     st.start(ring, rec, rec_b, gtid, gsize, nvec);
     prefetch_slice(slice, sib_mask + 1u, gtid, gsize);
-    for (uint32_t v = gtid; v < nvec; v += gsize) {
+    for (uint64_t v = gtid; v < nvec; v += gsize) {
         uint4 sd, w1;
         st.take(ring, sd, w1);
         uint32_t* sec[kApplyU];
@@ -215,7 +192,7 @@ k_apply_fill(uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, con
             fresh += fill_sector(sec[j], s[j], mask_from_seed<Q>(u4_get(sd, j)), u4_get(w1, j) >> kBinCodeShift);
     }
     cp_async_wait<0>();
-    for (uint32_t i = nvec * kApplyU + gtid; i < n; i += gsize) {
+    for (uint64_t i = nvec * kApplyU + gtid; i < n; i += gsize) {
         const uint32_t w1 = __ldcs(rec_b + i);
         fresh += fill_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), mask_from_seed<Q>(__ldcs(rec + i)), w1 >> kBinCodeShift);
     }
@@ -239,17 +216,17 @@ k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ r
     __shared__ unsigned long long red[8];
     __shared__ ApplyRing ring;
     unsigned long long n64 = *count;
-    const uint32_t n = (uint32_t)(n64 > cap ? cap : n64);
+    const uint64_t n = n64 > cap ? cap : n64;
     const uint32_t* __restrict__ rec_b = rec + cap;
     const uint32_t* __restrict__ rec_c = rec + 2 * cap;   // relative positions: read only for the (few) candidates
     const uint32_t sib_mask = (1u << sib_bits) - 1u;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
     uint32_t marks = 0;
-    const uint32_t nvec = n / kApplyU;
+    const uint64_t nvec = n / kApplyU;
     ApplyStream st;
     st.start(ring, rec, rec_b, gtid, gsize, nvec);
     prefetch_slice(slice, sib_mask + 1u, gtid, gsize);
-    for (uint32_t v = gtid; v < nvec; v += gsize) {
+    for (uint64_t v = gtid; v < nvec; v += gsize) {
         uint4 sd, w1;
         st.take(ring, sd, w1);
         Sector s[kApplyU];
@@ -260,13 +237,13 @@ k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ r
         for (int j = 0; j < kApplyU; ++j) {
             const uint32_t m = mask_from_seed<Q>(u4_get(sd, j));
             if (query_sector(s[j], m)) {
-                apply_mark(mask, hll, m, u4_get(w1, j), __ldcs(rec_c + (uint64_t)v * kApplyU + j), sib_bits, wave_base, slice_first_sector);
+                apply_mark(mask, hll, m, u4_get(w1, j), __ldcs(rec_c + v * kApplyU + j), sib_bits, wave_base, slice_first_sector);
                 ++marks;
             }
         }
     }
     cp_async_wait<0>();
-    for (uint32_t i = nvec * kApplyU + gtid; i < n; i += gsize) {
+    for (uint64_t i = nvec * kApplyU + gtid; i < n; i += gsize) {
         const uint32_t w1 = __ldcs(rec_b + i);
         const uint32_t m = mask_from_seed<Q>(__ldcs(rec + i));
         if (query_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), m)) {

@@ -57,11 +57,8 @@ template <int W, int R>
 static void launch_bin_list(const LaunchCtx& c, GenomeView g, KParams kp, const BinView& bv, uint64_t tile_begin, uint64_t tile_end,
                             uint64_t wave_base, const OwnPlanes& op) {
     constexpr size_t smem = bin_list_smem_bytes(R);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_bin_list<W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    // the attribute is per device (a process may hold sessions on several GPUs) and setting it is cheap
+    cudaFuncSetAttribute(k_bin_list<W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_list<W, R>, kTileThreads, smem);
     if (c.bin_ctas > 0 && per_sm > c.bin_ctas) per_sm = c.bin_ctas;
@@ -107,11 +104,7 @@ cudaError_t Launch<W>::bin(const LaunchCtx& c, GenomeView g, KParams kp, const B
         else if (force_r != 16) launch_bin_list<W, 8>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
         else launch_bin_list<W, 16>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
     } else {
-        static bool configured = false;
-        if (!configured) {
-            cudaFuncSetAttribute(k_bin<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinSmemBytes);
-            configured = true;
-        }
+        cudaFuncSetAttribute(k_bin<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinSmemBytes);
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin<W>, kTileThreads, kBinSmemBytes);
         uint64_t grid = std::min<uint64_t>((uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count, ntiles);

@@ -1,6 +1,7 @@
 // tpc_session.cu -- sessions (C ABI level 3), the packed-genome entry point (level 2) and the
 // W-independent kernels.  One session = one GPU = one hash-range shard.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -43,6 +44,45 @@ const char* last_error() { return g_error.c_str(); }
             return tpc::set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, \
                                   cudaGetErrorString(e_));                                         \
     } while (0)
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+// host wall clock of a scope, added to *acc on exit (also on the early returns of CK())
+struct WallTimer {
+    float* acc;
+    double t0;
+    explicit WallTimer(float* a) : acc(a), t0(now_ms()) {}
+    ~WallTimer() { *acc += (float)(now_ms() - t0); }
+};
+
+// RAII holders so that the early returns of CK() do not leak events / buffers
+struct Events {
+    std::vector<cudaEvent_t> e;
+    explicit Events(int n, unsigned flags = cudaEventDefault) : e(n, nullptr) {
+        for (auto& x : e) cudaEventCreateWithFlags(&x, flags);
+    }
+    ~Events() {
+        for (auto x : e)
+            if (x) cudaEventDestroy(x);
+    }
+    cudaEvent_t operator[](int i) const { return e[i]; }
+    Events(const Events&) = delete;
+    Events& operator=(const Events&) = delete;
+};
+struct DevBuf {   // stream-ordered device allocation released on scope exit
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    ~DevBuf() {
+        if (p) cudaFreeAsync(p, st);
+    }
+};
+struct PinnedBuf {
+    void* p = nullptr;
+    ~PinnedBuf() {
+        if (p) cudaFreeHost(p);
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // device memory: stream-ordered allocations from the device's default pool, which is told to keep
@@ -623,8 +663,8 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
     const BinView bv = s->bin_view;
     const uint32_t buckets = 1u << bv.bucket_bits;
     const uint64_t wave_tiles = s->bin_wave_tiles, nwaves = s->bin_nwaves;
-    cudaEvent_t e0, e1, e2;
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    Events evs(3);
+    cudaEvent_t e0 = evs[0], e1 = evs[1], e2 = evs[2];
     unsigned long long ov_total = 0, ov_now = 0;
     auto finish_wave = [&](float* a, float* b) -> int {
         CK(cudaMemcpyAsync(&ov_now, bv.ov_count, 8, cudaMemcpyDeviceToHost, s->stream));
@@ -679,7 +719,6 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
             rc = finish_wave(ms_bin, pass == 0 ? ms_fill : ms_query);
         }
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     if (rc) return rc;
     if (ov_total > bv.ov_cap) return -2;  // heavily skewed input: the caller redoes the round with k_fill / k_query
     s->used_binned = true;
@@ -718,8 +757,8 @@ static int filter_passes_pipelined(tpc_session* s, uint32_t r, const KParams& kp
     const uint32_t buckets = 1u << bv.bucket_bits;
     const bool has_next = r + 1 < s->rounds_eff;
     LaunchCtx lc = s->lctx();
-    cudaEvent_t e0, e1, e2, e3;
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    Events evs(4);
+    cudaEvent_t e0 = evs[0], e1 = evs[1], e2 = evs[2], e3 = evs[3];
     float t_bin_ahead = 0;
     CK(cudaEventRecord(e0, s->stream));
     if (s->pipe_round[h] != (long long)r) {   // first round of the call (or after a fallback): bin here, nothing to overlap with
@@ -760,7 +799,6 @@ static int filter_passes_pipelined(tpc_session* s, uint32_t r, const KParams& kp
     cudaEventElapsedTime(&t, e1, e2); *ms_fill += t;      // (overlapped with the next round's binning)
     cudaEventElapsedTime(&t, e2, e3); *ms_query += t;     // (includes waiting for that binning to end)
     if (has_next && cudaEventElapsedTime(&t_bin_ahead, s->pipe_ev[3], s->pipe_ev[4]) == cudaSuccess) s->st.ms_bin_overlapped += t_bin_ahead;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
     if (ov_now > bv.ov_cap) return -2;
     s->used_binned = true;
     s->st.bin_waves = 1;
@@ -791,9 +829,16 @@ int tpc_session_find_candidates(tpc_session* s) {
     s->local_count = 0;
     s->st = tpc_stats{};
     s->st.positions = s->g.npos;
+    WallTimer wall(&s->st.ms_wall_candidates);
+    const bool verbose = getenv("TPC_VERBOSE") != nullptr;
+    const double t_start = now_ms();
+    auto vlog = [&](const char* what, int round) {
+        if (verbose) fprintf(stderr, "[tpc find_candidates] +%9.3f ms  %s (round %d)\n", now_ms() - t_start, what, round);
+    };
     float ms_bin = 0, ms_fill = 0, ms_query = 0, ms_insert = 0, ms_classify = 0;
     Counters prev{}, cur{};
     CK(cudaStreamSynchronize(s->stream));  // the allocations above are visible to available_bytes()
+    vlog("buffers allocated, mask cleared", -1);
     s->sub_rounds = choose_sub_rounds(s);
     s->rounds_eff = s->prm.rounds * s->sub_rounds;
     s->st.sub_rounds = s->sub_rounds;
@@ -845,6 +890,7 @@ int tpc_session_find_candidates(tpc_session* s) {
         CK(cudaEventRecord(s->ev[2], s->stream));
         CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
+        vlog("filter passes done", (int)r);
         {
             float t;
             if (brc < 0) {
@@ -861,6 +907,7 @@ int tpc_session_find_candidates(tpc_session* s) {
         std::vector<uint32_t> hll(1u << kHllBits);
         CK(cudaMemcpyAsync(hll.data(), s->d_hll, 4u << kHllBits, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
+        vlog("sketch read", (int)r);
         double est = hll_estimate(hll);
         if (est > (double)marks_r) est = (double)marks_r;
         uint32_t lg = std::max<uint32_t>(ceil_log2((uint64_t)(est * 1.15 * 2.0) + 64), 10);
@@ -901,6 +948,7 @@ int tpc_session_find_candidates(tpc_session* s) {
             CK(cudaEventRecord(s->ev[3], s->stream));
             CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
             CK(cudaStreamSynchronize(s->stream));
+            vlog("insert done", (int)r);
             if (cur.overflow == prev.overflow && (cur.distinct - prev.distinct) * 10 <= (7ull << lg)) break;
             // estimate too low (cannot happen within HLL's error bars, but stay exact): grow and redo
             Counters redo = cur;
@@ -925,6 +973,7 @@ int tpc_session_find_candidates(tpc_session* s) {
         CK(cudaEventRecord(s->ev[4], s->stream));
         CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
+        vlog("classify done", (int)r);
         s->local_count = cur.junctions;
         float t;
         cudaEventElapsedTime(&t, s->ev[10], s->ev[3]); ms_insert += t;
@@ -943,6 +992,7 @@ int tpc_session_find_candidates(tpc_session* s) {
     s->st.ms_bin = ms_bin; s->st.ms_fill = ms_fill; s->st.ms_query = ms_query; s->st.ms_insert = ms_insert; s->st.ms_classify = ms_classify;
     s->have_candidates = true;
     s->have_index = false;
+    vlog("scratch released", -1);
     return 0;
 }
 
@@ -957,6 +1007,7 @@ int tpc_session_set_junctions(tpc_session* s, const uint64_t* dev_words_all, uin
     if (!s || !s->g.codes) return set_error("no genome set");
     if (int wrc = wait_genome(s, s->ntiles)) return wrc;
     LaunchCtx lc = s->lctx();
+    WallTimer wall(&s->st.ms_wall_index);
     CK(cudaEventRecord(s->ev[5], s->stream));
     if (s->d_sorted) { CK(dev_free(s->d_sorted, s->stream)); s->d_sorted = nullptr; }
     if (s->d_J) { CK(dev_free(s->d_J, s->stream)); s->d_J = nullptr; }
@@ -998,6 +1049,7 @@ int tpc_session_emit_count(tpc_session* s, uint64_t pos_begin, uint64_t pos_end,
     if (pos_begin % kTilePos && pos_begin != s->g.npos) return set_error("emit slice must start at a multiple of %d", kTilePos);
     if (pos_end % kTilePos && pos_end != s->g.npos) return set_error("emit slice must end at a multiple of %d", kTilePos);
     LaunchCtx lc = s->lctx();
+    WallTimer wall(&s->st.ms_wall_emit);
     uint64_t tb = pos_begin / kTilePos, te = (pos_end + kTilePos - 1) / kTilePos;
     if (pos_begin >= pos_end) te = tb;   // empty slice (more shards than tiles)
     uint64_t nt = te - tb;
@@ -1043,6 +1095,7 @@ int tpc_session_emit_write(tpc_session* s, uint64_t records_before, uint64_t stu
                            uint64_t out_capacity, uint64_t* image_offset, uint64_t* image_bytes) {
     if (!s || !s->have_count) return set_error("emit_count has not run");
     LaunchCtx lc = s->lctx();
+    WallTimer wall(&s->st.ms_wall_emit);
     uint64_t unit_base = records_before + emit_prev_at(s, s->slice_pos_begin);
     uint64_t units = s->slice_records + emit_prev_at(s, s->slice_pos_end) - emit_prev_at(s, s->slice_pos_begin);
     if (image_offset) *image_offset = unit_base * 12;
@@ -1159,9 +1212,11 @@ static int emit_write_parts(tpc_session* s, uint8_t* d_out, uint64_t image_bytes
 int tpc_session_write_host(tpc_session* s, uint8_t* out_image, uint64_t image_bytes) {
     uint8_t* d_out = nullptr;
     CK(dev_alloc(&d_out, std::max<uint64_t>(image_bytes, 16), s->stream));
+    DevBuf out_holder;
+    out_holder.p = d_out; out_holder.st = s->stream;
     if (!s->copy_stream) CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-    cudaEvent_t done;
-    CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    Events evs(1, cudaEventDisableTiming);
+    cudaEvent_t done = evs[0];
     // device->host copy of part i (copy stream) overlaps the emission of part i+1 (compute stream)
     int rc = emit_write_parts(s, d_out, image_bytes, 8, [&](uint64_t lo, uint64_t hi) -> int {
         if (hi <= lo) return 0;
@@ -1173,23 +1228,25 @@ int tpc_session_write_host(tpc_session* s, uint8_t* out_image, uint64_t image_by
     cudaError_t e = cudaStreamSynchronize(s->copy_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     if (e != cudaSuccess && rc == 0) rc = set_error("CUDA error %s copying the image", cudaGetErrorName(e));
-    cudaEventDestroy(done);
-    dev_free(d_out, s->stream);
     return rc;
 }
 
 int tpc_session_write_stream(tpc_session* s, uint64_t image_bytes, tpc_chunk_sink sink, void* ctx) {
     uint8_t* d_out = nullptr;
     CK(dev_alloc(&d_out, std::max<uint64_t>(image_bytes, 16), s->stream));
+    DevBuf out_holder;
+    out_holder.p = d_out; out_holder.st = s->stream;
     uint64_t off = 0, bytes = 0;
     int rc = tpc_session_emit_write(s, 0, 0, d_out, image_bytes, &off, &bytes);
     const uint64_t kChunk = 64ull << 20;
+    PinnedBuf pin[2];
     uint8_t* stage[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    Events evs(2, cudaEventDisableTiming);
+    cudaEvent_t ev[2] = {evs[0], evs[1]};
     if (rc == 0 && bytes) {
         for (int i = 0; i < 2 && rc == 0; ++i) {
-            if (cudaMallocHost((void**)&stage[i], std::min(kChunk, bytes)) != cudaSuccess) rc = set_error("out of (pinned) host memory");
-            else cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+            if (cudaMallocHost(&pin[i].p, std::min(kChunk, bytes)) != cudaSuccess) rc = set_error("out of (pinned) host memory");
+            stage[i] = (uint8_t*)pin[i].p;
         }
         uint64_t nchunks = (bytes + kChunk - 1) / kChunk;
         auto issue = [&](uint64_t c) {
@@ -1205,11 +1262,6 @@ int tpc_session_write_stream(tpc_session* s, uint64_t image_bytes, tpc_chunk_sin
         }
     }
     cudaStreamSynchronize(s->stream);
-    for (int i = 0; i < 2; ++i) {
-        if (stage[i]) cudaFreeHost(stage[i]);
-        if (ev[i]) cudaEventDestroy(ev[i]);
-    }
-    dev_free(d_out, s->stream);
     return rc;
 }
 
@@ -1233,46 +1285,6 @@ int tpc_junctions_host(const tpc_params* params, const tpc_genome* host_genome, 
     if (stats) tpc_session_stats(s, stats);
     tpc_session_destroy(s);
     return rc;
-}
-
-// ---------------------------------------------------------------------------------------------
-// random-access roofline probe
-// ---------------------------------------------------------------------------------------------
-int tpc_random_access_probe(uint32_t filter_bits, uint32_t mode, uint64_t touches, double* touches_per_s) {
-    if (filter_bits < 9 || filter_bits > 40 || mode > 2) return set_error("bad probe arguments");
-    if (const char* gran = getenv("TPC_L2_FETCH_GRANULARITY")) {
-        cudaError_t ge = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gran));
-        size_t got = 0;
-        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
-        fprintf(stderr, "[tpc] L2 fetch granularity: requested %s -> %s, now %zu\n", gran, cudaGetErrorName(ge), got);
-    }
-    uint32_t* table = nullptr;
-    unsigned long long* sink = nullptr;
-    uint64_t bytes = (1ull << filter_bits) / 8;
-    CK(cudaMalloc(&table, bytes));
-    CK(cudaMalloc(&sink, 8));
-    CK(cudaMemset(table, 0, bytes));
-    CK(cudaMemset(sink, 0, 8));
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int blocks = sms * 8;
-    uint64_t threads = (uint64_t)blocks * 256;
-    uint64_t per_thread = std::max<uint64_t>(touches / threads, 1);
-    cudaEvent_t a, b;
-    cudaEventCreate(&a); cudaEventCreate(&b);
-    k_probe<<<blocks, 256>>>(table, filter_bits - 8, mode, std::max<uint64_t>(per_thread / 8, 1), sink);  // warm-up
-    cudaEventRecord(a);
-    k_probe<<<blocks, 256>>>(table, filter_bits - 8, mode, per_thread, sink);
-    cudaEventRecord(b);
-    cudaError_t e = cudaDeviceSynchronize();
-    float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
-    cudaEventDestroy(a); cudaEventDestroy(b);
-    cudaFree(table); cudaFree(sink);
-    if (e != cudaSuccess) return set_error("probe failed: %s", cudaGetErrorString(e));
-    if (touches_per_s) *touches_per_s = (double)(per_thread * threads) / (ms * 1e-3);
-    return 0;
 }
 
 }  // extern "C"

@@ -24,6 +24,18 @@ def position_cuts(n_positions: int, world: int) -> list[int]:
     return [min(n_positions, r * chunk * TILE_POSITIONS) for r in range(world)] + [n_positions]
 
 
+def all_gather_into(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """dist.all_gather_into_tensor; gloo has no all-gather of CUDA tensors (ranks sharing one GPU in the tests):
+    there every rank drops its part into a zeroed buffer and the buffers are summed."""
+    if dist.get_backend() == "gloo" and src.is_cuda:
+        rank, n = dist.get_rank(), src.numel()
+        dst.zero_()
+        dst[rank * n:(rank + 1) * n].copy_(src)
+        dist.all_reduce(dst, op=dist.ReduceOp.SUM)
+    else:
+        dist.all_gather_into_tensor(dst, src)
+
+
 def allgather_varlen(local: torch.Tensor) -> torch.Tensor:
     """Concatenation over ranks (in rank order) of 1-D tensors of different lengths."""
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -34,9 +46,9 @@ def allgather_varlen(local: torch.Tensor) -> torch.Tensor:
     mx = max(max(counts_h), 1)
     padded = torch.zeros(mx, dtype=local.dtype, device=local.device)
     padded[:local.numel()] = local
-    gathered = [torch.empty(mx, dtype=local.dtype, device=local.device) for _ in range(world)]
-    dist.all_gather(gathered, padded)
-    return torch.cat([gathered[r][:counts_h[r]] for r in range(world)])
+    gathered = torch.empty(mx * world, dtype=local.dtype, device=local.device)
+    all_gather_into(gathered, padded)
+    return torch.cat([gathered[r * mx:r * mx + counts_h[r]] for r in range(world)])
 
 
 def or_reduce_disjoint_(mask_words: torch.Tensor) -> torch.Tensor:
@@ -239,7 +251,7 @@ def upload_allgather(shard: HostGenomeShard, rank: int, world: int, device):
                 if on_gpu:
                     ag.wait_event(copied)
                 if world > 1:
-                    dist.all_gather_into_tensor(full[a][start:start + part * world], mine)
+                    all_gather_into(full[a][start:start + part * world], mine)
                 if on_gpu:
                     gathered[a][b] = torch.cuda.Event()
                     gathered[a][b].record(ag)
