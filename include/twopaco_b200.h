@@ -32,6 +32,7 @@ extern "C" {
 
 typedef struct tpc_handle tpc_handle;         /* result of tpc_build (a VertexEnumerator) */
 typedef struct tpc_session tpc_session;       /* one GPU's shard of a run */
+typedef struct tpc_multi tpc_multi;           /* the GPUs of this process + their NCCL communicators */
 typedef void (*tpc_log_fn)(void *ctx, const char *text); /* receives the std::ostream & log text */
 
 /* ------------------------------------------------------------------------------------------
@@ -149,6 +150,19 @@ int tpc_junctions_host(const tpc_params *params, const tpc_genome *host_genome,
                        uint8_t *out_image, uint64_t out_capacity, uint64_t *out_bytes,
                        tpc_stats *stats);
 
+/* The same on N GPUs of this process (hash-range shards, one host thread and one session per GPU):
+ * every GPU uploads 1/N of the packed genome over its own PCIe link, the parts are all-gathered chunk by chunk over
+ * NVLink (NCCL) while the first pass already runs, junction lists are all-gathered, candidate masks OR-reduce-
+ * scattered, and every GPU copies its position slice of the image into out_image.  A context is created once
+ * (ncclCommInitAll over `devices`, NULL = 0..n_gpus-1) and reused by any number of runs.  This is what tpc_build
+ * uses when several GPUs are visible.  NCCL is loaded at run time (libnccl.so.2; TPC_NCCL_LIB overrides). */
+uint32_t tpc_visible_gpus(void);
+int tpc_multi_create(uint32_t n_gpus, const int *devices, tpc_multi **out);
+void tpc_multi_destroy(tpc_multi *m);
+uint32_t tpc_multi_gpus(const tpc_multi *m);
+int tpc_multi_junctions_host(tpc_multi *m, const tpc_params *params, const tpc_genome *host_genome,
+                             uint8_t *out_image, uint64_t out_capacity, uint64_t *out_bytes, tpc_stats *stats);
+
 /* ------------------------------------------------------------------------------------------
  * Level 3 -- sessions.  One session = one GPU (current device at creation) = one hash-range
  * shard (params->shard_index / shard_count).  All device pointers returned stay owned by the
@@ -228,6 +242,23 @@ int tpc_pack_ascii_device(const uint8_t *dev_ascii, uint64_t n_positions, uint64
  * nbytes and image_offset are multiples of 4.  Synchronises `stream`. */
 int tpc_image_digest_device(const uint8_t *dev_image, uint64_t nbytes, uint64_t image_offset, void *stream,
                             uint64_t digest[2]);
+
+/* ------------------------------------------------------------------------------------------
+ * The consumer side of de_bruijn.bin on the GPU.
+ *   tpc_graphdump_device : the text `graphdump -f seq` (format 0; graphdump.cpp:160-168: "chr pos id" per record) or
+ *                          `graphdump -f group` (format 1; graphdump.cpp:120-158: occurrences grouped by signed id,
+ *                          "chr pos; " per member, classes ordered by first occurrence) prints for an image in device
+ *                          memory; *dev_text is allocated by the callee (release with tpc_device_free).
+ *   tpc_graphdump_file   : file -> text file (out_path NULL or "-" = stdout), format "seq" | "group".
+ *   tpc_canonical_image_device : the canonical relabelling of SURVEY.md appendix C -- ids renumbered 1.. by first
+ *                          appearance of |id|, first occurrence positive, separators kept -- written to dev_out (same size).
+ *                          Two images describe the same graph iff their canonical images are byte-identical.
+ * ---------------------------------------------------------------------------------------- */
+int tpc_graphdump_device(const uint8_t *dev_image, uint64_t image_bytes, uint32_t format, void *stream,
+                         uint8_t **dev_text, uint64_t *text_bytes);
+int tpc_graphdump_file(const char *image_path, const char *format, const char *out_path);
+int tpc_canonical_image_device(const uint8_t *dev_image, uint64_t image_bytes, void *stream, uint8_t *dev_out,
+                               uint64_t *n_classes);
 
 int tpc_device_alloc(uint64_t bytes, void **out);
 void tpc_device_free(void *p);

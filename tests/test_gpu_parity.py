@@ -586,3 +586,61 @@ def test_undersized_candidate_table_grows_and_redoes(name, golden, monkeypatch):
     img, st = api.junctions_host(api.pack_records(recs), k=spec["k"], filter_bits=14, q=2)   # many false candidates
     assert canon_md5(bytes(img)) == g["canon_md5"] and st.junctions == g["distinct_junctions"]
     assert st.candidate_kmers > 2 * st.junctions
+
+
+# ---- the consumer side on the GPU: graphdump -f seq / -f group and the canonical relabelling -------------------
+def _numpy_group_text(image: bytes) -> bytes:
+    """graphdump.cpp:120-158 restated: classes of equal SIGNED id, members by (chr, pos), classes by first member."""
+    seq, pos, ids = O.decode(image)
+    classes = {}
+    for i, v in enumerate(ids.tolist()):
+        classes.setdefault(v, []).append(i)
+    lines = []
+    for members in sorted(classes.values(), key=lambda m: m[0]):
+        lines.append("".join(f"{seq[i]} {pos[i]}; " for i in members) + "\n")
+    return "".join(lines).encode()
+
+
+@pytest.mark.parametrize("name", ["example_k11", "family_k25", "edge_mixed_k5", "edge_leading_short_k5", "family_twofiles_k25"])
+def test_gpu_graphdump_seq_and_group(name, tmp_path):
+    """tpc_graphdump_device / tpc_graphdump_file == the text the reference's graphdump prints (live binary when it
+    travelled, else the restatement above), for our images and for a reference-style image with random ids / signs."""
+    import subprocess
+    spec = CASES[name]
+    with case_files(spec) as (paths, _, _):
+        recs = api.read_fasta(paths)
+    img, _ = api.junctions_host(api.pack_records(recs), k=spec["k"], filter_bits=20)
+    img = bytes(img)
+    # a relabelled variant: ids permuted and signs flipped per junction, as a differently seeded reference run would write
+    seq, pos, ids = O.decode(img)
+    rng = np.random.default_rng(7)
+    uniq = np.unique(np.abs(ids))
+    perm = dict(zip(uniq.tolist(), (rng.permutation(len(uniq)) + 1000).tolist()))
+    flip = {u: int(rng.integers(0, 2)) * 2 - 1 for u in uniq.tolist()}
+    rec = np.frombuffer(img, dtype=O.REC_DTYPE).copy()
+    sep = (rec["pos"] == O.SEP_POS) | (rec["id"] == O.SEP_ID)
+    rec["id"][~sep] = [perm[abs(v)] * (1 if v > 0 else -1) * flip[abs(v)] for v in ids.tolist()]
+    relabelled = rec.tobytes()
+    for image in (img, relabelled):
+        s2, p2, i2 = O.decode(image)
+        want_seq = "".join(f"{a} {b} {c}\n" for a, b, c in zip(s2.tolist(), p2.tolist(), i2.tolist())).encode()
+        assert api.graphdump(image, "seq") == want_seq
+        assert api.graphdump(image, "group") == _numpy_group_text(image)
+        # canonical relabelling on the GPU == oracle.canon
+        canon_img, n_classes = api.canonical_image(image)
+        cs, cp, cid = O.decode(canon_img)
+        ws, wp, wid = O.canon(image)
+        assert np.array_equal(cs, ws) and np.array_equal(cp, wp) and np.array_equal(cid, wid)
+        assert n_classes == len(np.unique(np.abs(i2)))
+    assert api.canonical_image(img)[0] == api.canonical_image(relabelled)[0]
+    # file -> file, against the unmodified reference graphdump
+    path = tmp_path / "x.dbg"
+    path.write_bytes(relabelled)
+    for fmt in ("seq", "group"):
+        out = tmp_path / f"x.{fmt}"
+        api.graphdump_file(str(path), fmt, str(out))
+        if O.have_reference():
+            q = subprocess.run([str(O.REF_GRAPHDUMP), "-f", fmt, "-k", str(spec["k"]), str(path)], capture_output=True)
+            assert q.returncode == 0, q.stderr
+            assert out.read_bytes() == q.stdout, fmt
+    assert api.graphdump(b"", "seq") == b"" and api.graphdump(b"", "group") == b""

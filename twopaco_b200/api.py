@@ -69,6 +69,12 @@ SIGNATURES = {
     "tpc_handle_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "tpc_free": (None, [C.c_void_p]),
     "tpc_junctions_host": (C.c_int, [C.POINTER(Params), C.POINTER(Genome), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(Stats)]),
+    "tpc_visible_gpus": (C.c_uint32, []),
+    "tpc_multi_create": (C.c_int, [C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tpc_multi_destroy": (None, [C.c_void_p]),
+    "tpc_multi_gpus": (C.c_uint32, [C.c_void_p]),
+    "tpc_multi_junctions_host": (C.c_int, [C.c_void_p, C.POINTER(Params), C.POINTER(Genome), C.c_void_p, C.c_uint64,
+                                           C.POINTER(C.c_uint64), C.POINTER(Stats)]),
     "tpc_session_create": (C.c_int, [C.POINTER(Params), C.c_void_p, C.POINTER(C.c_void_p)]),
     "tpc_session_destroy": (None, [C.c_void_p]),
     "tpc_session_set_genome_host": (C.c_int, [C.c_void_p, C.POINTER(Genome)]),
@@ -84,6 +90,9 @@ SIGNATURES = {
     "tpc_session_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "tpc_pack_ascii_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tpc_image_digest_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64 * 2)]),
+    "tpc_graphdump_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "tpc_graphdump_file": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p]),
+    "tpc_canonical_image_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "tpc_device_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
     "tpc_device_free": (None, [C.c_void_p]),
     "tpc_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -203,6 +212,47 @@ def junctions_host(genome: PackedGenome, k: int, filter_bits: int, q: int = 5, r
         rc = L.tpc_junctions_host(C.byref(prm), C.byref(g), out.ctypes.data, out.nbytes, C.byref(nbytes), C.byref(st))
     _check(rc)
     return out[:nbytes.value], st
+
+
+class MultiGpu:
+    """N GPUs of this process (tpc_multi_*): one host thread + one hash-range shard per GPU, NCCL in between."""
+
+    def __init__(self, n_gpus: int, devices: list[int] | None = None):
+        self._m = C.c_void_p()
+        arr = (C.c_int * n_gpus)(*devices) if devices else None
+        _check(lib().tpc_multi_create(n_gpus, arr, C.byref(self._m)))
+        self.n_gpus = n_gpus
+
+    def junctions_host(self, genome: PackedGenome, k: int, filter_bits: int, q: int = 5, rounds: int = 1,
+                       abundance: int = ABUNDANCE_MAX, seed: int = 0, out: np.ndarray | None = None):
+        """-> (image bytes as numpy uint8 view, Stats summed / maxed over the shards)."""
+        L = lib()
+        prm = Params(k, filter_bits, q, rounds, abundance, 0, self.n_gpus, seed)
+        g = genome.struct()
+        st = Stats()
+        nbytes = C.c_uint64(0)
+        if out is None:
+            out = np.empty(max(12 * (genome.n_records * 2 + 1024), 1 << 16), dtype=np.uint8)
+        rc = L.tpc_multi_junctions_host(self._m, C.byref(prm), C.byref(g), out.ctypes.data, out.nbytes, C.byref(nbytes), C.byref(st))
+        if rc == 2:   # buffer too small: the error message carries a lower bound; grow geometrically
+            for _ in range(8):
+                out = np.empty(max(out.nbytes * 4, 1 << 20), dtype=np.uint8)
+                rc = L.tpc_multi_junctions_host(self._m, C.byref(prm), C.byref(g), out.ctypes.data, out.nbytes, C.byref(nbytes), C.byref(st))
+                if rc != 2:
+                    break
+        _check(rc)
+        return out[:nbytes.value], st
+
+    def close(self) -> None:
+        if self._m:
+            lib().tpc_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------------------------------
@@ -333,6 +383,41 @@ def image_digest_device(dev_ptr: int, nbytes: int, image_offset: int = 0, stream
     d = (C.c_uint64 * 2)()
     _check(lib().tpc_image_digest_device(C.c_void_p(dev_ptr), nbytes, image_offset, C.c_void_p(stream), C.byref(d)))
     return int(d[0]), int(d[1])
+
+
+def graphdump(image, fmt: str = "seq") -> bytes:
+    """GPU `graphdump -f seq|group` of an image given as host bytes -> the text graphdump prints."""
+    data = np.frombuffer(bytes(image), dtype=np.uint8)
+    buf = DeviceBuffer(max(len(data), 16))
+    if len(data):
+        buf.from_host(data)
+    t, n = C.c_void_p(), C.c_uint64()
+    _check(lib().tpc_graphdump_device(C.c_void_p(buf.ptr), len(data), {"seq": 0, "group": 1}[fmt], None, C.byref(t), C.byref(n)))
+    text = DeviceBuffer.adopt(t.value, n.value)
+    try:
+        return text.to_host(n.value).tobytes() if n.value else b""
+    finally:
+        text.close()
+        buf.close()
+
+
+def graphdump_file(image_path: str, fmt: str, out_path: str | None = None) -> None:
+    _check(lib().tpc_graphdump_file(os.fsencode(image_path), fmt.encode(), os.fsencode(out_path) if out_path else None))
+
+
+def canonical_image(image) -> tuple[bytes, int]:
+    """Canonical relabelling of an image on the GPU -> (canonical image bytes, number of distinct |id|)."""
+    data = np.frombuffer(bytes(image), dtype=np.uint8)
+    a, b = DeviceBuffer(max(len(data), 16)), DeviceBuffer(max(len(data), 16))
+    if len(data):
+        a.from_host(data)
+    n = C.c_uint64()
+    try:
+        _check(lib().tpc_canonical_image_device(C.c_void_p(a.ptr), len(data), None, C.c_void_p(b.ptr), C.byref(n)))
+        return (b.to_host(len(data)).tobytes() if len(data) else b""), n.value
+    finally:
+        a.close()
+        b.close()
 
 
 def _fmix64(x: np.ndarray) -> np.ndarray:

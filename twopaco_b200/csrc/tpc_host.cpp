@@ -17,8 +17,12 @@
 
 #include <cuda_runtime_api.h>
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include "tpc_ingest.h"
 #include "tpc_internal.h"
+#include "tpc_multi.h"
 
 using tpc::set_error;
 
@@ -235,6 +239,8 @@ struct tpc_handle {
     void *d_codes = nullptr, *d_nmask = nullptr;
     tpc_stats stats{};
     uint64_t junctions = 0;
+    int device = 0;          // the GPU that holds the session and the genome (GetId)
+    uint32_t gpus = 1;
 };
 
 namespace {
@@ -295,10 +301,41 @@ int tpc_build(const char* const* fasta_paths, size_t n_files, uint32_t k, uint32
     }
     double t_upload = now();
     uint64_t bytes = 0;
-    if (rc == 0) rc = tpc_session_run_to_count(s, &bytes);
-    double t_gpu = now();
-    tpc_stats st{};
+    // How many GPUs: every visible device when the input is worth sharding, TPC_GPUS=<n> overrides (SURVEY 8(b):
+    // "-t keeps meaning host worker threads, GPU count from a new env/flag or CUDA_VISIBLE_DEVICES")
+    uint32_t gpus = 1;
     if (rc == 0) {
+        const uint32_t visible = tpc_visible_gpus();
+        if (const char* e = getenv("TPC_GPUS")) gpus = std::max(1, atoi(e));
+        else if (plan.n_positions >= (1ull << 27)) gpus = visible;
+        gpus = std::max<uint32_t>(1, std::min(gpus, visible));
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (gpus > 1 && cur != 0) gpus = 1;   // the genome was packed on the current device; shards start at device 0
+    }
+    tpc_stats st{};
+    tpc_multi* multi = nullptr;
+    if (rc == 0 && gpus > 1) {
+        // N GPUs of this process: chunked NCCL broadcast of the packed genome from GPU 0, hash-range shards, NCCL
+        // exchanges between the stages, every GPU pwrite()s its slice of the image (tpc_multi.cpp)
+        tpc_session_destroy(s);
+        s = nullptr;
+        rc = tpc_multi_create(gpus, nullptr, &multi);
+        if (rc == 0) {
+            int fd = open(outfile, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+            if (fd < 0) rc = set_error("Can't create the output file");
+            else {
+                rc = tpc::multi_run_from_device0(multi, &prm, (const uint64_t*)d_codes, (const uint64_t*)d_nmask, plan.n_positions,
+                                                 plan.rec_start.data(), plan.rec_len.data(), plan.rec_start.size(), fd, &bytes, &st, &s);
+                if (close(fd) != 0 && rc == 0) rc = set_error("Can't write to the output file");
+            }
+        }
+        if (multi) tpc_multi_destroy(multi);
+    } else {
+        if (rc == 0) rc = tpc_session_run_to_count(s, &bytes);
+    }
+    double t_gpu = now();
+    if (rc == 0 && gpus == 1) {
         // JunctionPositionWriter (junctionapi.h:110-116): creates / truncates the output file; the image
         // is produced on the device and streamed to the file through two pinned staging buffers
         FILE* f = fopen(outfile, "wb");
@@ -308,10 +345,10 @@ int tpc_build(const char* const* fasta_paths, size_t n_files, uint32_t k, uint32
             if (fclose(f) != 0 && rc == 0) rc = set_error("Can't write to the output file");
         }
     }
-    if (rc == 0) rc = tpc_session_stats(s, &st);
+    if (rc == 0 && gpus == 1) rc = tpc_session_stats(s, &st);
     if (verbose)
-        fprintf(stderr, "[tpc_build] frame+count %.3f s, normalise+upload+pack %.3f s, gpu passes %.3f s, emit+write %.3f s\n",
-                t_plan - t0, t_upload - t_plan, t_gpu - t_upload, now() - t_gpu);
+        fprintf(stderr, "[tpc_build] %u GPU(s): frame+count %.3f s, normalise+upload+pack %.3f s, gpu passes %.3f s, emit+write %.3f s\n",
+                gpus, t_plan - t0, t_upload - t_plan, t_gpu - t_upload, now() - t_gpu);
     if (rc == 0) {
         std::ostringstream ss;
         ss << std::string(80, '-') << "\n"
@@ -331,12 +368,13 @@ int tpc_build(const char* const* fasta_paths, size_t n_files, uint32_t k, uint32
     }
     tpc_handle* h = rc == 0 ? new (std::nothrow) tpc_handle() : nullptr;
     if (!h) {
-        tpc_session_destroy(s);
+        if (s) tpc_session_destroy(s);
         tpc_device_free(d_codes);
         tpc_device_free(d_nmask);
         return rc ? rc : set_error("out of memory");
     }
-    h->session = s; h->stats = st; h->junctions = st.junctions;
+    h->session = s; h->stats = st; h->junctions = st.junctions; h->gpus = gpus;
+    cudaGetDevice(&h->device);
     h->d_codes = d_codes; h->d_nmask = d_nmask;  // the session reads k-mers back from the genome (GetId)
     *out = h;
     return 0;
@@ -347,8 +385,12 @@ uint64_t tpc_vertices(const tpc_handle* h) { return h ? h->junctions : 0; }
 int64_t tpc_get_id(const tpc_handle* h, const char* kmer) {
     int64_t id = TPC_INVALID_VERTEX;
     if (!h || !h->session) return id;
-    if (tpc_session_get_id(h->session, kmer, &id) != 0) return TPC_INVALID_VERTEX;
-    return id;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != h->device) cudaSetDevice(h->device);
+    const int rc = tpc_session_get_id(h->session, kmer, &id);
+    if (cur != h->device) cudaSetDevice(cur);
+    return rc != 0 ? TPC_INVALID_VERTEX : id;
 }
 
 int tpc_handle_stats(const tpc_handle* h, tpc_stats* out) {
@@ -359,9 +401,13 @@ int tpc_handle_stats(const tpc_handle* h, tpc_stats* out) {
 
 void tpc_free(tpc_handle* h) {
     if (!h) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != h->device) cudaSetDevice(h->device);
     tpc_session_destroy(h->session);
     tpc_device_free(h->d_codes);
     tpc_device_free(h->d_nmask);
+    if (cur != h->device) cudaSetDevice(cur);
     delete h;
 }
 
