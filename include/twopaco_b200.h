@@ -247,9 +247,10 @@ int tpc_image_digest_device(const uint8_t *dev_image, uint64_t nbytes, uint64_t 
  * The consumer side of de_bruijn.bin on the GPU.
  *   tpc_graphdump_device : the text `graphdump -f seq` (format 0; graphdump.cpp:160-168: "chr pos id" per record) or
  *                          `graphdump -f group` (format 1; graphdump.cpp:120-158: occurrences grouped by signed id,
- *                          "chr pos; " per member, classes ordered by first occurrence) prints for an image in device
+ *                          "chr pos; " per member, classes ordered by first occurrence) or `graphdump -f dot` (format 2;
+ *                          graphdump.cpp:585-606: two edge lines per consecutive pair of records) prints for an image in device
  *                          memory; *dev_text is allocated by the callee (release with tpc_device_free).
- *   tpc_graphdump_file   : file -> text file (out_path NULL or "-" = stdout), format "seq" | "group".
+ *   tpc_graphdump_file   : file -> text file (out_path NULL or "-" = stdout), format "seq" | "group" | "dot".
  *   tpc_canonical_image_device : the canonical relabelling of SURVEY.md appendix C -- ids renumbered 1.. by first
  *                          appearance of |id|, first occurrence positive, separators kept -- written to dev_out (same size).
  *                          Two images describe the same graph iff their canonical images are byte-identical.

@@ -385,14 +385,15 @@ def test_sub_rounds_share_one_ownership_scan(name, sub, user_rounds, golden, mon
     monkeypatch.setenv("TPC_FILTER_MODE", "binned")
     monkeypatch.setenv("TPC_SLICE_LOG2", "12")
     monkeypatch.setenv("TPC_SUBROUNDS", str(sub))
+    monkeypatch.setenv("TPC_PIPELINE", "1")
     with case_files(spec) as (paths, _, _):
         recs = api.read_fasta(paths)
     img, st = api.junctions_host(api.pack_records(recs), k=spec["k"], filter_bits=20, q=4, rounds=user_rounds)
     assert st.ms_bin > 0 and st.sub_rounds == sub
     assert canon_md5(bytes(img)) == g["canon_md5"] and st.junctions == g["distinct_junctions"]
-    # rounds <= 15 per GPU are pipelined (round r+1 binned on a second stream beside the fill of round r) ...
+    # opt-in pipelining: rounds <= 15 per GPU are pipelined (round r+1 binned on a second stream beside the fill of round r) ...
     assert (st.ms_bin_overlapped > 0) == (sub * user_rounds <= 15)
-    # ... unless switched off: same result from the one-scratch path
+    # ... by default they run in sequence from one scratch: same result
     monkeypatch.setenv("TPC_PIPELINE", "0")
     img2, st2 = api.junctions_host(api.pack_records(recs), k=spec["k"], filter_bits=20, q=4, rounds=user_rounds)
     assert st2.ms_bin_overlapped == 0 and bytes(img2) == bytes(img)
@@ -524,18 +525,25 @@ def test_host_generator_matches_device_generator():
 
 
 def test_headline_code_path_at_100mbp_against_the_live_reference(tmp_path, monkeypatch):
-    """The code path of the benchmark's headline number (C3 on one GPU: k_own with 3 ownership planes, five pipelined
-    sub-rounds of k_bin_list beside k_apply_fill, 64 MiB slices, merged exact pass) on 105 Mbp of the same kind of input
-    (7 genomes, 0.1 % divergence, k = 25), against the UNMODIFIED reference run here with all host cores (the C oracle when
-    the reference binary did not travel); then the direct kernels must give the same bytes."""
+    """The code path of the benchmark's headline number (C3 on one GPU: k_own with 3 ownership planes, four sub-rounds of
+    k_bin_list + k_apply_fill / k_apply_query over 64 MiB slices, the slices cleared by the query kernels, merged exact pass
+    from the mark list, cached ids in the emit) on 105 Mbp of the same kind of input (7 genomes, 0.1 % divergence, k = 25),
+    against the UNMODIFIED reference run here with all host cores (the C oracle when the reference binary did not travel);
+    the opt-in pipelined variant (five sub-rounds, round r+1 binned beside the fill of round r) and the direct kernels must
+    give the same bytes."""
     dg = benchutil.synth_family_device(0x4855, 7, 1, 15_000_000, 0.001)
     recs = [dg.record_ascii(r) for r in range(7)]
     host = dg.to_host()
-    monkeypatch.setenv("TPC_SUBROUNDS", "5")
+    monkeypatch.setenv("TPC_SUBROUNDS", "4")
     monkeypatch.setenv("TPC_FILTER_MODE", "binned")
     img, st = api.junctions_host(host, k=25, filter_bits=30, q=5)
-    assert st.sub_rounds == 5 and st.ms_bin_overlapped > 0 and st.bin_waves == 1, "not the pipelined sub-round path"
+    assert st.sub_rounds == 4 and st.ms_bin_overlapped == 0 and st.bin_waves == 1, "not the sub-round path of the benchmark"
     img = bytes(img)
+    monkeypatch.setenv("TPC_SUBROUNDS", "5")
+    monkeypatch.setenv("TPC_PIPELINE", "1")
+    img_p, st_p = api.junctions_host(host, k=25, filter_bits=30, q=5)
+    assert st_p.sub_rounds == 5 and st_p.ms_bin_overlapped > 0 and bytes(img_p) == img
+    monkeypatch.delenv("TPC_PIPELINE")
     if O.have_reference():
         paths = []
         for i, r in enumerate(recs):
@@ -636,7 +644,7 @@ def test_gpu_graphdump_seq_and_group(name, tmp_path):
     # file -> file, against the unmodified reference graphdump
     path = tmp_path / "x.dbg"
     path.write_bytes(relabelled)
-    for fmt in ("seq", "group"):
+    for fmt in ("seq", "group", "dot"):
         out = tmp_path / f"x.{fmt}"
         api.graphdump_file(str(path), fmt, str(out))
         if O.have_reference():
@@ -644,3 +652,101 @@ def test_gpu_graphdump_seq_and_group(name, tmp_path):
             assert q.returncode == 0, q.stderr
             assert out.read_bytes() == q.stdout, fmt
     assert api.graphdump(b"", "seq") == b"" and api.graphdump(b"", "group") == b""
+
+
+DROPIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "twopaco_dropin")
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN), reason="oracle/_ref/twopaco_dropin was not built (no /root/reference at build time)")
+def test_reference_cli_sources_compile_and_run_against_the_library(tmp_path, golden):
+    """Drop-in proof: oracle/_ref/twopaco_dropin is the reference's UNMODIFIED constructor.cpp + test.cpp (TCLAP command
+    line, --test harness with its own brute-force junction finder and GetId checks) compiled with only
+    vertexenumerator.{h,cpp} replaced by twopaco_b200/host's and linked with libtwopaco_b200.so (oracle/Makefile)."""
+    import subprocess
+    from tests.cases import GOLDEN_DIR
+    out = tmp_path / "example.dbg"
+    p = subprocess.run([DROPIN, "-f", "20", "-k", "11", str(GOLDEN_DIR / "example.fa"), "-o", str(out), "--tmpdir", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "Distinct junctions = 7" in p.stdout
+    assert canon_md5(out.read_bytes()) == golden["example_k11"]["canon_md5"]
+    dummy = tmp_path / "dummy.fa"
+    dummy.write_bytes(b">d\nACGT\n")
+    r = subprocess.run([DROPIN, "--test", "-f", "20", "--tmpdir", str(tmp_path), str(dummy)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert (r.stdout + r.stderr).count("PASSED") == 10 and "FAILED" not in r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("name", ["family_k25", "family_k63", "family_seam_k25"])
+def test_mark_list_and_emit_id_cache_variants(name, golden, monkeypatch):
+    """The exact pass reads the candidates from the mark list the binned query kernels append to (sparse marks) or walks the
+    mask (list switched off, or overflowed -> pass redone from the mask); emit_write takes the ids emit_count cached or looks
+    them up again (cache off / too small).  Every combination must give the same bytes."""
+    spec, g = CASES[name], golden[name]
+    with case_files(spec) as (paths, _, _):
+        recs = api.read_fasta(paths)
+    gen = api.pack_records(recs)
+    monkeypatch.setenv("TPC_FILTER_MODE", "binned")
+    monkeypatch.setenv("TPC_SLICE_LOG2", "12")
+    base, st0 = api.junctions_host(gen, k=spec["k"], filter_bits=22, q=5)
+    base = bytes(base)
+    assert canon_md5(base) == g["canon_md5"] and st0.ms_bin > 0
+    for env in ({"TPC_MARK_LIST": "0"}, {"TPC_MARK_LIST_CAP": "600"}, {"TPC_EMIT_CACHE": "0"}, {"TPC_EMIT_CACHE_CAP": "37"},
+                {"TPC_MARK_LIST_CAP": "600", "TPC_SUBROUNDS": "3"}, {"TPC_MARK_LIST": "0", "TPC_EMIT_CACHE_CAP": "1"},
+                {"TPC_MARK_LIST_CAP": "600", "TPC_MARK_LIST_FORCE": "1"}, {"TPC_MARK_LIST_CAP": "1200", "TPC_MARK_LIST_FORCE": "1", "TPC_SUBROUNDS": "2"}):
+        for k_, v in env.items():
+            monkeypatch.setenv(k_, v)
+        img, st = api.junctions_host(gen, k=spec["k"], filter_bits=22, q=5)
+        assert bytes(img) == base and st.junctions == st0.junctions, env
+        for k_ in env:
+            monkeypatch.delenv(k_)
+
+
+# ---- the C++ multi-GPU driver (tpc_multi.cpp): one process, one host thread per GPU, NCCL between the stages ----------
+def _visible_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("mode", ["direct", "binned"])
+def test_cxx_multi_gpu_host_buffers(mode, monkeypatch):
+    """tpc_multi_junctions_host on all visible GPUs (up to 4): 1/N upload + NCCL all-gather of the genome, hash-range shards,
+    all-gather of the junction words, reduce-scatter of the masks, position-sharded emit -- byte-identical to the oracle."""
+    n = min(_visible_gpus(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    monkeypatch.setenv("TPC_FILTER_MODE", mode)
+    monkeypatch.setenv("TPC_SLICE_LOG2", "12")
+    mg = api.MultiGpu(n)
+    try:
+        for k, f, recs in ((25, 24, synth.founder_family(91, 6, 3, 60_000, 0.01, n_runs=2) + [b"ACG", b""]),
+                           (63, 22, synth.founder_family(92, 4, 2, 50_000, 0.02, n_runs=1)),
+                           (9, 20, synth.reference_selftest_set(93)), (11, 16, [b"ACGTACGTACG"]), (11, 16, [])):
+            ref, nj, nm = O.find_junctions(recs, k)
+            img, st = mg.junctions_host(api.pack_records(recs), k=k, filter_bits=f)
+            assert bytes(img) == ref, (k, mode)
+            assert st.junctions == nj and st.occurrences == nm
+    finally:
+        mg.close()
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="CLI not built")
+def test_cli_uses_several_gpus(tmp_path, monkeypatch):
+    """`twopaco` with TPC_GPUS=N (what it does on its own for inputs >= 2^27 positions): same file as on one GPU."""
+    import subprocess
+    n = min(_visible_gpus(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    recs = synth.founder_family(808, 6, 2, 120_000, 0.01, n_runs=2)
+    fa = tmp_path / "in.fa"
+    O.write_fasta(str(fa), recs)
+    outs = []
+    for gpus in (1, n):
+        out = tmp_path / f"o{gpus}.bin"
+        p = subprocess.run([CLI, "-k", "25", "-f", "24", str(fa), "-o", str(out), "--tmpdir", str(tmp_path)], capture_output=True, text=True,
+                           env={**os.environ, "TPC_GPUS": str(gpus), "TPC_VERBOSE": "1"})
+        assert p.returncode == 0, p.stderr
+        assert f"{gpus} GPU(s)" in p.stderr
+        outs.append(out.read_bytes())
+    ref, _, _ = O.find_junctions(recs, 25)
+    assert outs[0] == ref and outs[1] == ref

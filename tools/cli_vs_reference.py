@@ -53,13 +53,24 @@ def main():
         t_ref = time.perf_counter() - t0
         assert r.returncode == 0, r.stderr
         a, b = open(ours, "rb").read(), open(ref, "rb").read()
-        same = O.canon_equal(a, b)
+        # canonical relabelling on the GPU (tpc_canonical_image_device): byte-identical canonical images <=> same graph
+        ca, na = api.canonical_image(a)
+        cb, nb = api.canonical_image(b)
+        same = ca == cb and na == nb
+        d = api.image_digest_host(a)
+        try:
+            import bench
+            gold = bench.golden_digest(sys.argv[1] if len(sys.argv) > 1 else "c2")
+        except Exception:
+            gold = None
         dj = lambda s: [ln for ln in s.splitlines() if ln.startswith("Distinct junctions")]
         print(json.dumps({"workload": wl["name"], "total_bp": total_bp, "host_cores": cores,
                           "ours_cli_s": round(t_ours, 3), "ours_cli_best_of_2_s": round(t_ours_warm, 3),
                           "reference_cli_s": round(t_ref, 3), "speedup_files_to_file": round(t_ref / t_ours_warm, 1),
                           "ours_Gbps": round(total_bp / t_ours_warm / 1e9, 3), "reference_Gbps": round(total_bp / t_ref / 1e9, 5),
-                          "image_bytes": [len(a), len(b)], "canonical_streams_identical": bool(same),
+                          "image_bytes": [len(a), len(b)], "canonical_streams_identical": bool(same), "distinct_ids": [na, nb],
+                          "ours_image_digest": [f"{d[0]:016x}", f"{d[1]:016x}"],
+                          "ours_image_digest_equals_bench_golden": (None if not gold else gold["digest"] == [f"{d[0]:016x}", f"{d[1]:016x}"]),
                           "ours_breakdown": breakdown, "ours_log": dj(p.stdout), "reference_log": dj(r.stdout)}))
 
 

@@ -392,7 +392,7 @@ def graphdump(image, fmt: str = "seq") -> bytes:
     if len(data):
         buf.from_host(data)
     t, n = C.c_void_p(), C.c_uint64()
-    _check(lib().tpc_graphdump_device(C.c_void_p(buf.ptr), len(data), {"seq": 0, "group": 1}[fmt], None, C.byref(t), C.byref(n)))
+    _check(lib().tpc_graphdump_device(C.c_void_p(buf.ptr), len(data), {"seq": 0, "group": 1, "dot": 2}[fmt], None, C.byref(t), C.byref(n)))
     text = DeviceBuffer.adopt(t.value, n.value)
     try:
         return text.to_host(n.value).tobytes() if n.value else b""

@@ -100,6 +100,54 @@ __global__ void k_seq_write(const uint32_t* __restrict__ chr, const uint32_t* __
     }
 }
 
+// ---- dot (graphdump.cpp:585-606): two edge lines per pair of consecutive records of one sequence
+__device__ __forceinline__ uint32_t put_str(char* dst, const char* s) {
+    uint32_t n = 0;
+    while (s[n]) { dst[n] = s[n]; ++n; }
+    return n;
+}
+__device__ __forceinline__ uint32_t dot_line(char* p, long long from, long long to, const char* color, uint32_t chr, uint32_t pos, bool write) {
+    // "\t<from> -> <to>[color=\"<color>\", label=\"chr=<chr> pos=<pos>\"]\n"
+    uint32_t n = 0;
+    if (!write) {
+        uint32_t c = 0;
+        while (color[c]) ++c;
+        return 1 + len_i64(from) + 4 + len_i64(to) + 8 + c + 14 + digits_u64(chr) + 5 + digits_u64(pos) + 3;
+    }
+    p[n++] = '\t';
+    n += put_i64(p + n, from);
+    n += put_str(p + n, " -> ");
+    n += put_i64(p + n, to);
+    n += put_str(p + n, "[color=\"");
+    n += put_str(p + n, color);
+    n += put_str(p + n, "\", label=\"chr=");
+    n += put_u64(p + n, chr);
+    n += put_str(p + n, " pos=");
+    n += put_u64(p + n, pos);
+    n += put_str(p + n, "\"]\n");
+    return n;
+}
+__global__ void k_dot_len(const uint32_t* __restrict__ chr, const uint32_t* __restrict__ pos, const long long* __restrict__ id, uint64_t m,
+                          unsigned long long* __restrict__ len) {
+    GRID_STRIDE(r, m) {
+        unsigned long long n = 0;
+        if (r > 0 && chr[r] == chr[r - 1])
+            n = dot_line(nullptr, id[r - 1], id[r], "blue", chr[r - 1], pos[r - 1], false) +
+                dot_line(nullptr, -id[r], -id[r - 1], "red", chr[r - 1], pos[r - 1], false);
+        len[r] = n;
+    }
+}
+__global__ void k_dot_write(const uint32_t* __restrict__ chr, const uint32_t* __restrict__ pos, const long long* __restrict__ id, uint64_t m,
+                            const unsigned long long* __restrict__ off, char* __restrict__ text) {
+    GRID_STRIDE(r, m) {
+        if (r > 0 && chr[r] == chr[r - 1]) {
+            char* p = text + off[r];
+            p += dot_line(p, id[r - 1], id[r], "blue", chr[r - 1], pos[r - 1], true);
+            dot_line(p, -id[r], -id[r - 1], "red", chr[r - 1], pos[r - 1], true);
+        }
+    }
+}
+
 // ---- group / canon: after the stable sort by key, e = rank in sorted order, idx[e] = record index
 __global__ void k_iota(uint32_t* __restrict__ v, uint64_t m) { GRID_STRIDE(i, m) v[i] = (uint32_t)i; }
 __global__ void k_abs_keys(const long long* __restrict__ id, uint64_t m, unsigned long long* __restrict__ key) {
@@ -297,7 +345,7 @@ extern "C" {
 int tpc_graphdump_device(const uint8_t* dev_image, uint64_t image_bytes, uint32_t format, void* stream, uint8_t** dev_text,
                          uint64_t* text_bytes) {
     if (!dev_text || !text_bytes || (image_bytes && !dev_image)) return set_error("null argument");
-    if (format > 1) return set_error("format must be 0 (seq) or 1 (group)");
+    if (format > 2) return set_error("format must be 0 (seq), 1 (group) or 2 (dot)");
     if ((uintptr_t)dev_image & 3) return set_error("the image must be 4-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     Scratch sc(st);
@@ -312,7 +360,19 @@ int tpc_graphdump_device(const uint8_t* dev_image, uint64_t image_bytes, uint32_
     CKD(cudaMemsetAsync(len + m, 0, 8, st));
     char* text = nullptr;
     unsigned long long total = 0;
-    if (format == 0) {
+    if (format == 2) {
+        const char head[] = "digraph G\n{\n\trankdir = LR\n", tail[] = "}\n";
+        const uint64_t nh = sizeof head - 1, nt = sizeof tail - 1;
+        if (m) k_dot_len<<<grid_for(m), 256, 0, st>>>(R.chr, R.pos, R.id, m, len);
+        if (int rc = exclusive_sum(sc, len, off, m + 1)) return rc;
+        CKD(cudaMemcpyAsync(&total, off + m, 8, cudaMemcpyDeviceToHost, st));
+        CKD(cudaStreamSynchronize(st));
+        CKD(cudaMallocAsync((void**)&text, total + nh + nt + 16, st));
+        CKD(cudaMemcpyAsync(text, head, nh, cudaMemcpyHostToDevice, st));
+        if (m) k_dot_write<<<grid_for(m), 256, 0, st>>>(R.chr, R.pos, R.id, m, off, text + nh);
+        CKD(cudaMemcpyAsync(text + nh + total, tail, nt, cudaMemcpyHostToDevice, st));
+        total += nh + nt;
+    } else if (format == 0) {
         if (m) k_seq_len<<<grid_for(m), 256, 0, st>>>(R.chr, R.pos, R.id, m, len);
         if (int rc = exclusive_sum(sc, len, off, m + 1)) return rc;
         CKD(cudaMemcpyAsync(&total, off + m, 8, cudaMemcpyDeviceToHost, st));
@@ -388,8 +448,8 @@ int tpc_canonical_image_device(const uint8_t* dev_image, uint64_t image_bytes, v
 // file -> text file (NULL / "-" = stdout): what `graphdump -f seq|group <file>` prints
 int tpc_graphdump_file(const char* image_path, const char* format, const char* out_path) {
     if (!image_path || !format) return set_error("null argument");
-    const uint32_t fmt = !strcmp(format, "seq") ? 0u : !strcmp(format, "group") ? 1u : 2u;
-    if (fmt > 1) return set_error("only the 'seq' and 'group' output formats are produced on the GPU");
+    const uint32_t fmt = !strcmp(format, "seq") ? 0u : !strcmp(format, "group") ? 1u : !strcmp(format, "dot") ? 2u : 3u;
+    if (fmt > 2) return set_error("only the 'seq', 'group' and 'dot' output formats are produced on the GPU");
     FILE* f = fopen(image_path, "rb");
     if (!f) return set_error("Can't open file %s", image_path);
     fseek(f, 0, SEEK_END);
@@ -415,6 +475,11 @@ int tpc_graphdump_file(const char* image_path, const char* format, const char* o
     uint8_t* d_text = nullptr;
     uint64_t tbytes = 0;
     if (rc == 0) rc = tpc_graphdump_device(d_img, bytes, fmt, nullptr, &d_text, &tbytes);
+    if (rc == 0 && std::min<uint64_t>(tbytes, kPiece) > std::min<uint64_t>(std::max<uint64_t>(bytes, 16), kPiece)) {
+        cudaFreeHost(h);   // the text is larger than the image: a larger staging buffer
+        h = nullptr;
+        if (cudaMallocHost(&h, std::min<uint64_t>(tbytes, kPiece)) != cudaSuccess) rc = set_error("out of pinned host memory");
+    }
     if (rc == 0) {
         FILE* o = (!out_path || !strcmp(out_path, "-")) ? stdout : fopen(out_path, "wb");
         if (!o) rc = set_error("Can't create the output file");

@@ -31,6 +31,7 @@ struct Counters {
     unsigned long long overflow;     // insert: probe sequence exhausted
     unsigned long long junctions;    // classify: junctions appended
     unsigned long long dropped;      // classify: dropped by abundance
+    unsigned long long list_incomplete;  // insert from the mark list: regions that had overflowed (pass redone from the mask)
 };
 
 // HyperLogLog sketch (4096 registers) of the candidate k-mers, updated by the query kernels; the
@@ -207,6 +208,76 @@ __device__ __forceinline__ int match_rep(const GenomeView& g, unsigned long long
     return 0;
 }
 
+// One marked occurrence (k-mer X at position p, neighbours prv / nxt, 'N' flags) into the candidate table:
+// find or claim the slot of its canonical k-mer, keep the smallest position, OR the neighbour sets in canonical
+// orientation (candidateoccurence.h:25-50; h:778-796).  k <= 31: key inline in the slot (CAS on the key); else
+// position-identified slot (CAS on tag|position, atomicMin).  Returns false when the mark is not this round's.
+template <int W>
+__device__ __forceinline__ bool insert_occurrence(const GenomeView& g, const KParams& kp, const TableView& T, Counters* ctr, uint64_t p,
+                                                  const Kmer<W>& X, uint32_t prv, uint32_t nxt, bool prv_n, bool nxt_n, bool check_owner,
+                                                  unsigned long long& claimed) {
+    const uint64_t capmask = (1ull << T.log2cap) - 1;
+    const uint64_t probe_limit = capmask < 8192 ? capmask : 8192;  // a longer run means the table is too full: host grows it
+    Occ<W> o;
+    o.X = X;
+    o.Y = revcomp<W>(o.X, kp.k);
+    o.fwd = kmer_less<W>(o.X, o.Y);
+    const Kmer<W> canon = kmer_select<W>(o.fwd, o.X, o.Y);
+    if (check_owner && owner_part(owner_fold<W>(canon, kp.k), kp.nparts) != kp.part) return false;  // marked in another round
+    o.h = kmer_hash<W>(canon, kp.seed);
+    Neigh nb = orient(o.fwd, prv, nxt, prv_n, nxt_n);
+    unsigned long long want = 0;
+    if (!nb.a_n) want |= 1ull << nb.a;
+    if (!nb.b_n) want |= 16ull << nb.b;
+    uint64_t idx = hash_slot(o.h, T.log2cap);
+    Slot* s = nullptr;
+    unsigned long long meta = 0;
+    if (W == 1 && T.inline_keys) {
+        const unsigned long long key1 = canon.w[0] + 1ull;
+        for (uint64_t probe = 0; probe <= probe_limit; ++probe, idx = (idx + 1) & capmask) {
+            Slot* cand = T.slots + idx;
+            ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(cand));
+            if (v.x == 0) {
+                v.x = atomicCAS(&cand->rep, 0ull, key1);
+                if (v.x == 0) { s = cand; ++claimed; v.x = key1; v.y = 0; }
+            }
+            if (v.x == key1) { s = cand; meta = v.y; break; }
+        }
+        if (!s) { atomicAdd(&ctr->overflow, 1ull); return true; }
+        // flags by OR, first position by a CAS-min on the high bits (0 = not yet set)
+        if ((meta & want) != want) meta = atomicOr(&s->meta, want) | want;
+        while ((meta >> kInlinePosShift) == 0 || (meta >> kInlinePosShift) > p) {
+            unsigned long long neu = (meta & ((1ull << kInlinePosShift) - 1)) | ((unsigned long long)p << kInlinePosShift);
+            unsigned long long old = atomicCAS(&s->meta, meta, neu);
+            if (old == meta) break;
+            meta = old;
+        }
+    } else {
+        unsigned long long mine = hash_tag(o.h) | p;
+        for (uint64_t probe = 0; probe <= probe_limit; ++probe, idx = (idx + 1) & capmask) {
+            Slot* cand = T.slots + idx;
+            ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(cand));
+            unsigned long long rep = v.x;
+            if (rep == 0) {
+                rep = atomicCAS(&cand->rep, 0ull, mine);
+                if (rep == 0) { s = cand; ++claimed; break; }
+                v.y = 0;
+            }
+            if ((rep >> kPosBits) == (mine >> kPosBits) && match_rep<W>(g, rep, o, kp.k)) {
+                s = cand; meta = v.y;
+                if (mine < rep) atomicMin(&cand->rep, mine);  // keep the first occurrence
+                break;
+            }
+        }
+        if (!s) { atomicAdd(&ctr->overflow, 1ull); return true; }
+        if ((meta & want) != want) atomicOr(&s->meta, want);
+        if (kp.count_occurrences) atomicAdd(&s->meta, 1ull << kMetaCountShift);
+    }
+    if (nb.a_n) { if (atomicOr(&s->meta, kMetaInN1) & kMetaInN1) atomicOr(&s->meta, kMetaInN2); }
+    if (nb.b_n) { if (atomicOr(&s->meta, kMetaOutN1) & kMetaOutN1) atomicOr(&s->meta, kMetaOutN2); }
+    return true;
+}
+
 // Candidate marks are sparse (a few % of the positions), so the marks of a tile are compacted into a
 // CTA-wide list and inserted one per thread (tpc_tile.cuh).  `op` (optional) selects this round's
 // marks through the ownership planes; without planes ownership is recomputed from the k-mer.
@@ -214,8 +285,6 @@ template <int W>
 __global__ void __launch_bounds__(kTileThreads)
 k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t ntiles, TableView T, Counters* ctr, OwnPlanes op) {
     __shared__ TileStage ts;
-    const uint64_t capmask = (1ull << T.log2cap) - 1;
-    const uint64_t probe_limit = capmask < 8192 ? capmask : 8192;  // a longer run means the table is too full: host grows it
     unsigned long long claimed = 0;
     // this round's marks of a tile (software-pipelined: the next tile's words are requested while this one is processed)
     auto marks_of = [&](uint64_t t) -> uint32_t {
@@ -240,64 +309,40 @@ k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t n
             const uint32_t tp = ts.list[e];
             const uint64_t p = tile * kTilePos + tp;
             const uint32_t lp = tp + tg.c_off, mp = tp + tg.m_off;
-            Occ<W> o;
-            o.X = extract_kmer_smem<W>(s_codes, lp, kp.k);
-            o.Y = revcomp<W>(o.X, kp.k);
-            o.fwd = kmer_less<W>(o.X, o.Y);
-            const Kmer<W> canon = kmer_select<W>(o.fwd, o.X, o.Y);
-            if (!op.n && kp.nparts > 1 && owner_part(owner_fold<W>(canon, kp.k), kp.nparts) != kp.part) continue;  // marked in another round
-            o.h = kmer_hash<W>(canon, kp.seed);
-            Neigh nb = orient(o.fwd, stage_base(s_codes, lp - 1), stage_base(s_codes, lp + kp.k), stage_n(s_nmask, mp - 1), stage_n(s_nmask, mp + kp.k));
-            // neighbour sets in canonical orientation (candidateoccurence.h:25-50; h:778-796)
-            unsigned long long want = 0;
-            if (!nb.a_n) want |= 1ull << nb.a;
-            if (!nb.b_n) want |= 16ull << nb.b;
-            uint64_t idx = hash_slot(o.h, T.log2cap);
-            Slot* s = nullptr;
-            unsigned long long meta = 0;
-            if (W == 1 && T.inline_keys) {
-                const unsigned long long key1 = canon.w[0] + 1ull;
-                for (uint64_t probe = 0; probe <= probe_limit; ++probe, idx = (idx + 1) & capmask) {
-                    Slot* cand = T.slots + idx;
-                    ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(cand));
-                    if (v.x == 0) {
-                        v.x = atomicCAS(&cand->rep, 0ull, key1);
-                        if (v.x == 0) { s = cand; ++claimed; v.x = key1; v.y = 0; }
-                    }
-                    if (v.x == key1) { s = cand; meta = v.y; break; }
-                }
-                if (!s) { atomicAdd(&ctr->overflow, 1ull); continue; }
-                // flags by OR, first position by a CAS-min on the high bits (0 = not yet set)
-                if ((meta & want) != want) meta = atomicOr(&s->meta, want) | want;
-                while ((meta >> kInlinePosShift) == 0 || (meta >> kInlinePosShift) > p) {
-                    unsigned long long neu = (meta & ((1ull << kInlinePosShift) - 1)) | ((unsigned long long)p << kInlinePosShift);
-                    unsigned long long old = atomicCAS(&s->meta, meta, neu);
-                    if (old == meta) break;
-                    meta = old;
-                }
-            } else {
-                unsigned long long mine = hash_tag(o.h) | p;
-                for (uint64_t probe = 0; probe <= probe_limit; ++probe, idx = (idx + 1) & capmask) {
-                    Slot* cand = T.slots + idx;
-                    ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(cand));
-                    unsigned long long rep = v.x;
-                    if (rep == 0) {
-                        rep = atomicCAS(&cand->rep, 0ull, mine);
-                        if (rep == 0) { s = cand; ++claimed; break; }
-                        v.y = 0;
-                    }
-                    if ((rep >> kPosBits) == (mine >> kPosBits) && match_rep<W>(g, rep, o, kp.k)) {
-                        s = cand; meta = v.y;
-                        if (mine < rep) atomicMin(&cand->rep, mine);  // keep the first occurrence
-                        break;
-                    }
-                }
-                if (!s) { atomicAdd(&ctr->overflow, 1ull); continue; }
-                if ((meta & want) != want) atomicOr(&s->meta, want);
-                if (kp.count_occurrences) atomicAdd(&s->meta, 1ull << kMetaCountShift);
-            }
-            if (nb.a_n) { if (atomicOr(&s->meta, kMetaInN1) & kMetaInN1) atomicOr(&s->meta, kMetaInN2); }
-            if (nb.b_n) { if (atomicOr(&s->meta, kMetaOutN1) & kMetaOutN1) atomicOr(&s->meta, kMetaOutN2); }
+            const Kmer<W> X = extract_kmer_smem<W>(s_codes, lp, kp.k);
+            insert_occurrence<W>(g, kp, T, ctr, p, X, stage_base(s_codes, lp - 1), stage_base(s_codes, lp + kp.k),
+                                 stage_n(s_nmask, mp - 1) != 0, stage_n(s_nmask, mp + kp.k) != 0, !op.n && kp.nparts > 1, claimed);
+        }
+    }
+    if (claimed) atomicAdd(&ctr->distinct, claimed);
+}
+
+// The same from the mark list the binned query kernels append to (MarkList, tpc_kernels_common.cuh): when the marks are
+// sparse (hash-range shards: 1/N of them per GPU) walking every mask word and staging every tile costs more than the
+// inserts; here one thread takes one listed position and reads its k-mer straight from the packed genome.
+struct MarkList {
+    unsigned long long* entries;     // [regions][region_cap] positions; region = CTA index of the appending kernel
+    uint32_t* counts;                // [regions] entries appended (may exceed region_cap: the list is then incomplete)
+    uint32_t regions;
+    uint32_t region_cap;
+};
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k_insert_list(GenomeView g, MarkList ml, KParams kp, TableView T, Counters* ctr) {
+    unsigned long long claimed = 0;
+    for (uint32_t r = blockIdx.x; r < ml.regions; r += gridDim.x) {
+        uint32_t n = ml.counts[r];
+        if (n > ml.region_cap) {   // (the host then redoes the pass from the mask)
+            if (threadIdx.x == 0) atomicAdd(&ctr->list_incomplete, 1ull);
+            n = ml.region_cap;
+        }
+        const unsigned long long* e = ml.entries + (uint64_t)r * ml.region_cap;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint64_t p = __ldcs(e + i);
+            const Kmer<W> X = extract_kmer<W>(g.codes, p, kp.k);
+            insert_occurrence<W>(g, kp, T, ctr, p, X, load_base(g.codes, p - 1), load_base(g.codes, p + kp.k),
+                                 load_n(g.nmask, p - 1) != 0, load_n(g.nmask, p + kp.k) != 0, false, claimed);
         }
     }
     if (claimed) atomicAdd(&ctr->distinct, claimed);
@@ -379,17 +424,31 @@ k_ends(GenomeView g, RecordTable rt, KParams kp, TableView J, uint32_t* __restri
     }
 }
 
-// Resolve the candidate mask against the junction index (clears Bloom false positives in
-// place) and count records / stubs per tile.
+// Resolve the candidate mask against the junction index (clears Bloom false positives in place), count
+// records / stubs per tile, and keep the ids that were found: the kept marks of a tile, in position order, go to
+// id_cache[tile_cache_base[tile] ..] (the tile claims that run with one atomicAdd), so that k_emit_write reads
+// 8 sequential bytes per record instead of repeating the random index look-up.
+struct EmitCache {
+    long long* ids;                     // capacity `cap` entries; nullptr = no cache (k_emit_write looks ids up again)
+    unsigned long long* tile_base;      // per tile of the slice: first entry of the tile's run
+    unsigned long long* top;            // bump allocator
+    unsigned long long cap;
+};
+
 template <int W>
 __global__ void __launch_bounds__(kTileThreads)
 k_emit_count(GenomeView g, uint32_t* __restrict__ mask, const uint32_t* __restrict__ stubmask, KParams kp,
              TableView J, uint64_t tile_begin, uint64_t tile_end,
-             unsigned long long* __restrict__ tile_records, unsigned long long* __restrict__ tile_stubs) {
+             unsigned long long* __restrict__ tile_records, unsigned long long* __restrict__ tile_stubs, EmitCache ec) {
     __shared__ unsigned long long red[8];
+    __shared__ unsigned long long warp_tot[8];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (uint64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         uint64_t w = tile * kTileThreads + threadIdx.x;
         uint32_t keep = 0, stub = 0;
+        long long id0 = 0, id1 = 0, id2 = 0, id3 = 0;   // ids of the first kept marks of this word (a word rarely holds more)
+        uint32_t n_ids = 0;
         if (w * 32 < g.npos) {
             uint32_t m = mask[w];
             stub = stubmask[w];
@@ -398,15 +457,56 @@ k_emit_count(GenomeView g, uint32_t* __restrict__ mask, const uint32_t* __restri
                 int i = __ffs(todo) - 1;
                 todo &= todo - 1;
                 Occ<W> o = occurrence_at<W>(g, w * 32 + i, kp);
-                if (lookup_id<W>(g, J, o, kp.k) != 0) keep |= 1u << i;
+                const long long id = lookup_id<W>(g, J, o, kp.k);
+                if (id != 0) {
+                    keep |= 1u << i;
+                    if (n_ids == 0) id0 = id; else if (n_ids == 1) id1 = id; else if (n_ids == 2) id2 = id; else if (n_ids == 3) id3 = id;
+                    ++n_ids;
+                }
             }
             if (keep != m) mask[w] = keep;
         }
-        unsigned long long packed = ((unsigned long long)__popc(stub) << 32) | (unsigned)(__popc(keep) + __popc(stub));
+        const uint32_t n_keep = __popc(keep);
+        unsigned long long packed = ((unsigned long long)__popc(stub) << 32) | (unsigned)(n_keep + __popc(stub));
         unsigned long long t = block_sum(packed, red);
         if (threadIdx.x == 0) {
             tile_records[tile - tile_begin] = t & 0xFFFFFFFFull;
             tile_stubs[tile - tile_begin] = t >> 32;
+        }
+        if (ec.ids) {   // (CTA-uniform)
+            // exclusive scan of the kept marks over the CTA, one run per tile
+            unsigned long long incl = n_keep;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) warp_tot[wid] = incl;
+            if (threadIdx.x == 0) {
+                const unsigned long long n_tile = (t & 0xFFFFFFFFull) - (t >> 32);
+                s_base = n_tile ? atomicAdd(ec.top, n_tile) : 0ull;
+                ec.tile_base[tile - tile_begin] = s_base;
+            }
+            __syncthreads();
+            unsigned long long off = s_base + incl - n_keep;
+            for (int j = 0; j < wid; ++j) off += warp_tot[j];
+            if (n_keep && off + n_keep <= ec.cap) {
+                if (n_ids <= 4) {
+                    ec.ids[off] = id0;
+                    if (n_ids > 1) ec.ids[off + 1] = id1;
+                    if (n_ids > 2) ec.ids[off + 2] = id2;
+                    if (n_ids > 3) ec.ids[off + 3] = id3;
+                } else {   // more than 4 junction occurrences in 32 positions: look the ids up again, in order
+                    uint32_t todo = keep;
+                    while (todo) {
+                        int i = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        Occ<W> o = occurrence_at<W>(g, w * 32 + i, kp);
+                        ec.ids[off++] = lookup_id<W>(g, J, o, kp.k);
+                    }
+                }
+            }
+            __syncthreads();   // s_base / warp_tot are reused by the next tile
         }
     }
 }
@@ -420,7 +520,7 @@ k_emit_write(GenomeView g, const uint32_t* __restrict__ mask, const uint32_t* __
              TableView J, RecordTable rt, uint64_t tile_begin, uint64_t tile_end,
              const unsigned long long* __restrict__ tile_rec_prefix, const unsigned long long* __restrict__ tile_stub_prefix,
              uint64_t records_before, uint64_t stubs_before, uint64_t unit_base, uint64_t first_stub_id,
-             uint32_t* __restrict__ out, uint64_t out_units) {
+             uint32_t* __restrict__ out, uint64_t out_units, EmitCache ec, uint64_t cache_tile_begin) {
     __shared__ unsigned long long warp_tot[8];
     for (uint64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         uint64_t w = tile * kTileThreads + threadIdx.x;
@@ -445,6 +545,12 @@ k_emit_write(GenomeView g, const uint32_t* __restrict__ mask, const uint32_t* __
         uint64_t rec_ord = records_before + tile_rec_prefix[tile - tile_begin] + (excl & 0xFFFFFFFFull);
         uint64_t stub_ord = stubs_before + tile_stub_prefix[tile - tile_begin] + (excl >> 32);
         if (!bits) continue;
+        // cached ids of this thread's junction marks: the tile's run + (records - stubs) before this thread in the tile
+        const long long* cached = nullptr;
+        if (ec.ids) {
+            const unsigned long long at = ec.tile_base[tile - cache_tile_begin] + (excl & 0xFFFFFFFFull) - (excl >> 32);
+            if (at + __popc(m & ~stub) <= ec.cap) cached = ec.ids + at;
+        }
 
         // sequence containing the first position to write (binary search, once per thread)
         uint64_t p_first = w * 32 + (__ffs(bits) - 1);
@@ -463,6 +569,7 @@ k_emit_write(GenomeView g, const uint32_t* __restrict__ mask, const uint32_t* __
             while (p >= c_next) { ++c; c_start = c_next; c_next = (c + 1 < rt.n) ? rt.start[c + 1] : ~0ull; }
             long long id;
             if ((stub >> i) & 1u) id = (long long)(first_stub_id + stub_ord++);
+            else if (cached) id = *cached++;
             else {
                 Occ<W> o = occurrence_at<W>(g, p, kp);
                 id = lookup_id<W>(g, J, o, kp.k);

@@ -200,21 +200,43 @@ k_apply_fill(uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, con
     if (threadIdx.x == 0 && t) atomicAdd(&ctr->filter_new, t);
 }
 
+// a candidate: its mask bit, the sketch of distinct candidates, and (when a list is kept) its position appended to the
+// CTA's region of the mark list -- the count lives in shared memory during the launch
 __device__ __forceinline__ void apply_mark(uint32_t* __restrict__ mask, uint32_t* __restrict__ hll, uint32_t m, uint32_t w1,
-                                           uint32_t relpos, uint32_t sib_bits, uint64_t wave_base, uint64_t slice_first_sector) {
+                                           uint32_t relpos, uint32_t sib_bits, uint64_t wave_base, uint64_t slice_first_sector,
+                                           const MarkList& ml, uint32_t* s_list_count) {
     const uint32_t sib_mask = (1u << sib_bits) - 1u;
     hll_add(hll, m, slice_first_sector | (w1 & sib_mask));
     const uint64_t p = wave_base + (((uint64_t)((w1 & ((1u << kBinCodeShift) - 1u)) >> sib_bits)) << 32) + relpos;
     atomicOr(mask + (p >> 5), 1u << (p & 31));
+    if (ml.entries) {
+        const uint32_t at = atomicAdd(s_list_count, 1u);
+        if (at < ml.region_cap) ml.entries[(uint64_t)blockIdx.x * ml.region_cap + at] = p;
+    }
+}
+__device__ __forceinline__ void mark_list_begin(const MarkList& ml, uint32_t* s_list_count) {
+    if (threadIdx.x == 0) *s_list_count = ml.entries && blockIdx.x < ml.regions ? ml.counts[blockIdx.x] : 0u;
+    __syncthreads();
+}
+__device__ __forceinline__ void mark_list_end(const MarkList& ml, uint32_t* s_list_count) {   // call after a CTA-wide barrier
+    if (threadIdx.x == 0 && ml.entries && blockIdx.x < ml.regions) ml.counts[blockIdx.x] = *s_list_count;
 }
 
 template <int Q>
 __global__ void __launch_bounds__(256, 4)
 k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, const unsigned long long* __restrict__ count,
               uint64_t cap, uint32_t sib_bits, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr,
-              uint32_t* __restrict__ hll, uint64_t slice_first_sector) {
+              uint32_t* __restrict__ hll, uint64_t slice_first_sector, MarkList ml, uint4* __restrict__ zero_dst, uint32_t zero_vec) {
     __shared__ unsigned long long red[8];
     __shared__ ApplyRing ring;
+    __shared__ uint32_t s_list_count;
+    mark_list_begin(ml, &s_list_count);
+    // Another round follows: clear the slice queried by the PREVIOUS launch for it (h:257: every round starts from a
+    // zero-filled filter).  This kernel is bound by the L1 tag stage and leaves HBM idle, so the 64 MiB of streaming
+    // stores are free here, whereas a memset of the whole filter between rounds is not.
+    if (zero_dst)
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < zero_vec; i += gridDim.x * blockDim.x)
+            __stcs(zero_dst + i, make_uint4(0u, 0u, 0u, 0u));
     unsigned long long n64 = *count;
     const uint64_t n = n64 > cap ? cap : n64;
     const uint32_t* __restrict__ rec_b = rec + cap;
@@ -237,7 +259,7 @@ k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ r
         for (int j = 0; j < kApplyU; ++j) {
             const uint32_t m = mask_from_seed<Q>(u4_get(sd, j));
             if (query_sector(s[j], m)) {
-                apply_mark(mask, hll, m, u4_get(w1, j), __ldcs(rec_c + v * kApplyU + j), sib_bits, wave_base, slice_first_sector);
+                apply_mark(mask, hll, m, u4_get(w1, j), __ldcs(rec_c + v * kApplyU + j), sib_bits, wave_base, slice_first_sector, ml, &s_list_count);
                 ++marks;
             }
         }
@@ -247,11 +269,12 @@ k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ r
         const uint32_t w1 = __ldcs(rec_b + i);
         const uint32_t m = mask_from_seed<Q>(__ldcs(rec + i));
         if (query_vertex(slice + ((uint64_t)(w1 & sib_mask) << 3), m)) {
-            apply_mark(mask, hll, m, w1, __ldcs(rec_c + i), sib_bits, wave_base, slice_first_sector);
+            apply_mark(mask, hll, m, w1, __ldcs(rec_c + i), sib_bits, wave_base, slice_first_sector, ml, &s_list_count);
             ++marks;
         }
     }
     unsigned long long t = block_sum(marks, red);
+    mark_list_end(ml, &s_list_count);
     if (threadIdx.x == 0 && t) atomicAdd(&ctr->marks, t);
 }
 
@@ -259,8 +282,10 @@ k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ r
 __global__ void __launch_bounds__(256)
 k_apply_overflow(uint32_t* __restrict__ filter, const uint32_t* __restrict__ ov, const unsigned long long* __restrict__ ov_count,
                  uint64_t ov_cap, uint32_t sib_bits, uint32_t q, int do_query, uint32_t* __restrict__ mask, uint64_t wave_base,
-                 Counters* ctr, uint32_t* __restrict__ hll) {
+                 Counters* ctr, uint32_t* __restrict__ hll, MarkList ml) {
     __shared__ unsigned long long red[8];
+    __shared__ uint32_t s_list_count;
+    mark_list_begin(ml, &s_list_count);
     unsigned long long n = *ov_count;
     if (n > ov_cap) n = ov_cap;
     unsigned long long acc = 0;
@@ -271,11 +296,12 @@ k_apply_overflow(uint32_t* __restrict__ filter, const uint32_t* __restrict__ ov,
         uint32_t m = mask_from_seed_rt(r.x, q);
         if (!do_query) acc += fill_vertex(sec, m, r.y >> kBinCodeShift);
         else if (query_vertex(sec, m)) {
-            apply_mark(mask, hll, m, r.y, r.z, sib_bits, wave_base, (uint64_t)r.w << sib_bits);
+            apply_mark(mask, hll, m, r.y, r.z, sib_bits, wave_base, (uint64_t)r.w << sib_bits, ml, &s_list_count);
             ++acc;
         }
     }
     unsigned long long t = block_sum(acc, red);
+    mark_list_end(ml, &s_list_count);
     if (threadIdx.x == 0 && t) atomicAdd(do_query ? &ctr->marks : &ctr->filter_new, t);
 }
 

@@ -9,6 +9,8 @@ struct Counters;
 struct RecordTable;
 struct BinView;
 struct OwnPlanes;
+struct EmitCache;
+struct MarkList;
 
 struct LaunchCtx {
     cudaStream_t stream;
@@ -31,17 +33,18 @@ struct Launch {
                            uint64_t wave_base, const OwnPlanes* planes);
     static cudaError_t insert(const LaunchCtx&, GenomeView, const uint32_t* mask, KParams, uint64_t ntiles, TableView T, Counters*,
                               const OwnPlanes* planes);
+    static cudaError_t insert_list(const LaunchCtx&, GenomeView, const MarkList&, KParams, TableView T, Counters*);
     static cudaError_t build_index(const LaunchCtx&, GenomeView, const unsigned long long* sorted, uint64_t n, KParams, TableView J);
     static cudaError_t ends(const LaunchCtx&, GenomeView, const RecordTable&, KParams, TableView J, uint32_t* stubmask,
                             uint64_t pos_begin, uint64_t pos_end);
     static cudaError_t emit_count(const LaunchCtx&, GenomeView, uint32_t* mask, const uint32_t* stubmask, KParams, TableView J,
                                   uint64_t tile_begin, uint64_t tile_end, unsigned long long* tile_records,
-                                  unsigned long long* tile_stubs);
+                                  unsigned long long* tile_stubs, const EmitCache&);
     static cudaError_t emit_write(const LaunchCtx&, GenomeView, const uint32_t* mask, const uint32_t* stubmask, KParams,
                                   TableView J, const RecordTable&, uint64_t tile_begin, uint64_t tile_end,
                                   const unsigned long long* tile_rec_prefix, const unsigned long long* tile_stub_prefix,
                                   uint64_t records_before, uint64_t stubs_before, uint64_t unit_base, uint64_t first_stub_id,
-                                  uint32_t* out, uint64_t out_units);
+                                  uint32_t* out, uint64_t out_units, const EmitCache&, uint64_t cache_tile_begin);
     static cudaError_t get_id(const LaunchCtx&, GenomeView, TableView J, KParams, const uint64_t* words, long long* d_out);
 };
 

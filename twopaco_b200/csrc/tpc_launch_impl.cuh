@@ -127,6 +127,15 @@ cudaError_t Launch<W>::insert(const LaunchCtx& c, GenomeView g, const uint32_t* 
 }
 
 template <int W>
+cudaError_t Launch<W>::insert_list(const LaunchCtx& c, GenomeView g, const MarkList& ml, KParams kp, TableView T, Counters* ctr) {
+    if (ml.regions == 0) return cudaSuccess;
+    int grid = persistent_grid(k_insert_list<W>, 256, c.sm_count, ml.regions);
+    k_insert_list<W><<<grid, 256, 0, c.stream>>>(g, ml, kp, T, ctr);
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+template <int W>
 cudaError_t Launch<W>::build_index(const LaunchCtx& c, GenomeView g, const unsigned long long* sorted, uint64_t n, KParams kp,
                                    TableView J) {
     if (n == 0) return cudaSuccess;
@@ -149,10 +158,10 @@ cudaError_t Launch<W>::ends(const LaunchCtx& c, GenomeView g, const RecordTable&
 template <int W>
 cudaError_t Launch<W>::emit_count(const LaunchCtx& c, GenomeView g, uint32_t* mask, const uint32_t* stubmask, KParams kp,
                                   TableView J, uint64_t tile_begin, uint64_t tile_end, unsigned long long* tile_records,
-                                  unsigned long long* tile_stubs) {
+                                  unsigned long long* tile_stubs, const EmitCache& ec) {
     if (tile_end <= tile_begin) return cudaSuccess;
     int grid = persistent_grid(k_emit_count<W>, kTileThreads, c.sm_count, tile_end - tile_begin);
-    k_emit_count<W><<<grid, kTileThreads, 0, c.stream>>>(g, mask, stubmask, kp, J, tile_begin, tile_end, tile_records, tile_stubs);
+    k_emit_count<W><<<grid, kTileThreads, 0, c.stream>>>(g, mask, stubmask, kp, J, tile_begin, tile_end, tile_records, tile_stubs, ec);
     ++*c.launches;
     return cudaGetLastError();
 }
@@ -162,12 +171,12 @@ cudaError_t Launch<W>::emit_write(const LaunchCtx& c, GenomeView g, const uint32
                                   TableView J, const RecordTable& rt, uint64_t tile_begin, uint64_t tile_end,
                                   const unsigned long long* tile_rec_prefix, const unsigned long long* tile_stub_prefix,
                                   uint64_t records_before, uint64_t stubs_before, uint64_t unit_base, uint64_t first_stub_id,
-                                  uint32_t* out, uint64_t out_units) {
+                                  uint32_t* out, uint64_t out_units, const EmitCache& ec, uint64_t cache_tile_begin) {
     if (tile_end <= tile_begin) return cudaSuccess;
     int grid = persistent_grid(k_emit_write<W>, kTileThreads, c.sm_count, tile_end - tile_begin);
     k_emit_write<W><<<grid, kTileThreads, 0, c.stream>>>(g, mask, stubmask, kp, J, rt, tile_begin, tile_end, tile_rec_prefix,
                                                         tile_stub_prefix, records_before, stubs_before, unit_base,
-                                                        first_stub_id, out, out_units);
+                                                        first_stub_id, out, out_units, ec, cache_tile_begin);
     ++*c.launches;
     return cudaGetLastError();
 }

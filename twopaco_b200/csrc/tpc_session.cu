@@ -176,20 +176,23 @@ cudaError_t launch_apply_fill(const LaunchCtx& c, uint32_t* filter, const BinVie
     return cudaGetLastError();
 }
 
-cudaError_t launch_apply_query(const LaunchCtx& c, const uint32_t* filter, const BinView& bv, uint32_t bucket, uint32_t* mask,
-                               uint64_t wave_base, Counters* ctr, uint32_t* hll) {
+// zero_previous: also clear the slice of bucket - 1 (queried by the previous launch) for the next round
+cudaError_t launch_apply_query(const LaunchCtx& c, uint32_t* filter, const BinView& bv, uint32_t bucket, uint32_t* mask,
+                               uint64_t wave_base, Counters* ctr, uint32_t* hll, const MarkList& ml, bool zero_previous) {
     const uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
+    uint4* zero_dst = zero_previous && bucket > 0 ? reinterpret_cast<uint4*>(filter + (((uint64_t)(bucket - 1) << bv.sib_bits) << 3)) : nullptr;
+    const uint32_t zero_vec = (uint32_t)(((uint64_t)32 << bv.sib_bits) / 16);
     TPC_APPLY_Q_SWITCH(bv.q, (k_apply_query<Q><<<apply_grid(c), 256, 0, c.stream>>>(
         slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap, bv.sib_bits, mask, wave_base, ctr, hll,
-        (uint64_t)bucket << bv.sib_bits)));
+        (uint64_t)bucket << bv.sib_bits, ml, zero_dst, zero_vec)));
     ++*c.launches;
     return cudaGetLastError();
 }
 
 cudaError_t launch_apply_overflow(const LaunchCtx& c, uint32_t* filter, const BinView& bv, int do_query, uint32_t* mask,
-                                  uint64_t wave_base, Counters* ctr, uint32_t* hll) {
+                                  uint64_t wave_base, Counters* ctr, uint32_t* hll, const MarkList& ml) {
     k_apply_overflow<<<c.sm_count, 256, 0, c.stream>>>(filter, bv.ov, bv.ov_count, bv.ov_cap, bv.sib_bits, bv.q, do_query, mask,
-                                                       wave_base, ctr, hll);
+                                                       wave_base, ctr, hll, ml);
     ++*c.launches;
     return cudaGetLastError();
 }
@@ -245,6 +248,13 @@ struct tpc_session {
     unsigned long long* d_tile_stub = nullptr;
     unsigned long long* d_scan_scratch = nullptr;
     uint64_t tile_cap = 0;
+    // ids found by emit_count, kept for emit_write (k_emit_count): one run per tile of the slice
+    long long* d_id_cache = nullptr;
+    unsigned long long* d_cache_tile_base = nullptr;   // [tile_cap] + the bump allocator's top at [tile_cap]
+    uint64_t id_cache_cap = 0;
+    EmitCache emit_cache() const {
+        return EmitCache{d_id_cache, d_cache_tile_base, d_cache_tile_base ? d_cache_tile_base + tile_cap : nullptr, id_cache_cap};
+    }
     uint64_t slice_tile_begin = 0, slice_tile_end = 0, slice_pos_begin = 0, slice_pos_end = 0;
     uint64_t slice_records = 0, slice_stubs = 0;
     bool have_candidates = false, have_index = false, have_count = false;
@@ -266,7 +276,7 @@ struct tpc_session {
     // (apply kernels: bound by L2 / L1-tag traffic, few instructions) round r+1 is BINNED into the other
     // on a second stream (k_bin_list: bound by the integer pipes, little memory traffic), each kernel
     // capped to a share of the SM so that both are resident.  The query of round r runs alone afterwards.
-    int pipe_env = 1;               // env TPC_PIPELINE=0 disables
+    int pipe_env = 0;               // env TPC_PIPELINE=1 enables (not the default: see choose_sub_rounds)
     // CTAs per SM while both run (the register file holds four 256-thread CTAs of these kernels).  Measured at C3
     // on one GPU: 2+2 gains nothing (both kernels also share the LSU / L1 data path: binning 355 ms instead of
     // 226 ms alone), 3+1 turns 640 ms per step into 593 ms.
@@ -276,6 +286,16 @@ struct tpc_session {
     BinView pipe_view[2]{};
     long long pipe_round[2] = {-1, -1};   // round whose records a half holds
     cudaEvent_t pipe_ev[6]{};       // [0,1] half binned  [2] main-stream marker  [3,4] bin start/stop (timing)
+
+    // mark list (MarkList, tpc_kernels.cuh): positions of the candidates the binned query kernels found, appended per CTA;
+    // the exact pass reads it instead of walking the whole mask when the marks are sparse
+    unsigned long long* d_marklist = nullptr;
+    uint32_t* d_marklist_counts = nullptr;
+    uint32_t marklist_regions = 0, marklist_region_cap = 0;
+    bool marklist_valid = false;    // every mark of the current insert group went through the binned query kernels
+    MarkList mark_list(bool enabled) const {
+        return MarkList{enabled ? d_marklist : nullptr, d_marklist_counts, marklist_regions, marklist_region_cap};
+    }
 
     // hash sub-ranges processed in sequence by this GPU: the user's -r times the sub-rounds chosen so
     // that one round's records fit HBM in one wave (choose_sub_rounds); ownership planes of all of
@@ -393,7 +413,7 @@ void tpc_session_destroy(tpc_session* s) {
     cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_codes, s->d_nmask, s->d_rec_start, s->d_rec_len, s->d_sep_before, s->d_filter, s->d_mask,
                     s->d_stubmask, s->d_T, s->d_J, s->d_local, s->d_sorted, s->d_sort_tmp, s->d_ctr, s->d_id,
-                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch, s->d_bin_rec, s->d_bin_count, s->d_bin_ov, s->d_hll, s->d_own_extra};
+                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch, s->d_id_cache, s->d_cache_tile_base, s->d_marklist, s->d_marklist_counts, s->d_bin_rec, s->d_bin_count, s->d_bin_ov, s->d_hll, s->d_own_extra};
     for (void* p : ptrs)
         dev_free(p, s->stream);
     cudaStreamSynchronize(s->stream);
@@ -552,21 +572,19 @@ static uint32_t choose_sub_rounds(tpc_session* s) {
     uint32_t S1 = 8;
     for (uint32_t S = 1; S <= 8; ++S)
         if (fits(S, 1)) { S1 = S; break; }
-    if (can_pipe && s->prm.rounds * S1 >= 2) {   // several rounds anyway: overlap them, with two half-size scratches
-        // Pipelining hides the fill of all rounds but the last behind the binning, and pays for it with extra
-        // sub-rounds (two scratches must fit), each one more pass of k_bin_list over the ownership planes and the
-        // genome of ALL positions, whatever share of them the GPU owns.  Per position, measured at C3 (k = 25):
-        // fill 7.8 ps per owned record, one k_bin_list pass 1.9 ps.  1 GPU (3 -> 5 sub-rounds): 640 -> 586 ms per
-        // step; 2 GPUs (2 -> 3 or 4 sub-rounds): 321 -> 344 / 350 ms -- so only when the model predicts a clear gain.
-        for (uint32_t S = S1; S <= 2 * S1 && S <= 12; ++S) {
-            const double rounds_now = (double)s->prm.rounds * S;
-            const double hidden = 7.8 / s->prm.shard_count * (rounds_now - 1.0) / rounds_now;
-            const double extra = 1.9 * s->prm.rounds * (double)(S - S1);
-            if (rounds_now >= 3 && hidden - extra > 1.0 && own_planes_for(s->prm.rounds * S) > 0 && fits(S, 2)) {
+    // k_bin_list stages the owned positions of an 8192-position tile 2048 (or 1024) at a time: a share of 1/3 would run
+    // a full and a one-third-full staging round per tile (measured at C3 on one GPU: 3 sub-rounds bin in 241 ms, 4 in
+    // 218 ms), so the split is rounded up to a power of two -- whole stages for every tile, whatever the input
+    while (S1 & (S1 - 1)) ++S1;
+    if (can_pipe && s->prm.rounds * S1 >= 2) {
+        // Pipelined rounds (opt-in, TPC_PIPELINE=1): two half-size scratches, round r+1 binned beside the fill of round r.
+        // Measured at C3 on one GPU the overlap gains nothing any more (the fill is bound by L2 atomic throughput and loses
+        // as much as the binning hides: 590 ms pipelined with 5 sub-rounds, 580 ms in sequence with 4), hence not the default.
+        for (uint32_t S = S1; S <= 2 * S1 && S <= 12; ++S)
+            if (s->prm.rounds * S >= 2 && own_planes_for(s->prm.rounds * S) > 0 && fits(S, 2)) {
                 s->pipe = true;
                 return S;
             }
-        }
     }
     return S1;
 }
@@ -657,7 +675,7 @@ static int binned_release(tpc_session* s) {
 // Filter passes of one round through the binned path.  Returns -1 when the binned path does not
 // apply and -2 when a slice overflowed beyond the overflow area (then the caller uses k_fill /
 // k_query), 0 on success, >0 on error.
-static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin, float* ms_fill, float* ms_query) {
+static int filter_passes_binned(tpc_session* s, const KParams& kp, bool clear_for_next, float* ms_bin, float* ms_fill, float* ms_query) {
     if (int rc = binned_setup(s, kp)) return rc;
     LaunchCtx lc = s->lctx();
     const BinView bv = s->bin_view;
@@ -710,11 +728,15 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
                 if (int brc = bin_range(t0, t1, base)) return brc;
             }
             CK(cudaEventRecord(e1, s->stream));
+            const bool zero = pass == 1 && wv + 1 == nwaves && clear_for_next;   // last readers of the slices in this round
+            // (the overflow records touch any slice: their query runs before the slices are cleared)
+            if (pass == 1) CK(launch_apply_overflow(lc, s->d_filter, bv, 1, s->d_mask, base, s->d_ctr, s->d_hll, s->mark_list(true)));
             for (uint32_t b = 0; b < buckets; ++b) {
                 if (pass == 0) CK(launch_apply_fill(lc, s->d_filter, bv, b, s->d_ctr));
-                else CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, base, s->d_ctr, s->d_hll));
+                else CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, base, s->d_ctr, s->d_hll, s->mark_list(true), zero));
             }
-            CK(launch_apply_overflow(lc, s->d_filter, bv, pass, s->d_mask, base, s->d_ctr, s->d_hll));
+            if (pass == 0) CK(launch_apply_overflow(lc, s->d_filter, bv, 0, s->d_mask, base, s->d_ctr, s->d_hll, s->mark_list(false)));
+            if (zero) CK(cudaMemsetAsync(s->d_filter + (((uint64_t)(buckets - 1) << bv.sib_bits) << 3), 0, (uint64_t)32 << bv.sib_bits, s->stream));
             CK(cudaEventRecord(e2, s->stream));
             rc = finish_wave(ms_bin, pass == 0 ? ms_fill : ms_query);
         }
@@ -749,7 +771,7 @@ static int bin_whole_round(tpc_session* s, const LaunchCtx& lc, const KParams& k
 
 // Filter passes of round r (of rounds_eff) with the next round's binning overlapped (see tpc_session::pipe).
 // Same return convention as filter_passes_binned.
-static int filter_passes_pipelined(tpc_session* s, uint32_t r, const KParams& kp, float* ms_bin, float* ms_fill, float* ms_query) {
+static int filter_passes_pipelined(tpc_session* s, uint32_t r, const KParams& kp, bool clear_for_next, float* ms_bin, float* ms_fill, float* ms_query) {
     if (int rc = binned_setup(s, kp)) return rc;
     if (!s->pipe) return -3;   // the scratch could not be split after all: caller uses the one-scratch path
     const int h = (int)(r & 1);
@@ -784,12 +806,14 @@ static int filter_passes_pipelined(tpc_session* s, uint32_t r, const KParams& kp
         lc.apply_ctas = s->pipe_fill_ctas;   // share the SMs with the binning kernel
     }
     for (uint32_t b = 0; b < buckets; ++b) CK(launch_apply_fill(lc, s->d_filter, bv, b, s->d_ctr));
-    CK(launch_apply_overflow(lc, s->d_filter, bv, 0, s->d_mask, 0, s->d_ctr, s->d_hll));
+    CK(launch_apply_overflow(lc, s->d_filter, bv, 0, s->d_mask, 0, s->d_ctr, s->d_hll, s->mark_list(false)));
     CK(cudaEventRecord(e2, s->stream));
     if (has_next) CK(cudaStreamWaitEvent(s->stream, s->pipe_ev[h ^ 1], 0));   // the query runs alone, at full occupancy
     lc.apply_ctas = s->apply_ctas;
-    for (uint32_t b = 0; b < buckets; ++b) CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, 0, s->d_ctr, s->d_hll));
-    CK(launch_apply_overflow(lc, s->d_filter, bv, 1, s->d_mask, 0, s->d_ctr, s->d_hll));
+    CK(launch_apply_overflow(lc, s->d_filter, bv, 1, s->d_mask, 0, s->d_ctr, s->d_hll, s->mark_list(true)));   // before any slice is cleared
+    for (uint32_t b = 0; b < buckets; ++b)
+        CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, 0, s->d_ctr, s->d_hll, s->mark_list(true), clear_for_next));
+    if (clear_for_next) CK(cudaMemsetAsync(s->d_filter + (((uint64_t)(buckets - 1) << bv.sib_bits) << 3), 0, (uint64_t)32 << bv.sib_bits, s->stream));
     CK(cudaEventRecord(e3, s->stream));
     unsigned long long ov_now = 0;
     CK(cudaMemcpyAsync(&ov_now, bv.ov_count, 8, cudaMemcpyDeviceToHost, s->stream));
@@ -837,6 +861,21 @@ int tpc_session_find_candidates(tpc_session* s) {
     };
     float ms_bin = 0, ms_fill = 0, ms_query = 0, ms_insert = 0, ms_classify = 0;
     Counters prev{}, cur{};
+    // mark list: room for npos / 32 / shards candidates (C3: 1.5 % of the positions are marks); a denser input
+    // overflows it and the exact pass walks the mask instead
+    if (binned_applies(s, nullptr) && !(getenv("TPC_MARK_LIST") && atoi(getenv("TPC_MARK_LIST")) == 0)) {
+        const uint32_t regions = (uint32_t)s->sm_count * 4;
+        uint64_t cap = s->g.npos / 32 / s->prm.shard_count + (1u << 20);
+        if (const char* e = getenv("TPC_MARK_LIST_CAP")) cap = (uint64_t)atoll(e);   // (tests: a list that overflows)
+        const uint32_t region_cap = (uint32_t)std::min<uint64_t>((cap + regions - 1) / regions, 0x7FFFFFFFu);
+        if (!s->d_marklist || regions != s->marklist_regions || region_cap != s->marklist_region_cap) {
+            if (s->d_marklist) CK(dev_free(s->d_marklist, s->stream));
+            if (s->d_marklist_counts) CK(dev_free(s->d_marklist_counts, s->stream));
+            CK(dev_alloc(&s->d_marklist, (uint64_t)regions * region_cap * 8, s->stream));
+            CK(dev_alloc(&s->d_marklist_counts, regions * 4, s->stream));
+            s->marklist_regions = regions; s->marklist_region_cap = region_cap;
+        }
+    }
     CK(cudaStreamSynchronize(s->stream));  // the allocations above are visible to available_bytes()
     vlog("buffers allocated, mask cleared", -1);
     s->sub_rounds = choose_sub_rounds(s);
@@ -863,16 +902,25 @@ int tpc_session_find_candidates(tpc_session* s) {
     // (one table, sized from the HyperLogLog sketch accumulated over the sub-rounds) replaces one scan per
     // sub-round.  With -r > 1 the table stays per round, as in the reference (h:337-338).
     const bool merge_insert = s->prm.rounds == 1 && s->sub_rounds > 1;
+    bool filter_clean = false;
     for (uint32_t r = 0; r < s->rounds_eff; ++r) {
         KParams kp = s->kparams(s->prm.shard_index * s->rounds_eff + r);
         const Counters round_start = cur;
         CK(cudaEventRecord(s->ev[0], s->stream));
-        CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));  // h:257: zero-filled each round
-        if (!merge_insert || r == 0) CK(cudaMemsetAsync(s->d_hll, 0, 4u << kHllBits, s->stream));
+        // h:257: zero-filled each round -- by the previous round's query kernels when they were the binned ones
+        if (!filter_clean) CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));
+        filter_clean = false;
+        const bool clear_for_next = r + 1 < s->rounds_eff;
+        if (!merge_insert || r == 0) {
+            CK(cudaMemsetAsync(s->d_hll, 0, 4u << kHllBits, s->stream));
+            if (s->d_marklist) CK(cudaMemsetAsync(s->d_marklist_counts, 0, s->marklist_regions * 4, s->stream));
+            s->marklist_valid = s->d_marklist != nullptr;
+        }
         float b_bin = 0, b_fill = 0, b_query = 0;
-        int brc = s->pipe ? filter_passes_pipelined(s, r, kp, &b_bin, &b_fill, &b_query) : -3;
-        if (brc == -3) brc = filter_passes_binned(s, kp, &b_bin, &b_fill, &b_query);
+        int brc = s->pipe ? filter_passes_pipelined(s, r, kp, clear_for_next, &b_bin, &b_fill, &b_query) : -3;
+        if (brc == -3) brc = filter_passes_binned(s, kp, clear_for_next, &b_bin, &b_fill, &b_query);
         if (brc > 0) return brc;
+        filter_clean = brc == 0 && clear_for_next;
         if (brc == -2) {  // redo this round from scratch; marks already set are true marks and may stay
             CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));
             CK(cudaMemcpyAsync(s->d_ctr, &round_start, sizeof round_start, cudaMemcpyHostToDevice, s->stream));
@@ -881,6 +929,7 @@ int tpc_session_find_candidates(tpc_session* s) {
         }
         if (int wrc = wait_genome(s, s->ntiles)) return wrc;
         if (brc < 0) {
+            s->marklist_valid = false;   // the direct query kernel marks the mask only
             CK(W_DISPATCH(s, fill(lc, s->g, s->d_filter, kp, s->ntiles, s->d_ctr)));
             CK(cudaEventRecord(s->ev[1], s->stream));
             CK(W_DISPATCH(s, query(lc, s->g, s->d_filter, kp, s->ntiles, s->d_mask, r > 0 || brc == -2, s->d_ctr, s->d_hll)));
@@ -943,16 +992,24 @@ int tpc_session_find_candidates(tpc_session* s) {
             const bool planes_ok = !merge_insert && brc == 0 && s->own_shared && kp.nparts > 1 && s->own_done_tiles >= s->ntiles;
             KParams kpi = kp;
             if (merge_insert) kpi.nparts = 1;   // every mark in the mask belongs to this pass
-            CK(W_DISPATCH(s, insert(lc, s->g, s->d_mask, kpi, s->ntiles, TableView{s->d_T, lg, s->inline_keys()}, s->d_ctr,
-                                    planes_ok ? &iop : nullptr)));
+            // sparse marks that all went through the binned query kernels: insert from the mark list; else walk the mask
+            const uint64_t list_cap = (uint64_t)s->marklist_regions * s->marklist_region_cap;
+            const bool force_list = getenv("TPC_MARK_LIST_FORCE") != nullptr;   // (tests: the overflow -> redo path)
+            const bool from_list = s->marklist_valid && (marks_r * 10 <= list_cap * 8 || force_list);
+            if (from_list) CK(W_DISPATCH(s, insert_list(lc, s->g, s->mark_list(true), kpi, TableView{s->d_T, lg, s->inline_keys()}, s->d_ctr)));
+            else CK(W_DISPATCH(s, insert(lc, s->g, s->d_mask, kpi, s->ntiles, TableView{s->d_T, lg, s->inline_keys()}, s->d_ctr,
+                                         planes_ok ? &iop : nullptr)));
             CK(cudaEventRecord(s->ev[3], s->stream));
             CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
             CK(cudaStreamSynchronize(s->stream));
-            vlog("insert done", (int)r);
-            if (cur.overflow == prev.overflow && (cur.distinct - prev.distinct) * 10 <= (7ull << lg)) break;
+            vlog(from_list ? "insert (mark list) done" : "insert (mask) done", (int)r);
+            const bool list_bad = cur.list_incomplete != prev.list_incomplete;   // a region had overflowed: redo from the mask
+            if (list_bad) s->marklist_valid = false;
+            if (!list_bad && cur.overflow == prev.overflow && (cur.distinct - prev.distinct) * 10 <= (7ull << lg)) break;
             // estimate too low (cannot happen within HLL's error bars, but stay exact): grow and redo
             Counters redo = cur;
-            redo.distinct = prev.distinct; redo.overflow = prev.overflow;
+            redo.distinct = prev.distinct; redo.overflow = prev.overflow; redo.list_incomplete = prev.list_incomplete;
+            if (list_bad) --lg;   // same table size, other source
             CK(cudaMemcpyAsync(s->d_ctr, &redo, sizeof redo, cudaMemcpyHostToDevice, s->stream));
             cur = redo;
             ++lg;
@@ -1054,22 +1111,39 @@ int tpc_session_emit_count(tpc_session* s, uint64_t pos_begin, uint64_t pos_end,
     if (pos_begin >= pos_end) te = tb;   // empty slice (more shards than tiles)
     uint64_t nt = te - tb;
     if (nt + 1 > s->tile_cap) {
-        for (void* p : {(void*)s->d_tile_rec, (void*)s->d_tile_stub, (void*)s->d_scan_scratch})
+        for (void* p : {(void*)s->d_tile_rec, (void*)s->d_tile_stub, (void*)s->d_scan_scratch, (void*)s->d_cache_tile_base})
             if (p) CK(dev_free(p, s->stream));
-        s->d_tile_rec = s->d_tile_stub = s->d_scan_scratch = nullptr;
+        s->d_tile_rec = s->d_tile_stub = s->d_scan_scratch = s->d_cache_tile_base = nullptr;
+        CK(dev_alloc(&s->d_cache_tile_base, (nt + 2) * 8, s->stream));
         CK(dev_alloc(&s->d_tile_rec, (nt + 1) * 8, s->stream));
         CK(dev_alloc(&s->d_tile_stub, (nt + 1) * 8, s->stream));
         CK(dev_alloc(&s->d_scan_scratch, scan_scratch_items(nt + 1) * 8, s->stream));
         s->tile_cap = nt + 1;
     }
     CK(cudaEventRecord(s->ev[7], s->stream));
-    CK(cudaMemsetAsync(s->d_stubmask, 0, std::max<uint64_t>(s->ntiles * kTileThreads, 1) * 4, s->stream));
+    if (te > tb) CK(cudaMemsetAsync(s->d_stubmask + tb * kTileThreads, 0, (te - tb) * kTileThreads * 4, s->stream));   // (only the slice is read)
     CK(cudaMemsetAsync(s->d_tile_rec + nt, 0, 8, s->stream));
     CK(cudaMemsetAsync(s->d_tile_stub + nt, 0, 8, s->stream));
     KParams kp = s->kparams(0);
     TableView J{s->d_J, s->J_log2, s->inline_keys()};
+    {   // id cache: room for the marks of the slice.  Single GPU: the shard's mark count bounds it; sharded: the slice holds
+        // about 1/N of every shard's marks -- whatever does not fit is looked up again by emit_write (never wrong)
+        uint64_t want = s->st.candidate_marks + 1024;
+        if (s->prm.shard_count > 1) want = want + want / 4 + (1u << 20);
+        if (getenv("TPC_EMIT_CACHE") && atoi(getenv("TPC_EMIT_CACHE")) == 0) want = 0;   // (tests: the look-up path of emit_write)
+        else if (const char* e = getenv("TPC_EMIT_CACHE_CAP")) want = (uint64_t)atoll(e);  // (tests: a cache that overflows)
+        if (want > s->id_cache_cap || want == 0) {
+            if (s->d_id_cache) CK(dev_free(s->d_id_cache, s->stream));
+            s->d_id_cache = nullptr; s->id_cache_cap = 0;
+            if (want && want * 8 < available_bytes(s->device) / 2) {
+                CK(dev_alloc(&s->d_id_cache, want * 8, s->stream));
+                s->id_cache_cap = want;
+            }
+        }
+        CK(cudaMemsetAsync(s->d_cache_tile_base + s->tile_cap, 0, 8, s->stream));
+    }
     CK(W_DISPATCH(s, ends(lc, s->g, s->rtable(), kp, J, s->d_stubmask, pos_begin, pos_end)));
-    CK(W_DISPATCH(s, emit_count(lc, s->g, s->d_mask, s->d_stubmask, kp, J, tb, te, s->d_tile_rec, s->d_tile_stub)));
+    CK(W_DISPATCH(s, emit_count(lc, s->g, s->d_mask, s->d_stubmask, kp, J, tb, te, s->d_tile_rec, s->d_tile_stub, s->emit_cache())));
     CK(launch_scan_exclusive(lc, s->d_tile_rec, nt + 1, s->d_scan_scratch));
     CK(launch_scan_exclusive(lc, s->d_tile_stub, nt + 1, s->d_scan_scratch));
     unsigned long long tot[2];
@@ -1109,7 +1183,7 @@ int tpc_session_emit_write(tpc_session* s, uint64_t records_before, uint64_t stu
     TableView J{s->d_J, s->J_log2, s->inline_keys()};
     CK(W_DISPATCH(s, emit_write(lc, s->g, s->d_mask, s->d_stubmask, kp, J, s->rtable(), s->slice_tile_begin, s->slice_tile_end,
                                 s->d_tile_rec, s->d_tile_stub, records_before, stubs_before, unit_base,
-                                s->J_count + TPC_STUB_ID_OFFSET, (uint32_t*)dev_out, units)));
+                                s->J_count + TPC_STUB_ID_OFFSET, (uint32_t*)dev_out, units, s->emit_cache(), s->slice_tile_begin)));
     CK(cudaEventRecord(s->ev[8], s->stream));
     s->st.occurrences = s->slice_records;
     s->st.stubs = s->slice_stubs;
@@ -1196,7 +1270,7 @@ static int emit_write_parts(tpc_session* s, uint8_t* d_out, uint64_t image_bytes
     for (uint32_t i = 0; i < parts; ++i) {
         CK(W_DISPATCH(s, emit_write(lc, s->g, s->d_mask, s->d_stubmask, kp, J, s->rtable(), bt[i], bt[i + 1],
                                     s->d_tile_rec + (bt[i] - tb), s->d_tile_stub + (bt[i] - tb), 0, 0, unit_base,
-                                    s->J_count + TPC_STUB_ID_OFFSET, (uint32_t*)d_out, units)));
+                                    s->J_count + TPC_STUB_ID_OFFSET, (uint32_t*)d_out, units, s->emit_cache(), s->slice_tile_begin)));
         uint64_t pos_hi = std::min<uint64_t>(bt[i + 1] * kTilePos, s->slice_pos_end);
         uint64_t byte_hi = i + 1 == parts ? units * 12 : (pref[i + 1] + emit_prev_at(s, pos_hi) - unit_base) * 12;
         if (int rc = on_part(byte_lo, byte_hi)) return rc;

@@ -10,14 +10,36 @@
 #ifndef TWOPACO_B200_VERTEX_ENUMERATOR_H_
 #define TWOPACO_B200_VERTEX_ENUMERATOR_H_
 
+#include <algorithm>
+#include <climits>
+#include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
+#include <numeric>
 #include <ostream>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
+// The reference's header also makes its src/common helpers visible to its includers (constructor.cpp, test.cpp use
+// DnaChar and JunctionPositionReader through it, vertexenumerator.h:12-19); inside the reference tree those files stay.
+#if defined(__has_include)
+#if __has_include(<junctionapi.h>)
+#include <junctionapi.h>
+#endif
+#if __has_include(<dnachar.h>)
+#include <dnachar.h>
+#endif
+#endif
+
+#if defined(__has_include) && __has_include("twopaco_b200.h")
+#include "twopaco_b200.h"
+#else
 #include "../../include/twopaco_b200.h"
+#endif
 
 namespace TwoPaCo
 {
