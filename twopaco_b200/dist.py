@@ -91,9 +91,12 @@ def sharded_run(session, genome, rank: int, world: int, out=None):
     shard_index=rank, shard_count=world and already holds the genome).  Returns
     (info dict, device output buffer holding this rank's contiguous slice of the de_bruijn.bin
     image at bytes [slice_offset, slice_offset + slice_bytes))."""
+    import time
     from . import api
     s = session
+    t0 = time.perf_counter()
     s.find_candidates()
+    t_find = time.perf_counter()
     ptr, n = s.local_junctions()
     ms_x = {}
     if world == 1:
@@ -119,10 +122,15 @@ def sharded_run(session, genome, rank: int, world: int, out=None):
         if ev:   # (emit_count has synchronised the stream)
             ms_x = {"ms_allgather_junctions": round(ev[0].elapsed_time(ev[1]), 3),
                     "ms_reduce_scatter_masks": round(ev[2].elapsed_time(ev[3]), 3)}
+    t_count = time.perf_counter()
     need = 12 * (nrec + len(genome.rec_len)) + 16
     if out is None or out.nbytes < need:
         out = api.DeviceBuffer(need)
     off, nb = s.emit_write(rb, sb, out.ptr, out.nbytes)
+    t_end = time.perf_counter()
+    # host wall clock of the phases (find_candidates and the count exchange end with a synchronisation; emit_write is enqueued)
+    ms_x.update(wall_ms_find_candidates=round((t_find - t0) * 1e3, 3), wall_ms_exchange_index_count=round((t_count - t_find) * 1e3, 3),
+                wall_ms_emit_write_enqueue=round((t_end - t_count) * 1e3, 3))
     info = dict(junctions=nj, records=trec, stubs=tstub, slice_offset=off, slice_bytes=nb,
                 image_bytes=nb if world == 1 else None, **ms_x)
     return info, out
