@@ -678,10 +678,9 @@ def test_reference_cli_sources_compile_and_run_against_the_library(tmp_path, gol
 
 
 @pytest.mark.parametrize("name", ["family_k25", "family_k63", "family_seam_k25"])
-def test_mark_list_and_emit_id_cache_variants(name, golden, monkeypatch):
-    """The exact pass reads the candidates from the mark list the binned query kernels append to (sparse marks) or walks the
-    mask (list switched off, or overflowed -> pass redone from the mask); emit_write takes the ids emit_count cached or looks
-    them up again (cache off / too small).  Every combination must give the same bytes."""
+def test_mark_list_variants(name, golden, monkeypatch):
+    """The exact pass reads the candidates from the mark list the binned query kernels append to (sparse marks: hash-range
+    shards) or walks the mask (list off, or overflowed -> pass redone from the mask).  Same bytes either way."""
     spec, g = CASES[name], golden[name]
     with case_files(spec) as (paths, _, _):
         recs = api.read_fasta(paths)
@@ -691,9 +690,10 @@ def test_mark_list_and_emit_id_cache_variants(name, golden, monkeypatch):
     base, st0 = api.junctions_host(gen, k=spec["k"], filter_bits=22, q=5)
     base = bytes(base)
     assert canon_md5(base) == g["canon_md5"] and st0.ms_bin > 0
-    for env in ({"TPC_MARK_LIST": "0"}, {"TPC_MARK_LIST_CAP": "600"}, {"TPC_EMIT_CACHE": "0"}, {"TPC_EMIT_CACHE_CAP": "37"},
-                {"TPC_MARK_LIST_CAP": "600", "TPC_SUBROUNDS": "3"}, {"TPC_MARK_LIST": "0", "TPC_EMIT_CACHE_CAP": "1"},
-                {"TPC_MARK_LIST_CAP": "600", "TPC_MARK_LIST_FORCE": "1"}, {"TPC_MARK_LIST_CAP": "1200", "TPC_MARK_LIST_FORCE": "1", "TPC_SUBROUNDS": "2"}):
+    for env in ({"TPC_MARK_LIST": "0"}, {"TPC_MARK_LIST": "1"}, {"TPC_MARK_LIST": "1", "TPC_MARK_LIST_CAP": "600"},
+                {"TPC_MARK_LIST": "1", "TPC_MARK_LIST_FORCE": "1", "TPC_SUBROUNDS": "3"},
+                {"TPC_MARK_LIST": "1", "TPC_MARK_LIST_CAP": "600", "TPC_MARK_LIST_FORCE": "1"},
+                {"TPC_MARK_LIST": "1", "TPC_MARK_LIST_CAP": "1200", "TPC_MARK_LIST_FORCE": "1", "TPC_SUBROUNDS": "2"}):
         for k_, v in env.items():
             monkeypatch.setenv(k_, v)
         img, st = api.junctions_host(gen, k=spec["k"], filter_bits=22, q=5)

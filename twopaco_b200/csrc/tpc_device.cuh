@@ -48,11 +48,12 @@ struct TableView {
     Slot* slots;
     uint32_t log2cap;
     // Inline keys (k <= 31 only): the canonical k-mer (< 2^62) fits the slot, so lookups never
-    // touch the genome.  T slot = {key + 1, flags(0..11) | first position << 24}
+    // touch the genome.  T slot = {key + 1, flags(0..11) | (first position << 1 | its k-mer is on the canonical strand) << 23}
     //                    J slot = {key + 1 | first occurrence is on the canonical strand << 63, id}
+    // (the J slot's first word is also the "junction key" exchanged beside the position when the genome is windowed)
     uint32_t inline_keys;
 };
-constexpr int kInlinePosShift = 24;
+constexpr int kInlinePosShift = 23;
 
 struct KParams {
     uint32_t k;

@@ -306,8 +306,10 @@ int tpc_build(const char* const* fasta_paths, size_t n_files, uint32_t k, uint32
     uint32_t gpus = 1;
     if (rc == 0) {
         const uint32_t visible = tpc_visible_gpus();
-        if (const char* e = getenv("TPC_GPUS")) gpus = std::max(1, atoi(e));
-        else if (plan.n_positions >= (1ull << 27)) gpus = visible;
+        // creating the NCCL communicators takes seconds (measured: 5.6 s for 2 GPUs), more than one GPU needs for 20 Gbp, so
+        // several GPUs are opt-in (TPC_GPUS=<n>, 0 = all visible) unless one GPU cannot hold the input at all
+        if (const char* e = getenv("TPC_GPUS")) gpus = atoi(e) > 0 ? (uint32_t)atoi(e) : visible;
+        else if (plan.n_positions >= (1ull << 37)) gpus = visible;
         gpus = std::max<uint32_t>(1, std::min(gpus, visible));
         int cur = 0;
         cudaGetDevice(&cur);

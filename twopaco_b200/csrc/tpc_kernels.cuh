@@ -98,10 +98,10 @@ __device__ __forceinline__ bool query_vertex(const uint32_t* sec, uint32_t m) {
 
 template <int W, int Q>
 __global__ void __launch_bounds__(kTileThreads)
-k_fill(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t ntiles, Counters* ctr) {
+k_fill(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t tile_begin, uint64_t ntiles, Counters* ctr) {
     __shared__ unsigned long long red[8];
     unsigned long long fresh = 0;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (uint64_t tile = tile_begin + blockIdx.x; tile < ntiles; tile += gridDim.x) {
         uint64_t w = tile * kTileThreads + threadIdx.x;
         if (w * 32 >= g.npos) continue;
         Window<W> win;
@@ -134,11 +134,11 @@ k_fill(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t ntiles,
 // ------------------------------------------------------------------------------------------
 template <int W, int Q>
 __global__ void __launch_bounds__(kTileThreads)
-k_query(GenomeView g, const uint32_t* __restrict__ filter, KParams kp, uint64_t ntiles,
+k_query(GenomeView g, const uint32_t* __restrict__ filter, KParams kp, uint64_t tile_begin, uint64_t ntiles,
         uint32_t* __restrict__ mask, int accumulate, Counters* ctr, uint32_t* __restrict__ hll) {
     __shared__ unsigned long long red[8];
     unsigned long long marks = 0;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (uint64_t tile = tile_begin + blockIdx.x; tile < ntiles; tile += gridDim.x) {
         uint64_t w = tile * kTileThreads + threadIdx.x;
         if (w * 32 >= g.npos) continue;
         Window<W> win;
@@ -244,10 +244,11 @@ __device__ __forceinline__ bool insert_occurrence(const GenomeView& g, const KPa
             if (v.x == key1) { s = cand; meta = v.y; break; }
         }
         if (!s) { atomicAdd(&ctr->overflow, 1ull); return true; }
-        // flags by OR, first position by a CAS-min on the high bits (0 = not yet set)
+        // flags by OR, first position (with the strand of its occurrence) by a CAS-min on the high bits (0 = not yet set)
         if ((meta & want) != want) meta = atomicOr(&s->meta, want) | want;
-        while ((meta >> kInlinePosShift) == 0 || (meta >> kInlinePosShift) > p) {
-            unsigned long long neu = (meta & ((1ull << kInlinePosShift) - 1)) | ((unsigned long long)p << kInlinePosShift);
+        const unsigned long long field = ((unsigned long long)p << 1) | (o.fwd ? 1ull : 0ull);
+        while ((meta >> kInlinePosShift) == 0 || (meta >> kInlinePosShift) > field) {
+            unsigned long long neu = (meta & ((1ull << kInlinePosShift) - 1)) | (field << kInlinePosShift);
             unsigned long long old = atomicCAS(&s->meta, meta, neu);
             if (old == meta) break;
             meta = old;
@@ -283,7 +284,7 @@ __device__ __forceinline__ bool insert_occurrence(const GenomeView& g, const KPa
 // marks through the ownership planes; without planes ownership is recomputed from the k-mer.
 template <int W>
 __global__ void __launch_bounds__(kTileThreads)
-k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t ntiles, TableView T, Counters* ctr, OwnPlanes op) {
+k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t tile_begin, uint64_t ntiles, TableView T, Counters* ctr, OwnPlanes op) {
     __shared__ TileStage ts;
     unsigned long long claimed = 0;
     // this round's marks of a tile (software-pipelined: the next tile's words are requested while this one is processed)
@@ -293,7 +294,7 @@ k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t n
         if (op.n) m &= own_word(op, w);
         return m;
     };
-    uint64_t tile = blockIdx.x;
+    uint64_t tile = tile_begin + blockIdx.x;
     uint32_t m_next = 0;
     int buf = 0;
     if (tile < ntiles) { m_next = marks_of(tile); tile_request(ts, g, tile, 0); }
@@ -370,6 +371,31 @@ k_build_index(GenomeView g, const unsigned long long* __restrict__ sorted_pos, u
     }
 }
 
+// every position that starts a definite k-mer (emit without a candidate mask: the windowed runs test all of them
+// against the junction index)
+template <int W>
+__global__ void __launch_bounds__(kTileThreads)
+k_valid_mask(GenomeView g, KParams kp, uint64_t word_begin, uint64_t word_end, uint32_t* __restrict__ mask) {
+    for (uint64_t w = word_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < word_end; w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t valid = 0;
+        if (w * 32 < g.npos) {
+            valid = ~0u;
+            if (w == 0 || any_n(g.nmask, w * 32, 32 + kp.k)) {
+                valid = 0;
+                uint32_t run = 0;
+#pragma unroll 1
+                for (uint32_t j = 0; j + 1 < kp.k; ++j) run = load_n(g.nmask, w * 32 + j) ? 0 : run + 1;
+#pragma unroll 1
+                for (uint32_t i = 0; i < 32; ++i) {
+                    run = load_n(g.nmask, w * 32 + i + kp.k - 1) ? 0 : run + 1;
+                    if (run >= kp.k) valid |= 1u << i;
+                }
+            }
+        }
+        mask[w] = valid;
+    }
+}
+
 // -> signed id (+ same strand as the first occurrence, - opposite; bifurcationstorage.h:100-128),
 // 0 when the k-mer is not a junction
 template <int W>
@@ -424,31 +450,17 @@ k_ends(GenomeView g, RecordTable rt, KParams kp, TableView J, uint32_t* __restri
     }
 }
 
-// Resolve the candidate mask against the junction index (clears Bloom false positives in place), count
-// records / stubs per tile, and keep the ids that were found: the kept marks of a tile, in position order, go to
-// id_cache[tile_cache_base[tile] ..] (the tile claims that run with one atomicAdd), so that k_emit_write reads
-// 8 sequential bytes per record instead of repeating the random index look-up.
-struct EmitCache {
-    long long* ids;                     // capacity `cap` entries; nullptr = no cache (k_emit_write looks ids up again)
-    unsigned long long* tile_base;      // per tile of the slice: first entry of the tile's run
-    unsigned long long* top;            // bump allocator
-    unsigned long long cap;
-};
-
+// Resolve the candidate mask against the junction index (clears Bloom false positives in
+// place) and count records / stubs per tile.
 template <int W>
 __global__ void __launch_bounds__(kTileThreads)
 k_emit_count(GenomeView g, uint32_t* __restrict__ mask, const uint32_t* __restrict__ stubmask, KParams kp,
              TableView J, uint64_t tile_begin, uint64_t tile_end,
-             unsigned long long* __restrict__ tile_records, unsigned long long* __restrict__ tile_stubs, EmitCache ec) {
+             unsigned long long* __restrict__ tile_records, unsigned long long* __restrict__ tile_stubs) {
     __shared__ unsigned long long red[8];
-    __shared__ unsigned long long warp_tot[8];
-    __shared__ unsigned long long s_base;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (uint64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         uint64_t w = tile * kTileThreads + threadIdx.x;
         uint32_t keep = 0, stub = 0;
-        long long id0 = 0, id1 = 0, id2 = 0, id3 = 0;   // ids of the first kept marks of this word (a word rarely holds more)
-        uint32_t n_ids = 0;
         if (w * 32 < g.npos) {
             uint32_t m = mask[w];
             stub = stubmask[w];
@@ -457,56 +469,15 @@ k_emit_count(GenomeView g, uint32_t* __restrict__ mask, const uint32_t* __restri
                 int i = __ffs(todo) - 1;
                 todo &= todo - 1;
                 Occ<W> o = occurrence_at<W>(g, w * 32 + i, kp);
-                const long long id = lookup_id<W>(g, J, o, kp.k);
-                if (id != 0) {
-                    keep |= 1u << i;
-                    if (n_ids == 0) id0 = id; else if (n_ids == 1) id1 = id; else if (n_ids == 2) id2 = id; else if (n_ids == 3) id3 = id;
-                    ++n_ids;
-                }
+                if (lookup_id<W>(g, J, o, kp.k) != 0) keep |= 1u << i;
             }
             if (keep != m) mask[w] = keep;
         }
-        const uint32_t n_keep = __popc(keep);
-        unsigned long long packed = ((unsigned long long)__popc(stub) << 32) | (unsigned)(n_keep + __popc(stub));
+        unsigned long long packed = ((unsigned long long)__popc(stub) << 32) | (unsigned)(__popc(keep) + __popc(stub));
         unsigned long long t = block_sum(packed, red);
         if (threadIdx.x == 0) {
             tile_records[tile - tile_begin] = t & 0xFFFFFFFFull;
             tile_stubs[tile - tile_begin] = t >> 32;
-        }
-        if (ec.ids) {   // (CTA-uniform)
-            // exclusive scan of the kept marks over the CTA, one run per tile
-            unsigned long long incl = n_keep;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (lane == 31) warp_tot[wid] = incl;
-            if (threadIdx.x == 0) {
-                const unsigned long long n_tile = (t & 0xFFFFFFFFull) - (t >> 32);
-                s_base = n_tile ? atomicAdd(ec.top, n_tile) : 0ull;
-                ec.tile_base[tile - tile_begin] = s_base;
-            }
-            __syncthreads();
-            unsigned long long off = s_base + incl - n_keep;
-            for (int j = 0; j < wid; ++j) off += warp_tot[j];
-            if (n_keep && off + n_keep <= ec.cap) {
-                if (n_ids <= 4) {
-                    ec.ids[off] = id0;
-                    if (n_ids > 1) ec.ids[off + 1] = id1;
-                    if (n_ids > 2) ec.ids[off + 2] = id2;
-                    if (n_ids > 3) ec.ids[off + 3] = id3;
-                } else {   // more than 4 junction occurrences in 32 positions: look the ids up again, in order
-                    uint32_t todo = keep;
-                    while (todo) {
-                        int i = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        Occ<W> o = occurrence_at<W>(g, w * 32 + i, kp);
-                        ec.ids[off++] = lookup_id<W>(g, J, o, kp.k);
-                    }
-                }
-            }
-            __syncthreads();   // s_base / warp_tot are reused by the next tile
         }
     }
 }
@@ -520,7 +491,7 @@ k_emit_write(GenomeView g, const uint32_t* __restrict__ mask, const uint32_t* __
              TableView J, RecordTable rt, uint64_t tile_begin, uint64_t tile_end,
              const unsigned long long* __restrict__ tile_rec_prefix, const unsigned long long* __restrict__ tile_stub_prefix,
              uint64_t records_before, uint64_t stubs_before, uint64_t unit_base, uint64_t first_stub_id,
-             uint32_t* __restrict__ out, uint64_t out_units, EmitCache ec, uint64_t cache_tile_begin) {
+             uint32_t* __restrict__ out, uint64_t out_units) {
     __shared__ unsigned long long warp_tot[8];
     for (uint64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         uint64_t w = tile * kTileThreads + threadIdx.x;
@@ -545,12 +516,6 @@ k_emit_write(GenomeView g, const uint32_t* __restrict__ mask, const uint32_t* __
         uint64_t rec_ord = records_before + tile_rec_prefix[tile - tile_begin] + (excl & 0xFFFFFFFFull);
         uint64_t stub_ord = stubs_before + tile_stub_prefix[tile - tile_begin] + (excl >> 32);
         if (!bits) continue;
-        // cached ids of this thread's junction marks: the tile's run + (records - stubs) before this thread in the tile
-        const long long* cached = nullptr;
-        if (ec.ids) {
-            const unsigned long long at = ec.tile_base[tile - cache_tile_begin] + (excl & 0xFFFFFFFFull) - (excl >> 32);
-            if (at + __popc(m & ~stub) <= ec.cap) cached = ec.ids + at;
-        }
 
         // sequence containing the first position to write (binary search, once per thread)
         uint64_t p_first = w * 32 + (__ffs(bits) - 1);
@@ -569,7 +534,6 @@ k_emit_write(GenomeView g, const uint32_t* __restrict__ mask, const uint32_t* __
             while (p >= c_next) { ++c; c_start = c_next; c_next = (c + 1 < rt.n) ? rt.start[c + 1] : ~0ull; }
             long long id;
             if ((stub >> i) & 1u) id = (long long)(first_stub_id + stub_ord++);
-            else if (cached) id = *cached++;
             else {
                 Occ<W> o = occurrence_at<W>(g, p, kp);
                 id = lookup_id<W>(g, J, o, kp.k);

@@ -15,7 +15,7 @@ __device__ __forceinline__ bool meta_is_junction(unsigned long long meta) {
 // TrueBifurcations (h:1228-1256): junction && Count <= abundance -> append its word
 __global__ void __launch_bounds__(256)
 k_classify(TableView T, uint64_t abundance, uint32_t use_abundance, unsigned long long* __restrict__ out,
-           uint64_t out_cap, Counters* ctr) {
+           unsigned long long* __restrict__ out_keys /* inline tables only; may be null */, uint64_t out_cap, Counters* ctr) {
     uint64_t cap = 1ull << T.log2cap;
     const int lane = threadIdx.x & 31;
     // whole warps iterate together (the bound is rounded up to a warp), so every shuffle below is full-mask
@@ -36,7 +36,29 @@ k_classify(TableView T, uint64_t abundance, uint32_t use_abundance, unsigned lon
         base = __shfl_sync(0xffffffffu, base, leader);
         if (take) {
             unsigned long long at = base + __popc(ballot & ((1u << lane) - 1));
-            if (at < out_cap) out[at] = T.inline_keys ? (v.y >> kInlinePosShift) : (v.x & kPosMask);
+            if (at < out_cap) {
+                out[at] = T.inline_keys ? (v.y >> (kInlinePosShift + 1)) : (v.x & kPosMask);
+                if (out_keys) out_keys[at] = v.x | (((v.y >> kInlinePosShift) & 1ull) << 63);   // the J slot's first word
+            }
+        }
+    }
+}
+
+// junction index J (bifurcationstorage.h:27-66).  The same from the junction keys themselves ({canonical k-mer + 1 | strand of the first occurrence << 63}, in the
+// order of the sorted first positions): no genome access -- the windowed runs, whose genome is not resident.
+__global__ void __launch_bounds__(256)
+k_build_index_keys(const unsigned long long* __restrict__ sorted_keys, uint64_t n, KParams kp, TableView J) {
+    const uint64_t capmask = (1ull << J.log2cap) - 1;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long mine = sorted_keys[i];
+        Kmer<1> canon;
+        canon.w[0] = (mine & ~(1ull << 63)) - 1ull;
+        const uint64_t h = kmer_hash<1>(canon, kp.seed);
+        for (uint64_t idx = hash_slot(h, J.log2cap);; idx = (idx + 1) & capmask) {
+            if (atomicCAS(&J.slots[idx].rep, 0ull, mine) == 0ull) {
+                J.slots[idx].meta = i + 1;
+                break;
+            }
         }
     }
 }

@@ -33,22 +33,34 @@ static int persistent_grid(Kern kern, int threads, int sm_count, uint64_t work_i
     }
 
 template <int W>
-cudaError_t Launch<W>::fill(const LaunchCtx& c, GenomeView g, uint32_t* filter, KParams kp, uint64_t ntiles, Counters* ctr) {
+cudaError_t Launch<W>::fill(const LaunchCtx& c, GenomeView g, uint32_t* filter, KParams kp, uint64_t tile_begin, uint64_t tile_end,
+                            Counters* ctr) {
+    if (tile_end <= tile_begin) return cudaSuccess;
     TPC_Q_SWITCH(kp.q, {
-        int grid = persistent_grid(k_fill<W, Q>, kTileThreads, c.sm_count, ntiles);
-        k_fill<W, Q><<<grid, kTileThreads, 0, c.stream>>>(g, filter, kp, ntiles, ctr);
+        int grid = persistent_grid(k_fill<W, Q>, kTileThreads, c.sm_count, tile_end - tile_begin);
+        k_fill<W, Q><<<grid, kTileThreads, 0, c.stream>>>(g, filter, kp, tile_begin, tile_end, ctr);
     });
     ++*c.launches;
     return cudaGetLastError();
 }
 
 template <int W>
-cudaError_t Launch<W>::query(const LaunchCtx& c, GenomeView g, const uint32_t* filter, KParams kp, uint64_t ntiles,
+cudaError_t Launch<W>::query(const LaunchCtx& c, GenomeView g, const uint32_t* filter, KParams kp, uint64_t tile_begin, uint64_t tile_end,
                              uint32_t* mask, int accumulate, Counters* ctr, uint32_t* hll) {
+    if (tile_end <= tile_begin) return cudaSuccess;
     TPC_Q_SWITCH(kp.q, {
-        int grid = persistent_grid(k_query<W, Q>, kTileThreads, c.sm_count, ntiles);
-        k_query<W, Q><<<grid, kTileThreads, 0, c.stream>>>(g, filter, kp, ntiles, mask, accumulate, ctr, hll);
+        int grid = persistent_grid(k_query<W, Q>, kTileThreads, c.sm_count, tile_end - tile_begin);
+        k_query<W, Q><<<grid, kTileThreads, 0, c.stream>>>(g, filter, kp, tile_begin, tile_end, mask, accumulate, ctr, hll);
     });
+    ++*c.launches;
+    return cudaGetLastError();
+}
+
+template <int W>
+cudaError_t Launch<W>::valid_mask(const LaunchCtx& c, GenomeView g, KParams kp, uint64_t tile_begin, uint64_t tile_end, uint32_t* mask) {
+    if (tile_end <= tile_begin) return cudaSuccess;
+    int grid = persistent_grid(k_valid_mask<W>, kTileThreads, c.sm_count, tile_end - tile_begin);
+    k_valid_mask<W><<<grid, kTileThreads, 0, c.stream>>>(g, kp, tile_begin * kTileThreads, tile_end * kTileThreads, mask);
     ++*c.launches;
     return cudaGetLastError();
 }
@@ -115,13 +127,13 @@ cudaError_t Launch<W>::bin(const LaunchCtx& c, GenomeView g, KParams kp, const B
 }
 
 template <int W>
-cudaError_t Launch<W>::insert(const LaunchCtx& c, GenomeView g, const uint32_t* mask, KParams kp, uint64_t ntiles, TableView T,
-                              Counters* ctr, const OwnPlanes* planes) {
-    if (ntiles == 0) return cudaSuccess;
+cudaError_t Launch<W>::insert(const LaunchCtx& c, GenomeView g, const uint32_t* mask, KParams kp, uint64_t tile_begin, uint64_t tile_end,
+                              TableView T, Counters* ctr, const OwnPlanes* planes) {
+    if (tile_end <= tile_begin) return cudaSuccess;
     OwnPlanes op{};
     if (planes) op = *planes;
-    int grid = persistent_grid(k_insert<W>, kTileThreads, c.sm_count, ntiles);
-    k_insert<W><<<grid, kTileThreads, 0, c.stream>>>(g, mask, kp, ntiles, T, ctr, op);
+    int grid = persistent_grid(k_insert<W>, kTileThreads, c.sm_count, tile_end - tile_begin);
+    k_insert<W><<<grid, kTileThreads, 0, c.stream>>>(g, mask, kp, tile_begin, tile_end, T, ctr, op);
     ++*c.launches;
     return cudaGetLastError();
 }
@@ -158,10 +170,10 @@ cudaError_t Launch<W>::ends(const LaunchCtx& c, GenomeView g, const RecordTable&
 template <int W>
 cudaError_t Launch<W>::emit_count(const LaunchCtx& c, GenomeView g, uint32_t* mask, const uint32_t* stubmask, KParams kp,
                                   TableView J, uint64_t tile_begin, uint64_t tile_end, unsigned long long* tile_records,
-                                  unsigned long long* tile_stubs, const EmitCache& ec) {
+                                  unsigned long long* tile_stubs) {
     if (tile_end <= tile_begin) return cudaSuccess;
     int grid = persistent_grid(k_emit_count<W>, kTileThreads, c.sm_count, tile_end - tile_begin);
-    k_emit_count<W><<<grid, kTileThreads, 0, c.stream>>>(g, mask, stubmask, kp, J, tile_begin, tile_end, tile_records, tile_stubs, ec);
+    k_emit_count<W><<<grid, kTileThreads, 0, c.stream>>>(g, mask, stubmask, kp, J, tile_begin, tile_end, tile_records, tile_stubs);
     ++*c.launches;
     return cudaGetLastError();
 }
@@ -171,12 +183,12 @@ cudaError_t Launch<W>::emit_write(const LaunchCtx& c, GenomeView g, const uint32
                                   TableView J, const RecordTable& rt, uint64_t tile_begin, uint64_t tile_end,
                                   const unsigned long long* tile_rec_prefix, const unsigned long long* tile_stub_prefix,
                                   uint64_t records_before, uint64_t stubs_before, uint64_t unit_base, uint64_t first_stub_id,
-                                  uint32_t* out, uint64_t out_units, const EmitCache& ec, uint64_t cache_tile_begin) {
+                                  uint32_t* out, uint64_t out_units) {
     if (tile_end <= tile_begin) return cudaSuccess;
     int grid = persistent_grid(k_emit_write<W>, kTileThreads, c.sm_count, tile_end - tile_begin);
     k_emit_write<W><<<grid, kTileThreads, 0, c.stream>>>(g, mask, stubmask, kp, J, rt, tile_begin, tile_end, tile_rec_prefix,
                                                         tile_stub_prefix, records_before, stubs_before, unit_base,
-                                                        first_stub_id, out, out_units, ec, cache_tile_begin);
+                                                        first_stub_id, out, out_units);
     ++*c.launches;
     return cudaGetLastError();
 }

@@ -14,6 +14,7 @@
 // libtwopaco_b200.so has no link-time dependency on it (single-GPU use never touches it).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -219,6 +220,13 @@ static int shard_worker(MultiImpl* mi, Shared* sh, int r, const tpc_params& base
     Nccl& nc = Nccl::get();
     const int N = sh->n;
     int rc = 0;
+    const bool verbose = getenv("TPC_VERBOSE") != nullptr && r == 0;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto vlog = [&](const char* what) {
+        if (verbose)
+            fprintf(stderr, "[tpc multi, GPU 0 of %d] +%9.3f ms  %s\n", N,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), what);
+    };
     cudaStream_t st = nullptr, h2d = nullptr, ag = nullptr;
     uint64_t *d_codes = nullptr, *d_nmask = nullptr;
     unsigned long long* d_allj = nullptr;
@@ -238,11 +246,13 @@ static int shard_worker(MultiImpl* mi, Shared* sh, int r, const tpc_params& base
         // ---- 0. the whole packed genome on this GPU, chunk by chunk
         const uint64_t* codes = src.dev0_codes;
         const uint64_t* nmask = src.dev0_nmask;
-        if (own_genome) {
-            CKM(cudaMalloc(&d_codes, plan.device_words(0, N) * 8));
-            CKM(cudaMalloc(&d_nmask, plan.device_words(1, N) * 8));
+        if (own_genome) {   // (stream-ordered: the device's pool keeps the memory between runs)
+            CKM(cudaMallocAsync((void**)&d_codes, plan.device_words(0, N) * 8, st));
+            CKM(cudaMallocAsync((void**)&d_nmask, plan.device_words(1, N) * 8, st));
+            CKM(cudaStreamSynchronize(st));
             codes = d_codes; nmask = d_nmask;
         }
+        vlog("streams + genome arrays ready");
         uint64_t* full[2] = {const_cast<uint64_t*>(codes), const_cast<uint64_t*>(nmask)};
         const uint64_t* host_arr[2] = {src.host ? src.host->codes : nullptr, src.host ? src.host->n_mask : nullptr};
         for (size_t c = 0; c < plan.tile_begin.size(); ++c) {
@@ -282,10 +292,13 @@ static int shard_worker(MultiImpl* mi, Shared* sh, int r, const tpc_params& base
         if (own_genome)
             for (size_t c = 0; c < plan.tile_begin.size(); ++c)
                 if (int e = tpc_session_add_genome_event(s, plan.tile_begin[c], ev_chunk[c])) return e;
+        vlog("upload / all-gather enqueued, session ready");
         return tpc_session_find_candidates(s);
     };
     rc = body();
+    vlog("find_candidates done");
     if (!sh->sync_ok(r, rc)) return rc;
+    vlog("all shards done");
 
     // ---- 1. all-gather of the shards' junction words
     const uint64_t* words = nullptr;
@@ -319,6 +332,7 @@ static int shard_worker(MultiImpl* mi, Shared* sh, int r, const tpc_params& base
         return 0;
     };
     rc = exchange();
+    vlog("junction all-gather, index, mask reduce-scatter, emit count done");
     if (!sh->sync_ok(r, rc)) return rc;
     uint64_t rb = 0, sb = 0;
     for (int i = 0; i < r; ++i) { rb += sh->nrec[i]; sb += sh->nstub[i]; }
@@ -374,6 +388,7 @@ static int shard_worker(MultiImpl* mi, Shared* sh, int r, const tpc_params& base
         return tpc_session_stats(s, &sh->stats[r]);
     };
     rc = emit();
+    vlog("emit + copy-out done");
     if (r == N - 1 && image_bytes_out && rc == 0) *image_bytes_out = sh->slice_off[r] + sh->slice_bytes[r];
     const bool ok = sh->sync_ok(r, rc);
 
@@ -386,8 +401,9 @@ static int shard_worker(MultiImpl* mi, Shared* sh, int r, const tpc_params& base
     const bool keep = ok && keep_session0 && r == 0;
     if (s && !keep) { tpc_session_destroy(s); sh->session[r] = nullptr; }
     if (!keep) {
-        if (d_codes) cudaFree(d_codes);
-        if (d_nmask) cudaFree(d_nmask);
+        if (d_codes) cudaFreeAsync(d_codes, st);
+        if (d_nmask) cudaFreeAsync(d_nmask, st);
+        if (st) cudaStreamSynchronize(st);
     }
     for (auto e : ev_chunk) cudaEventDestroy(e);
     for (auto e : ev_tmp) cudaEventDestroy(e);
@@ -396,6 +412,7 @@ static int shard_worker(MultiImpl* mi, Shared* sh, int r, const tpc_params& base
     if (st && !keep) cudaStreamDestroy(st);   // (a kept session keeps using its stream)
     if (h2d) cudaStreamDestroy(h2d);
     if (ag) cudaStreamDestroy(ag);
+    vlog("released");
     return rc;
 }
 

@@ -119,10 +119,10 @@ static uint64_t available_bytes(int device) {
 // W-independent launchers
 // ---------------------------------------------------------------------------------------------
 cudaError_t launch_classify(const LaunchCtx& c, TableView T, uint64_t abundance, uint32_t use_abundance,
-                            unsigned long long* out, uint64_t out_cap, Counters* ctr) {
+                            unsigned long long* out, unsigned long long* out_keys, uint64_t out_cap, Counters* ctr) {
     uint64_t cap = 1ull << T.log2cap;
     uint64_t blocks = std::min<uint64_t>((cap + 255) / 256, (uint64_t)c.sm_count * 8);
-    k_classify<<<(int)blocks, 256, 0, c.stream>>>(T, abundance, use_abundance, out, out_cap, ctr);
+    k_classify<<<(int)blocks, 256, 0, c.stream>>>(T, abundance, use_abundance, out, out_keys, out_cap, ctr);
     ++*c.launches;
     return cudaGetLastError();
 }
@@ -248,13 +248,6 @@ struct tpc_session {
     unsigned long long* d_tile_stub = nullptr;
     unsigned long long* d_scan_scratch = nullptr;
     uint64_t tile_cap = 0;
-    // ids found by emit_count, kept for emit_write (k_emit_count): one run per tile of the slice
-    long long* d_id_cache = nullptr;
-    unsigned long long* d_cache_tile_base = nullptr;   // [tile_cap] + the bump allocator's top at [tile_cap]
-    uint64_t id_cache_cap = 0;
-    EmitCache emit_cache() const {
-        return EmitCache{d_id_cache, d_cache_tile_base, d_cache_tile_base ? d_cache_tile_base + tile_cap : nullptr, id_cache_cap};
-    }
     uint64_t slice_tile_begin = 0, slice_tile_end = 0, slice_pos_begin = 0, slice_pos_end = 0;
     uint64_t slice_records = 0, slice_stubs = 0;
     bool have_candidates = false, have_index = false, have_count = false;
@@ -413,7 +406,7 @@ void tpc_session_destroy(tpc_session* s) {
     cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_codes, s->d_nmask, s->d_rec_start, s->d_rec_len, s->d_sep_before, s->d_filter, s->d_mask,
                     s->d_stubmask, s->d_T, s->d_J, s->d_local, s->d_sorted, s->d_sort_tmp, s->d_ctr, s->d_id,
-                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch, s->d_id_cache, s->d_cache_tile_base, s->d_marklist, s->d_marklist_counts, s->d_bin_rec, s->d_bin_count, s->d_bin_ov, s->d_hll, s->d_own_extra};
+                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch, s->d_marklist, s->d_marklist_counts, s->d_bin_rec, s->d_bin_count, s->d_bin_ov, s->d_hll, s->d_own_extra};
     for (void* p : ptrs)
         dev_free(p, s->stream);
     cudaStreamSynchronize(s->stream);
@@ -861,9 +854,19 @@ int tpc_session_find_candidates(tpc_session* s) {
     };
     float ms_bin = 0, ms_fill = 0, ms_query = 0, ms_insert = 0, ms_classify = 0;
     Counters prev{}, cur{};
-    // mark list: room for npos / 32 / shards candidates (C3: 1.5 % of the positions are marks); a denser input
-    // overflows it and the exact pass walks the mask instead
-    if (binned_applies(s, nullptr) && !(getenv("TPC_MARK_LIST") && atoi(getenv("TPC_MARK_LIST")) == 0)) {
+    // Mark list: room for npos / 32 / shards candidates (C3: 1.5 % of the positions are marks); a denser input overflows
+    // it and the exact pass walks the mask instead.  Reading the k-mer of a listed position is a random access into the
+    // packed genome, walking the mask stages whole tiles: measured at C3 the list wins below one mark per ~128 positions
+    // (4 and more hash-range shards: 13 -> 4 ms on 8 GPUs) and loses above (one GPU: 22 -> 36 ms), so it is kept for
+    // 4 and more shards only (TPC_MARK_LIST=0 / 1 overrides).
+    const char* ml_env = getenv("TPC_MARK_LIST");
+    const bool want_list = ml_env ? atoi(ml_env) != 0 : s->prm.shard_count >= 4;
+    if (!want_list && s->d_marklist) {
+        CK(dev_free(s->d_marklist, s->stream));
+        CK(dev_free(s->d_marklist_counts, s->stream));
+        s->d_marklist = nullptr; s->d_marklist_counts = nullptr; s->marklist_regions = 0;
+    }
+    if (binned_applies(s, nullptr) && want_list) {
         const uint32_t regions = (uint32_t)s->sm_count * 4;
         uint64_t cap = s->g.npos / 32 / s->prm.shard_count + (1u << 20);
         if (const char* e = getenv("TPC_MARK_LIST_CAP")) cap = (uint64_t)atoll(e);   // (tests: a list that overflows)
@@ -910,7 +913,7 @@ int tpc_session_find_candidates(tpc_session* s) {
         // h:257: zero-filled each round -- by the previous round's query kernels when they were the binned ones
         if (!filter_clean) CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));
         filter_clean = false;
-        const bool clear_for_next = r + 1 < s->rounds_eff;
+        const bool clear_for_next = r + 1 < s->rounds_eff && !(getenv("TPC_QUERY_ZERO") && atoi(getenv("TPC_QUERY_ZERO")) == 0);
         if (!merge_insert || r == 0) {
             CK(cudaMemsetAsync(s->d_hll, 0, 4u << kHllBits, s->stream));
             if (s->d_marklist) CK(cudaMemsetAsync(s->d_marklist_counts, 0, s->marklist_regions * 4, s->stream));
@@ -930,9 +933,9 @@ int tpc_session_find_candidates(tpc_session* s) {
         if (int wrc = wait_genome(s, s->ntiles)) return wrc;
         if (brc < 0) {
             s->marklist_valid = false;   // the direct query kernel marks the mask only
-            CK(W_DISPATCH(s, fill(lc, s->g, s->d_filter, kp, s->ntiles, s->d_ctr)));
+            CK(W_DISPATCH(s, fill(lc, s->g, s->d_filter, kp, 0, s->ntiles, s->d_ctr)));
             CK(cudaEventRecord(s->ev[1], s->stream));
-            CK(W_DISPATCH(s, query(lc, s->g, s->d_filter, kp, s->ntiles, s->d_mask, r > 0 || brc == -2, s->d_ctr, s->d_hll)));
+            CK(W_DISPATCH(s, query(lc, s->g, s->d_filter, kp, 0, s->ntiles, s->d_mask, r > 0 || brc == -2, s->d_ctr, s->d_hll)));
         } else {
             CK(cudaEventRecord(s->ev[1], s->stream));
         }
@@ -995,9 +998,9 @@ int tpc_session_find_candidates(tpc_session* s) {
             // sparse marks that all went through the binned query kernels: insert from the mark list; else walk the mask
             const uint64_t list_cap = (uint64_t)s->marklist_regions * s->marklist_region_cap;
             const bool force_list = getenv("TPC_MARK_LIST_FORCE") != nullptr;   // (tests: the overflow -> redo path)
-            const bool from_list = s->marklist_valid && (marks_r * 10 <= list_cap * 8 || force_list);
+            const bool from_list = s->marklist_valid && ((marks_r * 10 <= list_cap * 8 && marks_r * 128 <= s->g.npos) || force_list);
             if (from_list) CK(W_DISPATCH(s, insert_list(lc, s->g, s->mark_list(true), kpi, TableView{s->d_T, lg, s->inline_keys()}, s->d_ctr)));
-            else CK(W_DISPATCH(s, insert(lc, s->g, s->d_mask, kpi, s->ntiles, TableView{s->d_T, lg, s->inline_keys()}, s->d_ctr,
+            else CK(W_DISPATCH(s, insert(lc, s->g, s->d_mask, kpi, 0, s->ntiles, TableView{s->d_T, lg, s->inline_keys()}, s->d_ctr,
                                          planes_ok ? &iop : nullptr)));
             CK(cudaEventRecord(s->ev[3], s->stream));
             CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
@@ -1026,7 +1029,7 @@ int tpc_session_find_candidates(tpc_session* s) {
             if (s->d_local) CK(dev_free(s->d_local, s->stream));
             s->d_local = nl; s->local_cap = ncap;
         }
-        CK(launch_classify(lc, T, s->prm.abundance, kp.count_occurrences, s->d_local, s->local_cap, s->d_ctr));
+        CK(launch_classify(lc, T, s->prm.abundance, kp.count_occurrences, s->d_local, nullptr, s->local_cap, s->d_ctr));
         CK(cudaEventRecord(s->ev[4], s->stream));
         CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
@@ -1111,10 +1114,9 @@ int tpc_session_emit_count(tpc_session* s, uint64_t pos_begin, uint64_t pos_end,
     if (pos_begin >= pos_end) te = tb;   // empty slice (more shards than tiles)
     uint64_t nt = te - tb;
     if (nt + 1 > s->tile_cap) {
-        for (void* p : {(void*)s->d_tile_rec, (void*)s->d_tile_stub, (void*)s->d_scan_scratch, (void*)s->d_cache_tile_base})
+        for (void* p : {(void*)s->d_tile_rec, (void*)s->d_tile_stub, (void*)s->d_scan_scratch})
             if (p) CK(dev_free(p, s->stream));
-        s->d_tile_rec = s->d_tile_stub = s->d_scan_scratch = s->d_cache_tile_base = nullptr;
-        CK(dev_alloc(&s->d_cache_tile_base, (nt + 2) * 8, s->stream));
+        s->d_tile_rec = s->d_tile_stub = s->d_scan_scratch = nullptr;
         CK(dev_alloc(&s->d_tile_rec, (nt + 1) * 8, s->stream));
         CK(dev_alloc(&s->d_tile_stub, (nt + 1) * 8, s->stream));
         CK(dev_alloc(&s->d_scan_scratch, scan_scratch_items(nt + 1) * 8, s->stream));
@@ -1126,24 +1128,8 @@ int tpc_session_emit_count(tpc_session* s, uint64_t pos_begin, uint64_t pos_end,
     CK(cudaMemsetAsync(s->d_tile_stub + nt, 0, 8, s->stream));
     KParams kp = s->kparams(0);
     TableView J{s->d_J, s->J_log2, s->inline_keys()};
-    {   // id cache: room for the marks of the slice.  Single GPU: the shard's mark count bounds it; sharded: the slice holds
-        // about 1/N of every shard's marks -- whatever does not fit is looked up again by emit_write (never wrong)
-        uint64_t want = s->st.candidate_marks + 1024;
-        if (s->prm.shard_count > 1) want = want + want / 4 + (1u << 20);
-        if (getenv("TPC_EMIT_CACHE") && atoi(getenv("TPC_EMIT_CACHE")) == 0) want = 0;   // (tests: the look-up path of emit_write)
-        else if (const char* e = getenv("TPC_EMIT_CACHE_CAP")) want = (uint64_t)atoll(e);  // (tests: a cache that overflows)
-        if (want > s->id_cache_cap || want == 0) {
-            if (s->d_id_cache) CK(dev_free(s->d_id_cache, s->stream));
-            s->d_id_cache = nullptr; s->id_cache_cap = 0;
-            if (want && want * 8 < available_bytes(s->device) / 2) {
-                CK(dev_alloc(&s->d_id_cache, want * 8, s->stream));
-                s->id_cache_cap = want;
-            }
-        }
-        CK(cudaMemsetAsync(s->d_cache_tile_base + s->tile_cap, 0, 8, s->stream));
-    }
     CK(W_DISPATCH(s, ends(lc, s->g, s->rtable(), kp, J, s->d_stubmask, pos_begin, pos_end)));
-    CK(W_DISPATCH(s, emit_count(lc, s->g, s->d_mask, s->d_stubmask, kp, J, tb, te, s->d_tile_rec, s->d_tile_stub, s->emit_cache())));
+    CK(W_DISPATCH(s, emit_count(lc, s->g, s->d_mask, s->d_stubmask, kp, J, tb, te, s->d_tile_rec, s->d_tile_stub)));
     CK(launch_scan_exclusive(lc, s->d_tile_rec, nt + 1, s->d_scan_scratch));
     CK(launch_scan_exclusive(lc, s->d_tile_stub, nt + 1, s->d_scan_scratch));
     unsigned long long tot[2];
@@ -1183,7 +1169,7 @@ int tpc_session_emit_write(tpc_session* s, uint64_t records_before, uint64_t stu
     TableView J{s->d_J, s->J_log2, s->inline_keys()};
     CK(W_DISPATCH(s, emit_write(lc, s->g, s->d_mask, s->d_stubmask, kp, J, s->rtable(), s->slice_tile_begin, s->slice_tile_end,
                                 s->d_tile_rec, s->d_tile_stub, records_before, stubs_before, unit_base,
-                                s->J_count + TPC_STUB_ID_OFFSET, (uint32_t*)dev_out, units, s->emit_cache(), s->slice_tile_begin)));
+                                s->J_count + TPC_STUB_ID_OFFSET, (uint32_t*)dev_out, units)));
     CK(cudaEventRecord(s->ev[8], s->stream));
     s->st.occurrences = s->slice_records;
     s->st.stubs = s->slice_stubs;
@@ -1270,7 +1256,7 @@ static int emit_write_parts(tpc_session* s, uint8_t* d_out, uint64_t image_bytes
     for (uint32_t i = 0; i < parts; ++i) {
         CK(W_DISPATCH(s, emit_write(lc, s->g, s->d_mask, s->d_stubmask, kp, J, s->rtable(), bt[i], bt[i + 1],
                                     s->d_tile_rec + (bt[i] - tb), s->d_tile_stub + (bt[i] - tb), 0, 0, unit_base,
-                                    s->J_count + TPC_STUB_ID_OFFSET, (uint32_t*)d_out, units, s->emit_cache(), s->slice_tile_begin)));
+                                    s->J_count + TPC_STUB_ID_OFFSET, (uint32_t*)d_out, units)));
         uint64_t pos_hi = std::min<uint64_t>(bt[i + 1] * kTilePos, s->slice_pos_end);
         uint64_t byte_hi = i + 1 == parts ? units * 12 : (pref[i + 1] + emit_prev_at(s, pos_hi) - unit_base) * 12;
         if (int rc = on_part(byte_lo, byte_hi)) return rc;
