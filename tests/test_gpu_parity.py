@@ -750,3 +750,43 @@ def test_cli_uses_several_gpus(tmp_path, monkeypatch):
         outs.append(out.read_bytes())
     ref, _, _ = O.find_junctions(recs, 25)
     assert outs[0] == ref and outs[1] == ref
+
+
+# ---- position-windowed sessions (tpc_windowed.inl): inputs larger than HBM stream through it window by window ----------
+@pytest.mark.parametrize("window_tiles,rounds", [(1, 1), (3, 1), (7, 3), (1000, 2)])
+@pytest.mark.parametrize("name", ["family_k25", "family_seam_k25", "family_k29", "selftest_s3_k9", "edge_mixed_k5", "family_twofiles_k25"])
+def test_windowed_run_equals_resident_run(name, window_tiles, rounds, golden, monkeypatch):
+    """TPC_WINDOW_TILES forces the driver BASELINE config 5 needs (genome, masks and planes never resident; filter, table
+    and index resident; every definite k-mer position resolved against the index in the emit) on inputs small enough to
+    compare: byte-identical to the resident run and to the reference's golden canonical stream, for windows of 1, 3, 7
+    tiles (k-mers, records and sequence ends straddle them) and one window holding everything."""
+    spec, g = CASES[name], golden[name]
+    with case_files(spec) as (paths, _, _):
+        recs = api.read_fasta(paths)
+    gen = api.pack_records(recs)
+    base, st0 = api.junctions_host(gen, k=spec["k"], filter_bits=20, q=4, rounds=rounds)
+    monkeypatch.setenv("TPC_WINDOW_TILES", str(window_tiles))
+    img, st = api.junctions_host(gen, k=spec["k"], filter_bits=20, q=4, rounds=rounds)
+    assert bytes(img) == bytes(base), "windowed image differs from the resident one"
+    assert canon_md5(bytes(img)) == g["canon_md5"]
+    assert st.junctions == st0.junctions == g["distinct_junctions"] and st.occurrences == st0.occurrences
+
+
+def test_windowed_run_edge_cases(monkeypatch):
+    monkeypatch.setenv("TPC_WINDOW_TILES", "2")
+    for recs in ([], [b""], [b"ACG"], [b"N" * 40], [b"ACGTACGTACG"], [b"", b"ACGTTGCAAGC", b""],
+                 synth.founder_family(17, 3, 2, 30_000, 0.02, n_runs=3) + [b"ACG", b""]):
+        ref, nj, nm = O.find_junctions(recs, 11)
+        img, st = api.junctions_host(api.pack_records(recs), k=11, filter_bits=16)
+        assert bytes(img) == ref
+        assert st.junctions == nj and st.occurrences == nm
+    # a candidate table that starts far too small doubles and the round is redone
+    monkeypatch.setenv("TPC_WINDOW_TABLE_LOG2", "4")
+    recs = synth.founder_family(18, 4, 2, 40_000, 0.02)
+    ref, nj, _ = O.find_junctions(recs, 25)
+    img, st = api.junctions_host(api.pack_records(recs), k=25, filter_bits=18, rounds=2)
+    assert bytes(img) == ref and st.junctions == nj
+    monkeypatch.delenv("TPC_WINDOW_TABLE_LOG2")
+    # longer k-mers keep position-identified slots, which read the genome back: not available windowed
+    with pytest.raises(api.TpcError, match="k <= 31"):
+        api.junctions_host(api.pack_records(recs), k=63, filter_bits=18)

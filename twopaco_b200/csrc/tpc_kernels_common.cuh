@@ -248,17 +248,11 @@ template <int Q>
 __global__ void __launch_bounds__(256, 4)
 k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, const unsigned long long* __restrict__ count,
               uint64_t cap, uint32_t sib_bits, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr,
-              uint32_t* __restrict__ hll, uint64_t slice_first_sector, MarkList ml, uint4* __restrict__ zero_dst, uint32_t zero_vec) {
+              uint32_t* __restrict__ hll, uint64_t slice_first_sector, MarkList ml) {
     __shared__ unsigned long long red[8];
     __shared__ ApplyRing ring;
     __shared__ uint32_t s_list_count;
     mark_list_begin(ml, &s_list_count);
-    // Another round follows: clear the slice queried by the PREVIOUS launch for it (h:257: every round starts from a
-    // zero-filled filter).  This kernel is bound by the L1 tag stage and leaves HBM idle, so the 64 MiB of streaming
-    // stores are free here, whereas a memset of the whole filter between rounds is not.
-    if (zero_dst)
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < zero_vec; i += gridDim.x * blockDim.x)
-            __stcs(zero_dst + i, make_uint4(0u, 0u, 0u, 0u));
     unsigned long long n64 = *count;
     const uint64_t n = n64 > cap ? cap : n64;
     const uint32_t* __restrict__ rec_b = rec + cap;

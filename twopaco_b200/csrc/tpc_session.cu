@@ -18,6 +18,7 @@
 #include "tpc_internal.h"
 #include "tpc_kernels_common.cuh"
 #include "tpc_launch.cuh"
+#include "tpc_window_provider.h"
 
 namespace tpc {
 
@@ -176,15 +177,12 @@ cudaError_t launch_apply_fill(const LaunchCtx& c, uint32_t* filter, const BinVie
     return cudaGetLastError();
 }
 
-// zero_previous: also clear the slice of bucket - 1 (queried by the previous launch) for the next round
-cudaError_t launch_apply_query(const LaunchCtx& c, uint32_t* filter, const BinView& bv, uint32_t bucket, uint32_t* mask,
-                               uint64_t wave_base, Counters* ctr, uint32_t* hll, const MarkList& ml, bool zero_previous) {
+cudaError_t launch_apply_query(const LaunchCtx& c, const uint32_t* filter, const BinView& bv, uint32_t bucket, uint32_t* mask,
+                               uint64_t wave_base, Counters* ctr, uint32_t* hll, const MarkList& ml) {
     const uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
-    uint4* zero_dst = zero_previous && bucket > 0 ? reinterpret_cast<uint4*>(filter + (((uint64_t)(bucket - 1) << bv.sib_bits) << 3)) : nullptr;
-    const uint32_t zero_vec = (uint32_t)(((uint64_t)32 << bv.sib_bits) / 16);
     TPC_APPLY_Q_SWITCH(bv.q, (k_apply_query<Q><<<apply_grid(c), 256, 0, c.stream>>>(
         slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap, bv.sib_bits, mask, wave_base, ctr, hll,
-        (uint64_t)bucket << bv.sib_bits, ml, zero_dst, zero_vec)));
+        (uint64_t)bucket << bv.sib_bits, ml)));
     ++*c.launches;
     return cudaGetLastError();
 }
@@ -289,6 +287,15 @@ struct tpc_session {
     MarkList mark_list(bool enabled) const {
         return MarkList{enabled ? d_marklist : nullptr, d_marklist_counts, marklist_regions, marklist_region_cap};
     }
+
+    // position-windowed sessions (tpc_windowed.inl): the genome streams through HBM window by window from `wp`;
+    // g / d_mask / d_stubmask then are VIRTUAL views of the current window's buffers
+    bool windowed = false;
+    WindowProvider* wp = nullptr;
+    uint64_t window_tiles = 0, w_npos = 0;
+    uint32_t* d_wmask = nullptr;
+    uint32_t* d_wstub = nullptr;
+    unsigned long long* d_local_keys = nullptr;   // junction keys beside d_local (windowed runs)
 
     // hash sub-ranges processed in sequence by this GPU: the user's -r times the sub-rounds chosen so
     // that one round's records fit HBM in one wave (choose_sub_rounds); ownership planes of all of
@@ -404,9 +411,10 @@ int tpc_session_create(const tpc_params* params, void* stream, tpc_session** out
 void tpc_session_destroy(tpc_session* s) {
     if (!s) return;
     cudaStreamSynchronize(s->stream);
+    if (s->windowed) { s->d_mask = nullptr; s->d_stubmask = nullptr; }   // (views of d_wmask / d_wstub)
     void* ptrs[] = {s->d_codes, s->d_nmask, s->d_rec_start, s->d_rec_len, s->d_sep_before, s->d_filter, s->d_mask,
                     s->d_stubmask, s->d_T, s->d_J, s->d_local, s->d_sorted, s->d_sort_tmp, s->d_ctr, s->d_id,
-                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch, s->d_marklist, s->d_marklist_counts, s->d_bin_rec, s->d_bin_count, s->d_bin_ov, s->d_hll, s->d_own_extra};
+                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch, s->d_marklist, s->d_marklist_counts, s->d_wmask, s->d_wstub, s->d_local_keys, s->d_bin_rec, s->d_bin_count, s->d_bin_ov, s->d_hll, s->d_own_extra};
     for (void* p : ptrs)
         dev_free(p, s->stream);
     cudaStreamSynchronize(s->stream);
@@ -668,7 +676,7 @@ static int binned_release(tpc_session* s) {
 // Filter passes of one round through the binned path.  Returns -1 when the binned path does not
 // apply and -2 when a slice overflowed beyond the overflow area (then the caller uses k_fill /
 // k_query), 0 on success, >0 on error.
-static int filter_passes_binned(tpc_session* s, const KParams& kp, bool clear_for_next, float* ms_bin, float* ms_fill, float* ms_query) {
+static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin, float* ms_fill, float* ms_query) {
     if (int rc = binned_setup(s, kp)) return rc;
     LaunchCtx lc = s->lctx();
     const BinView bv = s->bin_view;
@@ -721,15 +729,11 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, bool clear_fo
                 if (int brc = bin_range(t0, t1, base)) return brc;
             }
             CK(cudaEventRecord(e1, s->stream));
-            const bool zero = pass == 1 && wv + 1 == nwaves && clear_for_next;   // last readers of the slices in this round
-            // (the overflow records touch any slice: their query runs before the slices are cleared)
-            if (pass == 1) CK(launch_apply_overflow(lc, s->d_filter, bv, 1, s->d_mask, base, s->d_ctr, s->d_hll, s->mark_list(true)));
             for (uint32_t b = 0; b < buckets; ++b) {
                 if (pass == 0) CK(launch_apply_fill(lc, s->d_filter, bv, b, s->d_ctr));
-                else CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, base, s->d_ctr, s->d_hll, s->mark_list(true), zero));
+                else CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, base, s->d_ctr, s->d_hll, s->mark_list(true)));
             }
-            if (pass == 0) CK(launch_apply_overflow(lc, s->d_filter, bv, 0, s->d_mask, base, s->d_ctr, s->d_hll, s->mark_list(false)));
-            if (zero) CK(cudaMemsetAsync(s->d_filter + (((uint64_t)(buckets - 1) << bv.sib_bits) << 3), 0, (uint64_t)32 << bv.sib_bits, s->stream));
+            CK(launch_apply_overflow(lc, s->d_filter, bv, pass, s->d_mask, base, s->d_ctr, s->d_hll, s->mark_list(pass == 1)));
             CK(cudaEventRecord(e2, s->stream));
             rc = finish_wave(ms_bin, pass == 0 ? ms_fill : ms_query);
         }
@@ -764,7 +768,7 @@ static int bin_whole_round(tpc_session* s, const LaunchCtx& lc, const KParams& k
 
 // Filter passes of round r (of rounds_eff) with the next round's binning overlapped (see tpc_session::pipe).
 // Same return convention as filter_passes_binned.
-static int filter_passes_pipelined(tpc_session* s, uint32_t r, const KParams& kp, bool clear_for_next, float* ms_bin, float* ms_fill, float* ms_query) {
+static int filter_passes_pipelined(tpc_session* s, uint32_t r, const KParams& kp, float* ms_bin, float* ms_fill, float* ms_query) {
     if (int rc = binned_setup(s, kp)) return rc;
     if (!s->pipe) return -3;   // the scratch could not be split after all: caller uses the one-scratch path
     const int h = (int)(r & 1);
@@ -803,10 +807,8 @@ static int filter_passes_pipelined(tpc_session* s, uint32_t r, const KParams& kp
     CK(cudaEventRecord(e2, s->stream));
     if (has_next) CK(cudaStreamWaitEvent(s->stream, s->pipe_ev[h ^ 1], 0));   // the query runs alone, at full occupancy
     lc.apply_ctas = s->apply_ctas;
-    CK(launch_apply_overflow(lc, s->d_filter, bv, 1, s->d_mask, 0, s->d_ctr, s->d_hll, s->mark_list(true)));   // before any slice is cleared
-    for (uint32_t b = 0; b < buckets; ++b)
-        CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, 0, s->d_ctr, s->d_hll, s->mark_list(true), clear_for_next));
-    if (clear_for_next) CK(cudaMemsetAsync(s->d_filter + (((uint64_t)(buckets - 1) << bv.sib_bits) << 3), 0, (uint64_t)32 << bv.sib_bits, s->stream));
+    for (uint32_t b = 0; b < buckets; ++b) CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, 0, s->d_ctr, s->d_hll, s->mark_list(true)));
+    CK(launch_apply_overflow(lc, s->d_filter, bv, 1, s->d_mask, 0, s->d_ctr, s->d_hll, s->mark_list(true)));
     CK(cudaEventRecord(e3, s->stream));
     unsigned long long ov_now = 0;
     CK(cudaMemcpyAsync(&ov_now, bv.ov_count, 8, cudaMemcpyDeviceToHost, s->stream));
@@ -828,7 +830,10 @@ static uint64_t padded_mask_words(const tpc_session* s) {
     return std::max<uint64_t>(chunk_tiles * n * kTileThreads, 1);
 }
 
+namespace tpc { static int find_candidates_windowed(tpc_session* s); }
+
 int tpc_session_find_candidates(tpc_session* s) {
+    if (s && s->windowed) return tpc::find_candidates_windowed(s);
     if (!s || !s->g.codes) return set_error("no genome set");
     LaunchCtx lc = s->lctx();
     const uint64_t mask_words = s->ntiles * kTileThreads;
@@ -905,25 +910,20 @@ int tpc_session_find_candidates(tpc_session* s) {
     // (one table, sized from the HyperLogLog sketch accumulated over the sub-rounds) replaces one scan per
     // sub-round.  With -r > 1 the table stays per round, as in the reference (h:337-338).
     const bool merge_insert = s->prm.rounds == 1 && s->sub_rounds > 1;
-    bool filter_clean = false;
     for (uint32_t r = 0; r < s->rounds_eff; ++r) {
         KParams kp = s->kparams(s->prm.shard_index * s->rounds_eff + r);
         const Counters round_start = cur;
         CK(cudaEventRecord(s->ev[0], s->stream));
-        // h:257: zero-filled each round -- by the previous round's query kernels when they were the binned ones
-        if (!filter_clean) CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));
-        filter_clean = false;
-        const bool clear_for_next = r + 1 < s->rounds_eff && !(getenv("TPC_QUERY_ZERO") && atoi(getenv("TPC_QUERY_ZERO")) == 0);
+        CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));  // h:257: zero-filled each round
         if (!merge_insert || r == 0) {
             CK(cudaMemsetAsync(s->d_hll, 0, 4u << kHllBits, s->stream));
             if (s->d_marklist) CK(cudaMemsetAsync(s->d_marklist_counts, 0, s->marklist_regions * 4, s->stream));
             s->marklist_valid = s->d_marklist != nullptr;
         }
         float b_bin = 0, b_fill = 0, b_query = 0;
-        int brc = s->pipe ? filter_passes_pipelined(s, r, kp, clear_for_next, &b_bin, &b_fill, &b_query) : -3;
-        if (brc == -3) brc = filter_passes_binned(s, kp, clear_for_next, &b_bin, &b_fill, &b_query);
+        int brc = s->pipe ? filter_passes_pipelined(s, r, kp, &b_bin, &b_fill, &b_query) : -3;
+        if (brc == -3) brc = filter_passes_binned(s, kp, &b_bin, &b_fill, &b_query);
         if (brc > 0) return brc;
-        filter_clean = brc == 0 && clear_for_next;
         if (brc == -2) {  // redo this round from scratch; marks already set are true marks and may stay
             CK(cudaMemsetAsync(s->d_filter, 0, filter_bytes, s->stream));
             CK(cudaMemcpyAsync(s->d_ctr, &round_start, sizeof round_start, cudaMemcpyHostToDevice, s->stream));
@@ -1096,6 +1096,7 @@ int tpc_session_set_junctions(tpc_session* s, const uint64_t* dev_words_all, uin
 }
 
 int tpc_session_candidate_mask(tpc_session* s, uint32_t** dev_mask, uint64_t* n_words) {
+    if (s && s->windowed) return set_error("a windowed session keeps no candidate mask");
     if (!s || !s->d_mask) return set_error("find_candidates has not run");
     if (dev_mask) *dev_mask = s->d_mask;
     if (n_words) *n_words = padded_mask_words(s);
@@ -1325,6 +1326,9 @@ int tpc_session_write_stream(tpc_session* s, uint64_t image_bytes, tpc_chunk_sin
     return rc;
 }
 
+static int host_windowed_run(tpc_session* s, const tpc_genome* g, uint64_t window_tiles, uint8_t* out_image, uint64_t out_capacity,
+                             uint64_t* out_bytes);
+
 int tpc_junctions_host(const tpc_params* params, const tpc_genome* host_genome, uint8_t* out_image, uint64_t out_capacity,
                        uint64_t* out_bytes, tpc_stats* stats) {
     if (!params || !host_genome) return set_error("null argument");
@@ -1333,6 +1337,20 @@ int tpc_junctions_host(const tpc_params* params, const tpc_genome* host_genome, 
     p.shard_count = 1;
     tpc_session* s = nullptr;
     if (int rc = tpc_session_create(&p, nullptr, &s)) return rc;
+    // Inputs that do not fit HBM beside the filter (genome 0.375 B + candidate / stub masks 0.25 B per position), or
+    // TPC_WINDOW_TILES=<tiles per window>: the position-windowed driver (tpc_windowed.inl)
+    uint64_t window_tiles = 0;
+    if (const char* e = getenv("TPC_WINDOW_TILES")) window_tiles = (uint64_t)std::max(0ll, atoll(e));
+    else {
+        const double resident = 0.75 * (double)host_genome->n_positions + (double)((1ull << std::max<uint32_t>(p.filter_bits, 9u)) / 8);
+        if (resident > 0.85 * (double)available_bytes(s->device)) window_tiles = 1u << 17;   // 2^30 positions per window
+    }
+    if (window_tiles) {
+        int rc = host_windowed_run(s, host_genome, window_tiles, out_image, out_capacity, out_bytes);
+        if (stats) tpc_session_stats(s, stats);
+        tpc_session_destroy(s);
+        return rc;
+    }
     int rc = tpc_session_set_genome_host(s, host_genome);
     uint64_t bytes = 0;
     if (rc == 0) rc = tpc_session_run_to_count(s, &bytes);
@@ -1348,3 +1366,45 @@ int tpc_junctions_host(const tpc_params* params, const tpc_genome* host_genome, 
 }
 
 }  // extern "C"
+
+#include "tpc_windowed.inl"
+
+// level 2, one GPU, windowed: packed genome in host memory -> image in host memory
+namespace {
+struct HostImageSink {
+    uint8_t* image;
+    uint64_t capacity, written;
+};
+int host_image_sink(void* ctx, const uint8_t* dev_bytes, uint64_t image_offset, uint64_t nbytes, cudaStream_t stream) {
+    HostImageSink* k = static_cast<HostImageSink*>(ctx);
+    k->written = std::max(k->written, image_offset + nbytes);
+    if (image_offset + nbytes > k->capacity || nbytes == 0) return 0;   // (too small: keep counting, report the size at the end)
+    return cudaMemcpyAsync(k->image + image_offset, dev_bytes, nbytes, cudaMemcpyDeviceToHost, stream) == cudaSuccess
+               ? 0 : tpc::set_error("device to host copy of the image failed");
+}
+}  // namespace
+
+static int host_windowed_run(tpc_session* s, const tpc_genome* g, uint64_t window_tiles, uint8_t* out_image, uint64_t out_capacity,
+                             uint64_t* out_bytes) {
+    HostWindowProvider prov(g->codes, g->n_mask, g->n_positions, window_tiles, 0, 1, nullptr);
+    if (int rc = prov.init()) return rc;
+    if (int rc = tpc_session_set_genome_windowed(s, g->n_positions, g->rec_start, g->rec_len, g->n_records, window_tiles, &prov)) return rc;
+    if (int rc = tpc_session_find_candidates(s)) return rc;
+    const uint64_t *words = nullptr, *keys = nullptr;
+    uint64_t n = 0;
+    if (int rc = tpc_session_local_junctions(s, &words, &n)) return rc;
+    if (int rc = tpc_session_local_junction_keys(s, &keys)) return rc;
+    if (int rc = tpc_session_set_junctions_keyed(s, words, keys, n)) return rc;
+    HostImageSink sink{out_image, out_image ? out_capacity : 0, 0};
+    uint64_t nrec = 0, nstub = 0;
+    if (int rc = tpc_session_emit_windowed(s, 0, g->n_positions, 1, 0, 0, host_image_sink, &sink, &nrec, &nstub)) return rc;
+    const uint64_t bytes = (nrec + s->emit_prev[s->rec_start.size()]) * 12;
+    if (out_bytes) *out_bytes = bytes;
+    s->st.out_bytes = bytes;
+    s->wp = nullptr;   // (the provider dies with this frame)
+    if (bytes > out_capacity) {
+        tpc::set_error("output buffer too small: need %llu bytes", (unsigned long long)bytes);
+        return 2;
+    }
+    return 0;
+}
