@@ -162,6 +162,17 @@ void tpc_multi_destroy(tpc_multi *m);
 uint32_t tpc_multi_gpus(const tpc_multi *m);
 int tpc_multi_junctions_host(tpc_multi *m, const tpc_params *params, const tpc_genome *host_genome,
                              uint8_t *out_image, uint64_t out_capacity, uint64_t *out_bytes, tpc_stats *stats);
+/* The same run whose image never leaves the GPUs: only its size and its position-keyed digest (tpc_image_digest_device)
+ * come back -- for outputs too large to keep (BASELINE config 5 writes ~0.7 TB of records) and for timing the path
+ * without the device-to-host copy. */
+int tpc_multi_junctions_digest(tpc_multi *m, const tpc_params *params, const tpc_genome *host_genome, uint64_t digest[2],
+                               uint64_t *image_bytes, tpc_stats *stats);
+/* Inputs that do not fit a GPU's memory beside the filter (packed genome 0.375 B + masks 0.25 B per position) run
+ * position-windowed, in tpc_junctions_host and tpc_multi_*: the packed genome stays in (pinned) host memory and streams
+ * through HBM window by window, once per pass (fill, query + exact insert per round; emit), the filter, the candidate
+ * table and the junction index stay resident (reference: DistributeTasks re-reads the FASTA once per stage,
+ * vertexenumerator.h:1108-1226).  Several GPUs: every GPU uploads 1/N of a window over its own PCIe link, NCCL
+ * all-gathers it.  Needs k <= 31 and no -a.  TPC_WINDOW_TILES=<8192-position tiles per window> forces it (0: never). */
 
 /* ------------------------------------------------------------------------------------------
  * Level 3 -- sessions.  One session = one GPU (current device at creation) = one hash-range

@@ -726,6 +726,16 @@ def test_cxx_multi_gpu_host_buffers(mode, monkeypatch):
             img, st = mg.junctions_host(api.pack_records(recs), k=k, filter_bits=f)
             assert bytes(img) == ref, (k, mode)
             assert st.junctions == nj and st.occurrences == nm
+            # image left on the GPUs: size and digest only
+            d, nbytes, _ = mg.junctions_digest(api.pack_records(recs), k=k, filter_bits=f)
+            assert nbytes == len(ref) and d == api.image_digest_host(ref)
+            if k <= 31:   # position-windowed shards: 1/N of every window per GPU + all-gather; emit from private windows
+                monkeypatch.setenv("TPC_WINDOW_TILES", "3")
+                img, st = mg.junctions_host(api.pack_records(recs), k=k, filter_bits=f, rounds=2)
+                assert bytes(img) == ref and st.junctions == nj, ("windowed", k, mode)
+                d, nbytes, _ = mg.junctions_digest(api.pack_records(recs), k=k, filter_bits=f)
+                assert nbytes == len(ref) and d == api.image_digest_host(ref)
+                monkeypatch.delenv("TPC_WINDOW_TILES")
     finally:
         mg.close()
 
@@ -770,6 +780,16 @@ def test_windowed_run_equals_resident_run(name, window_tiles, rounds, golden, mo
     assert bytes(img) == bytes(base), "windowed image differs from the resident one"
     assert canon_md5(bytes(img)) == g["canon_md5"]
     assert st.junctions == st0.junctions == g["distinct_junctions"] and st.occurrences == st0.occurrences
+
+
+def test_host_assembled_family_equals_device_family():
+    """tools/benchutil synth_family_host (C5-size inputs: generated in groups of genomes, packed at arbitrary bit offsets
+    straight into host memory) == synth_family_device packed in one piece."""
+    a = benchutil.synth_family_device(0x4831, 5, 3, 100_003, 0.01).to_host()
+    for group in (1, 2, 5):
+        b = benchutil.synth_family_host(0x4831, 5, 3, 100_003, 0.01, group=group, pin=False)
+        assert b.n_positions == a.n_positions and np.array_equal(b.rec_start, a.rec_start) and np.array_equal(b.rec_len, a.rec_len)
+        assert np.array_equal(b.codes, a.codes) and np.array_equal(b.n_mask, a.n_mask), group
 
 
 def test_windowed_run_edge_cases(monkeypatch):

@@ -75,6 +75,8 @@ SIGNATURES = {
     "tpc_multi_gpus": (C.c_uint32, [C.c_void_p]),
     "tpc_multi_junctions_host": (C.c_int, [C.c_void_p, C.POINTER(Params), C.POINTER(Genome), C.c_void_p, C.c_uint64,
                                            C.POINTER(C.c_uint64), C.POINTER(Stats)]),
+    "tpc_multi_junctions_digest": (C.c_int, [C.c_void_p, C.POINTER(Params), C.POINTER(Genome), C.POINTER(C.c_uint64 * 2),
+                                             C.POINTER(C.c_uint64), C.POINTER(Stats)]),
     "tpc_session_create": (C.c_int, [C.POINTER(Params), C.c_void_p, C.POINTER(C.c_void_p)]),
     "tpc_session_destroy": (None, [C.c_void_p]),
     "tpc_session_set_genome_host": (C.c_int, [C.c_void_p, C.POINTER(Genome)]),
@@ -242,6 +244,14 @@ class MultiGpu:
                     break
         _check(rc)
         return out[:nbytes.value], st
+
+    def junctions_digest(self, genome: PackedGenome, k: int, filter_bits: int, q: int = 5, rounds: int = 1, seed: int = 0):
+        """The same run with the image left on the GPUs -> ((digest a, digest b), image bytes, Stats)."""
+        prm = Params(k, filter_bits, q, rounds, ABUNDANCE_MAX, 0, self.n_gpus, seed)
+        g = genome.struct()
+        st, d, nbytes = Stats(), (C.c_uint64 * 2)(), C.c_uint64(0)
+        _check(lib().tpc_multi_junctions_digest(self._m, C.byref(prm), C.byref(g), C.byref(d), C.byref(nbytes), C.byref(st)))
+        return (int(d[0]), int(d[1])), nbytes.value, st
 
     def close(self) -> None:
         if self._m:

@@ -19,6 +19,9 @@ struct WindowProvider {
     virtual void begin_pass(int kind, uint64_t tile_first, uint64_t tile_last) = 0;
     virtual int fetch(uint64_t tile_begin, uint64_t tile_end, const uint64_t** codes_v, const uint64_t** nmask_v, cudaEvent_t* ready) = 0;
     virtual void release(uint64_t tile_begin) = 0;
+    // Shards that share the passes (and the collectives inside them) must repeat a round together: true when ANY shard
+    // says so.  One shard: its own answer.
+    virtual bool any_shard(bool mine) { return mine; }
 };
 }  // namespace tpc
 

@@ -13,6 +13,7 @@
 // it is what tpc_build / the twopaco CLI run when more than one GPU is visible.  NCCL is loaded with dlopen so that
 // libtwopaco_b200.so has no link-time dependency on it (single-GPU use never touches it).
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -33,6 +34,7 @@
 
 #include "tpc_internal.h"
 #include "tpc_multi.h"
+#include "tpc_window_provider.h"
 
 using tpc::set_error;
 
@@ -147,11 +149,22 @@ struct Shared {
     std::vector<int> rc;
     std::vector<std::string> err;
     std::vector<uint64_t> jcount, nrec, nstub, slice_off, slice_bytes;
+    std::vector<std::array<uint64_t, 2>> digest;
     std::vector<tpc_stats> stats;
     std::vector<tpc_session*> session;
+    std::vector<char> flag;
     HostBarrier bar;
+    // logical OR of the shards' flags (every shard's thread calls it)
+    bool any(int r, bool mine) {
+        flag[r] = mine ? 1 : 0;
+        bar.wait();
+        bool a = false;
+        for (int i = 0; i < n; ++i) a = a || flag[i];
+        bar.wait();
+        return a;
+    }
     explicit Shared(int n_) : n(n_), dev(n_), comm(n_, nullptr), rc(n_, 0), err(n_), jcount(n_, 0), nrec(n_, 0), nstub(n_, 0),
-                              slice_off(n_, 0), slice_bytes(n_, 0), stats(n_), session(n_, nullptr), bar(n_) {}
+                              slice_off(n_, 0), slice_bytes(n_, 0), digest(n_, std::array<uint64_t, 2>{0, 0}), stats(n_), session(n_, nullptr), flag(n_, 0), bar(n_) {}
     // all threads call this with their own status; returns true when every thread is fine
     bool sync_ok(int r, int my_rc) {
         if (my_rc != 0 && rc[r] == 0) { rc[r] = my_rc; err[r] = tpc::last_error(); }
@@ -204,6 +217,7 @@ struct ImageSink {
     uint8_t* host_image = nullptr;   // level 2: bytes [offset, offset + n) of this buffer
     uint64_t host_capacity = 0;
     int fd = -1;                     // level 1: pwrite() at the offset
+    bool digest_only = false;        // neither: the image never leaves the GPUs, only its digest does (Shared::digest)
 };
 
 struct GenomeSource {
@@ -213,10 +227,57 @@ struct GenomeSource {
     uint64_t n_positions = 0;
     const uint64_t *rec_start = nullptr, *rec_len = nullptr;
     uint64_t n_records = 0;
+    uint64_t window_tiles = 0;                 // > 0: position-windowed run (host source only; tpc_windowed.inl)
 };
+
+// a window's part of the image (windowed runs): to the host image, the file, or into the digest
+struct WindowSinkCtx {
+    const ImageSink* sink;
+    uint64_t digest[2] = {0, 0};
+    uint64_t end = 0;
+    void* pin = nullptr;
+    uint64_t pin_cap = 0;
+};
+static int window_sink(void* ctx, const uint8_t* dev_bytes, uint64_t image_offset, uint64_t nbytes, cudaStream_t stream) {
+    WindowSinkCtx* w = static_cast<WindowSinkCtx*>(ctx);
+    w->end = std::max(w->end, image_offset + nbytes);
+    if (nbytes == 0) return 0;
+    if (w->sink->digest_only) {
+        uint64_t d[2];
+        if (int rc = tpc_image_digest_device(dev_bytes, nbytes, image_offset, stream, d)) return rc;
+        w->digest[0] += d[0]; w->digest[1] += d[1];
+        return 0;
+    }
+    if (w->sink->host_image) {
+        if (image_offset + nbytes > w->sink->host_capacity) return 0;   // (too small: the size is reported at the end)
+        return cudaMemcpyAsync(w->sink->host_image + image_offset, dev_bytes, nbytes, cudaMemcpyDeviceToHost, stream) == cudaSuccess
+                   ? 0 : set_error("device to host copy of the image failed");
+    }
+    if (w->sink->fd >= 0) {
+        if (w->pin_cap < nbytes) {
+            if (w->pin) cudaFreeHost(w->pin);
+            w->pin = nullptr;
+            if (cudaMallocHost(&w->pin, nbytes + nbytes / 4) != cudaSuccess) return set_error("out of pinned host memory");
+            w->pin_cap = nbytes + nbytes / 4;
+        }
+        if (cudaMemcpyAsync(w->pin, dev_bytes, nbytes, cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess)
+            return set_error("device to host copy of the image failed");
+        uint64_t done = 0;
+        while (done < nbytes) {
+            ssize_t n = pwrite(w->sink->fd, (const uint8_t*)w->pin + done, nbytes - done, (off_t)(image_offset + done));
+            if (n <= 0) return set_error("Can't write to the output file");
+            done += (uint64_t)n;
+        }
+    }
+    return 0;
+}
+
+static int shard_worker_windowed(MultiImpl* mi, Shared* sh, int r, const tpc_params& base, const GenomeSource& src, const ImageSink& sink,
+                                 uint64_t* image_bytes_out);
 
 static int shard_worker(MultiImpl* mi, Shared* sh, int r, const tpc_params& base, const GenomeSource& src, const ImageSink& sink,
                         bool keep_session0, uint64_t* image_bytes_out) {
+    if (src.window_tiles) return shard_worker_windowed(mi, sh, r, base, src, sink, image_bytes_out);
     Nccl& nc = Nccl::get();
     const int N = sh->n;
     int rc = 0;
@@ -343,7 +404,11 @@ static int shard_worker(MultiImpl* mi, Shared* sh, int r, const tpc_params& base
         uint64_t off = 0, nb = 0;
         if (int e = tpc_session_emit_write(s, rb, sb, d_out, cap, &off, &nb)) return e;
         sh->slice_off[r] = off; sh->slice_bytes[r] = nb;
-        if (sink.host_image) {
+        if (sink.digest_only) {
+            uint64_t d[2] = {0, 0};
+            if (int e = tpc_image_digest_device(d_out, nb, off, st, d)) return e;
+            sh->digest[r][0] = d[0]; sh->digest[r][1] = d[1];
+        } else if (sink.host_image) {
             if (off + nb > sink.host_capacity) {
                 set_error("output buffer too small: need at least %llu bytes", (unsigned long long)(off + nb));
                 return 2;
@@ -417,7 +482,7 @@ static int shard_worker(MultiImpl* mi, Shared* sh, int r, const tpc_params& base
 }
 
 static int run_shards(MultiImpl* mi, const tpc_params& prm, const GenomeSource& src, const ImageSink& sink, bool keep_session0,
-                      uint64_t* image_bytes, tpc_stats* stats, tpc_session** session0) {
+                      uint64_t* image_bytes, tpc_stats* stats, tpc_session** session0, uint64_t* digest = nullptr) {
     const int N = (int)mi->dev.size();
     Shared sh(N);
     sh.dev = mi->dev;
@@ -454,7 +519,122 @@ static int run_shards(MultiImpl* mi, const tpc_params& prm, const GenomeSource& 
         *stats = t;
     }
     if (session0) *session0 = sh.session[0];
+    if (digest) {
+        digest[0] = digest[1] = 0;
+        for (int r = 0; r < N; ++r) { digest[0] += sh.digest[r][0]; digest[1] += sh.digest[r][1]; }
+    }
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// windowed shards (tpc_windowed.inl): the packed genome stays in host memory and streams through every GPU once per
+// pass -- shared passes: 1/N of each window per GPU over its own PCIe link + ncclAllGather; the position-sharded emit:
+// each GPU uploads the windows of its slice itself.  No candidate mask exists, so there is no mask exchange; the
+// junction exchange carries (first position, key) pairs.
+// ---------------------------------------------------------------------------------------------
+static int shard_worker_windowed(MultiImpl* mi, Shared* sh, int r, const tpc_params& base, const GenomeSource& src, const ImageSink& sink,
+                                 uint64_t* image_bytes_out) {
+    Nccl& nc = Nccl::get();
+    const int N = sh->n;
+    const bool verbose = getenv("TPC_VERBOSE") != nullptr && r == 0;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto vlog = [&](const char* what) {
+        if (verbose)
+            fprintf(stderr, "[tpc multi windowed, GPU 0 of %d] +%9.3f ms  %s\n", N,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), what);
+    };
+    int rc = 0;
+    cudaStream_t st = nullptr;
+    tpc_session* s = nullptr;
+    unsigned long long *d_allj = nullptr, *d_allk = nullptr;
+    HostWindowProvider* prov = nullptr;
+    WindowSinkCtx wctx;
+    wctx.sink = &sink;
+    auto body = [&]() -> int {
+        CKM(cudaSetDevice(sh->dev[r]));
+        CKM(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ncclComm_t comm = sh->comm[r];
+        prov = new HostWindowProvider(src.host->codes, src.host->n_mask, src.n_positions, src.window_tiles, r, N,
+                                      [comm, r, &nc](uint64_t* buffer, uint64_t part_words, cudaStream_t stream) -> int {
+                                          ncclResult_t e = nc.AllGather(buffer + (uint64_t)r * part_words, buffer, part_words, ncclUint64, comm, stream);
+                                          return e == ncclSuccess ? 0 : set_error("ncclAllGather of a genome window failed: %s", nc.GetErrorString(e));
+                                      });
+        if (int e = prov->init()) return e;
+        prov->set_agree([sh, r](bool mine) { return sh->any(r, mine); });
+        tpc_params prm = base;
+        prm.shard_index = (uint32_t)r; prm.shard_count = (uint32_t)N;
+        if (int e = tpc_session_create(&prm, st, &s)) return e;
+        sh->session[r] = s;
+        if (int e = tpc_session_set_genome_windowed(s, src.n_positions, src.rec_start, src.rec_len, src.n_records, src.window_tiles, prov)) return e;
+        return tpc_session_find_candidates(s);
+    };
+    rc = body();
+    vlog("find_candidates done");
+    if (!sh->sync_ok(r, rc)) goto done;
+    {
+        const uint64_t *words = nullptr, *keys = nullptr;
+        uint64_t nj = 0;
+        rc = tpc_session_local_junctions(s, &words, &nj);
+        if (rc == 0) rc = tpc_session_local_junction_keys(s, &keys);
+        sh->jcount[r] = nj;
+        if (!sh->sync_ok(r, rc)) goto done;
+        uint64_t total_j = 0, my_off = 0;
+        for (int i = 0; i < N; ++i) { if (i < r) my_off += sh->jcount[i]; total_j += sh->jcount[i]; }
+        auto exchange = [&]() -> int {
+            CKM(cudaMallocAsync((void**)&d_allj, std::max<uint64_t>(total_j, 1) * 8, st));
+            CKM(cudaMallocAsync((void**)&d_allk, std::max<uint64_t>(total_j, 1) * 8, st));
+            if (nj) {
+                CKM(cudaMemcpyAsync(d_allj + my_off, words, nj * 8, cudaMemcpyDeviceToDevice, st));
+                CKM(cudaMemcpyAsync(d_allk + my_off, keys, nj * 8, cudaMemcpyDeviceToDevice, st));
+            }
+            CKN(nc.GroupStart());
+            uint64_t off = 0;
+            for (int i = 0; i < N; ++i) {
+                if (sh->jcount[i]) {
+                    CKN(nc.Broadcast(d_allj + off, d_allj + off, sh->jcount[i], ncclUint64, i, sh->comm[r], st));
+                    CKN(nc.Broadcast(d_allk + off, d_allk + off, sh->jcount[i], ncclUint64, i, sh->comm[r], st));
+                }
+                off += sh->jcount[i];
+            }
+            CKN(nc.GroupEnd());
+            if (int e = tpc_session_set_junctions_keyed(s, (const uint64_t*)d_allj, (const uint64_t*)d_allk, total_j)) return e;
+            // count pass over this GPU's position slice
+            uint64_t nr = 0, ns = 0;
+            if (int e = tpc_session_emit_windowed(s, slice_cut(src.n_positions, N, r), slice_cut(src.n_positions, N, r + 1), 0, 0, 0, nullptr,
+                                                  nullptr, &nr, &ns)) return e;
+            sh->nrec[r] = nr; sh->nstub[r] = ns;
+            return 0;
+        };
+        rc = exchange();
+        vlog("junction exchange, index, count pass done");
+        if (!sh->sync_ok(r, rc)) goto done;
+        uint64_t rb = 0, sb = 0;
+        for (int i = 0; i < r; ++i) { rb += sh->nrec[i]; sb += sh->nstub[i]; }
+        uint64_t nr = 0, ns = 0;
+        rc = tpc_session_emit_windowed(s, slice_cut(src.n_positions, N, r), slice_cut(src.n_positions, N, r + 1), 1, rb, sb, window_sink, &wctx, &nr, &ns);
+        if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) rc = set_error("emit failed");
+        if (rc == 0) rc = tpc_session_stats(s, &sh->stats[r]);
+        sh->digest[r][0] = wctx.digest[0]; sh->digest[r][1] = wctx.digest[1];
+        sh->slice_bytes[r] = wctx.end;   // (end of this GPU's part of the image)
+        vlog("write pass done");
+        sh->sync_ok(r, rc);
+        if (r == 0 && image_bytes_out) {
+            uint64_t end = 0;
+            for (int i = 0; i < N; ++i) end = std::max(end, sh->slice_bytes[i]);
+            // a slice without records reports 0: the image ends where the last record of any slice ends
+            *image_bytes_out = end;
+        }
+    }
+done:
+    cudaSetDevice(sh->dev[r]);
+    if (st) cudaStreamSynchronize(st);
+    if (d_allj) cudaFreeAsync(d_allj, st);
+    if (d_allk) cudaFreeAsync(d_allk, st);
+    if (s) { tpc_session_destroy(s); sh->session[r] = nullptr; }
+    delete prov;
+    if (wctx.pin) cudaFreeHost(wctx.pin);
+    if (st) cudaStreamDestroy(st);
+    return rc;
 }
 
 }  // namespace tpc
@@ -501,19 +681,55 @@ void tpc_multi_destroy(tpc_multi* m) { delete m; }
 
 uint32_t tpc_multi_gpus(const tpc_multi* m) { return m ? (uint32_t)m->impl.dev.size() : 0; }
 
-int tpc_multi_junctions_host(tpc_multi* m, const tpc_params* params, const tpc_genome* host_genome, uint8_t* out_image,
-                             uint64_t out_capacity, uint64_t* out_bytes, tpc_stats* stats) {
-    if (!m || !params || !host_genome || !out_image) return set_error("null argument");
+// position-windowed run? TPC_WINDOW_TILES=<tiles per window> forces it (0 = never); else when a GPU cannot hold the
+// packed genome (0.375 B per position), the candidate and stub masks (0.25 B) and the filter side by side
+static uint64_t choose_window_tiles(const tpc_multi* m, const tpc_params* params, uint64_t n_positions) {
+    if (const char* e = getenv("TPC_WINDOW_TILES")) return (uint64_t)std::max(0ll, atoll(e));
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(m->impl.dev[0]);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    cudaSetDevice(prev);
+    const double resident = 0.75 * (double)n_positions + (double)((1ull << std::max<uint32_t>(params->filter_bits, 9u)) / 8);
+    return resident > 0.85 * (double)total_b ? (1u << 17) : 0;   // 2^30 positions per window
+}
+
+static int multi_run_host(tpc_multi* m, const tpc_params* params, const tpc_genome* host_genome, const ImageSink& sink,
+                          uint64_t* out_bytes, tpc_stats* stats, uint64_t* digest) {
     GenomeSource src;
     src.host = host_genome;
     src.n_positions = host_genome->n_positions;
     src.rec_start = host_genome->rec_start; src.rec_len = host_genome->rec_len; src.n_records = host_genome->n_records;
+    src.window_tiles = choose_window_tiles(m, params, host_genome->n_positions);
+    uint64_t bytes = 0;
+    int rc = run_shards(&m->impl, *params, src, sink, false, &bytes, stats, nullptr, digest);
+    if (out_bytes) *out_bytes = bytes;
+    if (rc == 0 && stats) stats->out_bytes = bytes;
+    return rc;
+}
+
+int tpc_multi_junctions_host(tpc_multi* m, const tpc_params* params, const tpc_genome* host_genome, uint8_t* out_image,
+                             uint64_t out_capacity, uint64_t* out_bytes, tpc_stats* stats) {
+    if (!m || !params || !host_genome || !out_image) return set_error("null argument");
     ImageSink sink;
     sink.host_image = out_image; sink.host_capacity = out_capacity;
     uint64_t bytes = 0;
-    int rc = run_shards(&m->impl, *params, src, sink, false, &bytes, stats, nullptr);
+    int rc = multi_run_host(m, params, host_genome, sink, &bytes, stats, nullptr);
     if (out_bytes) *out_bytes = bytes;
+    if (rc == 0 && bytes > out_capacity) {
+        set_error("output buffer too small: need %llu bytes", (unsigned long long)bytes);
+        return 2;
+    }
     return rc;
+}
+
+int tpc_multi_junctions_digest(tpc_multi* m, const tpc_params* params, const tpc_genome* host_genome, uint64_t digest[2],
+                               uint64_t* image_bytes, tpc_stats* stats) {
+    if (!m || !params || !host_genome || !digest) return set_error("null argument");
+    ImageSink sink;
+    sink.digest_only = true;
+    return multi_run_host(m, params, host_genome, sink, image_bytes, stats, digest);
 }
 
 }  // extern "C"

@@ -20,6 +20,9 @@ public:
     // allgather(buffer, part_words, stream): in-place all-gather of `world` parts of part_words 64-bit words each (this
     // rank's part already sits at buffer + rank * part_words); unused when world == 1
     using AllGather = std::function<int(uint64_t* buffer, uint64_t part_words, cudaStream_t stream)>;
+    using Agree = std::function<bool(bool)>;   // logical OR over the shards (a host-side barrier between their threads)
+    void set_agree(Agree a) { agree_ = std::move(a); }
+    bool any_shard(bool mine) override { return agree_ ? agree_(mine) : mine; }
 
     HostWindowProvider(const uint64_t* codes, const uint64_t* nmask, uint64_t n_positions, uint64_t window_tiles, int rank, int world,
                        AllGather allgather)
@@ -130,6 +133,7 @@ private:
     uint64_t n_positions_, window_tiles_;
     int rank_, world_;
     AllGather allgather_;
+    Agree agree_;
     uint64_t* buf_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     uint64_t cap_[2] = {0, 0};
     uint64_t first_word_[2][2] = {{0, 0}, {0, 0}};

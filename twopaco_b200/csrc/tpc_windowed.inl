@@ -108,12 +108,15 @@ static int find_candidates_windowed(tpc_session* s) {
             float t = 0;
             cudaEventElapsedTime(&t, evs[0], evs[1]); ms_fill += t;
             cudaEventElapsedTime(&t, evs[1], evs[2]); ms_query += t;
-            if (cur.overflow == prev.overflow && (cur.distinct - prev.distinct) * 10 <= (7ull << lg)) break;
+            const bool too_small = !(cur.overflow == prev.overflow && (cur.distinct - prev.distinct) * 10 <= (7ull << lg));
+            if (!wp->any_shard(too_small)) break;   // (shards share the passes: they repeat a round together)
             Counters redo = prev;   // forget the round: marks, filter statistics and table counters
             CK(cudaMemcpyAsync(s->d_ctr, &redo, sizeof redo, cudaMemcpyHostToDevice, s->stream));
             cur = redo;
-            if (lg >= 31) return set_error("too many candidates for one round: use more rounds (-r)");
-            ++lg;
+            if (too_small) {
+                if (lg >= 31) return set_error("too many candidates for one round: use more rounds (-r)");
+                ++lg;
+            }
         }
         const TableView T{s->d_T, s->T_log2, 1u};
         const uint64_t distinct_r = cur.distinct - prev.distinct;
