@@ -452,43 +452,48 @@ def main() -> None:
                          "api": "tpc_junctions_host (pinned host genome -> pinned host de_bruijn.bin image)",
                          "image_digest_equals_device_run": [f"{d_host[0]:016x}", f"{d_host[1]:016x}"] == digest}
     elif not args.no_e2e:
-        # N GPUs, host buffers in / host buffers out (twopaco_b200.dist.sharded_run_host): every rank uploads
-        # 1/N of the packed genome from pinned host memory, chunk by chunk, NCCL all-gathers the chunks over
-        # NVLink while the first pass already runs on those that have arrived, runs its shard, and copies its
-        # slice of the image back to pinned host memory.  Wall clock between barriers, max over ranks.
-        from twopaco_b200 import dist as tdist
+        # N GPUs, host buffers in / host buffers out through the C ABI: rank 0 calls tpc_multi_junctions_host (one process, one
+        # host thread per GPU, every GPU uploads 1/N of each chunk of the packed genome from rank 0's pinned host memory over its
+        # own PCIe link, NCCL all-gathers the chunks over NVLink while the first pass already runs, every GPU copies its slice
+        # of the image back).  The other ranks of the launch free their GPUs and wait on the CPU.  Wall clock on rank 0.
+        cpu_group = torch.distributed.new_group(backend="gloo")
         runner.session.close()
         runner.out = None
-        L = api.lib()
-        cw, mw = L.tpc_code_words(dg.n_positions), L.tpc_mask_words(dg.n_positions)
-        shard = tdist.host_shard(cw, mw, dg.n_positions, dg.rec_start, dg.rec_len, rank, world, n_chunks=16,
-                                 fetch=lambda a, lo, hi: (dg.codes if a == 0 else dg.n_mask).to_host((hi - lo) * 8, lo * 8).view(np.uint64))
+        e2e = None
+        if rank == 0:
+            host = dg.to_host()
+            codes = torch.empty(len(host.codes), dtype=torch.int64, pin_memory=True)
+            nmask = torch.empty(len(host.n_mask), dtype=torch.int64, pin_memory=True)
+            codes.numpy().view(np.uint64)[:] = host.codes
+            nmask.numpy().view(np.uint64)[:] = host.n_mask
+            pinned = api.PackedGenome(codes.numpy().view(np.uint64), nmask.numpy().view(np.uint64), host.n_positions, host.rec_start, host.rec_len)
+            del host
         dg.codes.close(); dg.n_mask.close()                     # the e2e region starts from HOST buffers only
-        out_host, dev_out, times = None, None, []
-        for i in range(1 + max(1, min(args.steps, 3))):
-            barrier()
-            t0 = time.perf_counter()
-            info, out_host, dev_out = tdist.sharded_run_host(shard, rank, world, wl["k"], wl["f"], wl["q"], wl.get("rounds", 1),
-                                                             out_host, dev_out)
-            barrier()
-            if i:
-                times.append(time.perf_counter() - t0)
-        d_host = api.image_digest_host(out_host[:info["slice_bytes"]].numpy(), info["slice_offset"])
-        dt = torch.tensor([x - (1 << 64) if x >= (1 << 63) else x for x in d_host], dtype=torch.int64, device="cuda")
-        torch.distributed.all_reduce(dt)
-        d_all = [f"{int(x) & (2**64 - 1):016x}" for x in dt.tolist()]
-        t = torch.tensor([float(np.mean(times)), float(shard.nbytes), float(info["slice_bytes"])], dtype=torch.float64, device="cuda")
-        tmax = t.clone()
-        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
-        torch.distributed.all_reduce(t)
-        e2e_s = float(tmax[0].item())
-        result["e2e"] = {"value": round(total_bp / e2e_s / 1e9, 4), "unit": "Gbp/s",
-                         "h2d_bytes_per_step": int(t[1].item()), "d2h_bytes_per_step": int(t[2].item()),
-                         "ms_per_step": round(e2e_s * 1e3, 3),
-                         "api": "twopaco_b200.dist.sharded_run_host (each rank: pinned 1/N of the packed genome -> NCCL all-gather -> "
-                                "shard run -> its slice of the de_bruijn.bin image in pinned host memory)",
-                         "junctions": info["junctions"], "records": info["records"],
-                         "image_digest_equals_device_run": d_all == digest}
+        torch.cuda.empty_cache()
+        api.release_cached_memory()                             # (this process's pool: rank 0's threads need the GPU's memory)
+        torch.distributed.barrier(group=cpu_group)
+        if rank == 0:
+            out = torch.empty((timed_result["records"] + len(pinned.rec_len)) * 12 + 4096, dtype=torch.uint8, pin_memory=True).numpy()
+            mg = api.MultiGpu(world)
+            times = []
+            for i in range(1 + max(1, min(args.steps, 3))):
+                t0 = time.perf_counter()
+                img, st2 = mg.junctions_host(pinned, k=wl["k"], filter_bits=wl["f"], q=wl["q"], rounds=wl.get("rounds", 1), out=out)
+                if i:
+                    times.append(time.perf_counter() - t0)
+            mg.close()
+            e2e_s = float(np.mean(times))
+            d_host = api.image_digest_host(img)
+            e2e = {"value": round(total_bp / e2e_s / 1e9, 4), "unit": "Gbp/s",
+                   "h2d_bytes_per_step": int(pinned.codes.nbytes + pinned.n_mask.nbytes), "d2h_bytes_per_step": int(len(img)),
+                   "ms_per_step": round(e2e_s * 1e3, 3),
+                   "api": "tpc_multi_junctions_host (C ABI, one process: pinned host genome -> 1/N upload per GPU + NCCL all-gather -> "
+                          "hash-range shards -> de_bruijn.bin image in pinned host memory)",
+                   "junctions": st2.junctions, "records": st2.occurrences,
+                   "image_digest_equals_device_run": [f"{d_host[0]:016x}", f"{d_host[1]:016x}"] == digest}
+        torch.distributed.barrier(group=cpu_group)
+        if rank == 0:
+            result["e2e"] = e2e
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(sample_records(wl), wl)
@@ -507,9 +512,12 @@ def windowed_workload(args, wl, rank, world, local_rank) -> None:
     from tools import benchutil
     from twopaco_b200 import api
 
+    # the other ranks wait on the CPU (a gloo group): an NCCL barrier would spin on their GPUs, which rank 0's threads use
+    cpu_group = torch.distributed.new_group(backend="gloo") if world > 1 else None
+
     def barrier():
         if world > 1:
-            torch.distributed.barrier()
+            torch.distributed.barrier(group=cpu_group)
         torch.cuda.synchronize()
 
     result = None
@@ -528,7 +536,7 @@ def windowed_workload(args, wl, rank, world, local_rank) -> None:
                 return mg.junctions_digest(host, k=wl["k"], filter_bits=wl["f"], q=wl["q"], rounds=wl["rounds"])
             img, st = api.junctions_host(host, k=wl["k"], filter_bits=wl["f"], q=wl["q"], rounds=wl["rounds"], out=out)
             out = img.base if img.base is not None else img
-            return api.image_digest_host(img), len(img), st
+            return img, len(img), st
 
         for _ in range(max(args.warmup, 0)):
             step()
@@ -540,10 +548,14 @@ def windowed_workload(args, wl, rank, world, local_rank) -> None:
                 digest, nbytes, st = step()
                 times.append(time.perf_counter() - t0)
         sec = float(np.mean(times))
+        if not mg:
+            digest = api.image_digest_host(digest)   # (one GPU: the image came back; its digest is computed outside the timed region)
         verify = None
         if not args.no_verify and wl["f"] <= 34:   # (small enough for the resident path: same digest?)
             os.environ["TPC_WINDOW_TILES"] = "0"
             d2, n2, _ = step()
+            if not mg:
+                d2 = api.image_digest_host(d2)
             verify = {"windowed_equals_resident": d2 == digest and n2 == nbytes}
             os.environ["TPC_WINDOW_TILES"] = str(wl["windowed"])
         if mg:

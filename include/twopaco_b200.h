@@ -272,6 +272,9 @@ int tpc_graphdump_file(const char *image_path, const char *format, const char *o
 int tpc_canonical_image_device(const uint8_t *dev_image, uint64_t image_bytes, void *stream, uint8_t *dev_out,
                                uint64_t *n_classes);
 
+/* Sessions allocate from the current device's stream-ordered pool, which keeps freed memory for the next run; this
+ * hands it back to the driver (e.g. before another process uses the GPU). */
+int tpc_release_cached_memory(void);
 int tpc_device_alloc(uint64_t bytes, void **out);
 void tpc_device_free(void *p);
 int tpc_copy_to_host(void *host_dst, const void *dev_src, uint64_t bytes);

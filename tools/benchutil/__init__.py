@@ -91,7 +91,8 @@ def synth_family_host(seed: int, genomes: int, records_per_genome: int, record_l
     # upper bound of the positions (insertions lengthen a record by ~ p / 10)
     max_pos = 1 + n_rec * (int(record_len * (1 + p)) + 64)
     cw_cap, mw_cap = P.tpc_code_words(max_pos), P.tpc_mask_words(max_pos)
-    mk = (lambda n: torch.empty(n, dtype=torch.int64).pin_memory()) if pin else (lambda n: torch.empty(n, dtype=torch.int64))
+    # (pinned memory is allocated as such: pinning a pageable copy would need the 116 GB of C5 twice)
+    mk = (lambda n: torch.empty(n, dtype=torch.int64, pin_memory=True)) if pin else (lambda n: torch.empty(n, dtype=torch.int64))
     codes, nmask = mk(cw_cap), mk(mw_cap)
     codes_np, nmask_np = codes.numpy().view(np.uint64), nmask.numpy().view(np.uint64)
     rec_start = np.empty(n_rec, dtype=np.uint64)

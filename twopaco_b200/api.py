@@ -95,6 +95,7 @@ SIGNATURES = {
     "tpc_graphdump_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "tpc_graphdump_file": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p]),
     "tpc_canonical_image_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "tpc_release_cached_memory": (C.c_int, []),
     "tpc_device_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
     "tpc_device_free": (None, [C.c_void_p]),
     "tpc_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -386,6 +387,10 @@ class Session:
             self.close()
         except Exception:
             pass
+
+
+def release_cached_memory() -> None:
+    _check(lib().tpc_release_cached_memory())
 
 
 def image_digest_device(dev_ptr: int, nbytes: int, image_offset: int = 0, stream: int = 0) -> tuple[int, int]:

@@ -120,6 +120,16 @@ int tpc_image_digest_device(const uint8_t* dev_image, uint64_t nbytes, uint64_t 
     return 0;
 }
 
+int tpc_release_cached_memory(void) {
+    int dev = 0;
+    CKS(cudaGetDevice(&dev));
+    CKS(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    CKS(cudaDeviceGetDefaultMemPool(&pool, dev));
+    CKS(cudaMemPoolTrimTo(pool, 0));
+    return 0;
+}
+
 int tpc_device_alloc(uint64_t bytes, void** out) {
     if (!out) return set_error("null argument");
     CKS(cudaMalloc(out, std::max<uint64_t>(bytes, 16)));
