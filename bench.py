@@ -79,16 +79,22 @@ def golden_digest(workload: str):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi samples of one GPU's clocks and throttle reasons every 50 ms.  Started before the warm-up steps (nvidia-smi needs
+    about a second to come up on an 8-GPU box) and asked for the samples that fell inside [mark_begin(), mark_end()]; rank 0 only --
+    eight nvidia-smi loops contend for the driver."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, enabled: bool = True):
+        self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
+        self.t0 = self.t1 = None
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -97,20 +103,31 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *exc):
         if self.proc:
+            if self.t1 is not None:
+                time.sleep(0.12)   # the sample taken at the end of the region is still being printed
             self.proc.terminate()
             self.thread.join(timeout=2)
 
     def summary(self) -> dict:
-        sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        lo = self.t0 if self.t0 is not None else float("-inf")
+        hi = (self.t1 if self.t1 is not None else float("inf")) + 0.06
+        rows = [r for t, r in self.rows if lo <= t <= hi and len(r) >= 6]
+        sm = [int(r[0]) for r in rows if r[0].isdigit()]
+        mx = [int(r[1]) for r in rows if r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[2 + i].lower() == "active"})
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "samples_outside_region": len(self.rows) - len(rows)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -275,15 +292,16 @@ def main() -> None:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 0)):
-        runner.step()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_keys = ("ms_bin", "ms_bin_overlapped", "ms_fill", "ms_query", "ms_insert", "ms_classify", "ms_index", "ms_emit")
     wall_keys = ("ms_wall_candidates", "ms_wall_index", "ms_wall_emit")
     stage_ms = {k: 0.0 for k in stage_keys + wall_keys}
     launches = 0
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clocks:
+        for _ in range(max(args.warmup, 0)):
+            runner.step()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks.mark_begin()
         ev0.record()
         for _ in range(args.steps):
             runner.step()
@@ -293,6 +311,7 @@ def main() -> None:
             launches += st.kernel_launches
         ev1.record()
         barrier()
+        clocks.mark_end()
     ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -542,11 +561,13 @@ def windowed_workload(args, wl, rank, world, local_rank) -> None:
             step()
         times = []
         with ClockSampler(local_rank) as clocks:
+            clocks.mark_begin()
             for _ in range(args.steps):
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 digest, nbytes, st = step()
                 times.append(time.perf_counter() - t0)
+            clocks.mark_end()
         sec = float(np.mean(times))
         if not mg:
             digest = api.image_digest_host(digest)   # (one GPU: the image came back; its digest is computed outside the timed region)

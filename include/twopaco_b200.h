@@ -73,6 +73,8 @@ typedef struct tpc_stats {
     float ms_wall_candidates;    /* host wall clock of tpc_session_find_candidates (kernels + memsets + allocations +
                                     host synchronisations), so that time outside the CUDA-event stage times is visible */
     float ms_wall_index, ms_wall_emit;   /* the same for set_junctions and emit_count + emit_write */
+    uint32_t skew_rebins;        /* binned path: rounds whose slices overflowed (repeat-rich input) and were re-binned into
+                                    arrays sized from the exact per-slice record counts */
 } tpc_stats;
 
 /* ------------------------------------------------------------------------------------------

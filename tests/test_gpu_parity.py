@@ -368,11 +368,20 @@ def test_binned_rounds_and_shards(monkeypatch, golden):
         recs = api.read_fasta(paths)
     img, st = api.junctions_host(api.pack_records(recs), k=25, filter_bits=20, q=3, rounds=3)
     assert st.ms_bin > 0 and canon_md5(bytes(img)) == g["canon_md5"]
-    # skew: a genome that is one k-mer repeated sends every record to a single slice (overflow path)
+    # skew: a genome that is one k-mer repeated sends every record to a single slice: the slice's array and the overflow
+    # list run over, the round is re-binned into arrays sized from the exact per-slice counts (no fall-back to the direct kernels)
     rep = [b"ACGTTGCA" * 40_000, b"ACGTTGCA" * 30_000 + b"T"]
     ref, nj, _ = O.find_junctions(rep, 25)
     img, st = api.junctions_host(api.pack_records(rep), k=25, filter_bits=22, q=5)
-    assert bytes(img) == ref   # (falls back to the direct kernels when the overflow area is exceeded)
+    assert bytes(img) == ref
+    assert st.skew_rebins == 1 and st.bin_waves == 1
+    # a repeat-rich family (5 % microsatellite / poly-A runs inside otherwise random genomes), with sub-rounds
+    rich = synth.founder_family(4711, 5, 2, 60_000, 0.01)
+    rich = [r[:20_000] + b"A" * 1500 + r[20_000:40_000] + b"AC" * 800 + r[40_000:] for r in rich]
+    ref, nj, _ = O.find_junctions(rich, 25)
+    monkeypatch.setenv("TPC_SUBROUNDS", "2")
+    img, st = api.junctions_host(api.pack_records(rich), k=25, filter_bits=20, q=3)
+    assert bytes(img) == ref and st.ms_bin > 0 and st.junctions == nj
 
 
 @pytest.mark.parametrize("sub,user_rounds", [(2, 1), (3, 1), (5, 2), (9, 2)])

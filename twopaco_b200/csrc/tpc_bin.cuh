@@ -31,6 +31,14 @@ struct BinView {
     uint32_t bucket_bits;          // log2(#slices)
     uint32_t sib_bits;             // log2(sectors per slice) <= 25
     uint32_t q;                    // Bloom bits per edge (the apply kernels expand the mask seed)
+    // Skewed inputs (repeat-rich genomes: every copy of a k-mer goes to one slice): when a slice's array and the overflow
+    // list both ran over, the round is re-binned into arrays sized from the exact per-slice counts of the failed attempt:
+    // slice b then owns records [off[b], off[b] + capv[b]) of the scratch (three arrays of capv[b] words at rec + 3 off[b]).
+    // nullptr = the uniform layout (off[b] = b * cap, capv[b] = cap).
+    const unsigned long long* off;
+    const unsigned long long* capv;
+    __device__ __forceinline__ uint32_t* block_of(uint32_t b) const { return rec + 3 * (off ? off[b] : (uint64_t)b * cap); }
+    __device__ __forceinline__ uint64_t cap_of(uint32_t b) const { return capv ? capv[b] : cap; }
 };
 
 // record word 1 carries the 6-bit occurrence code in canonical orientation (occurrence_code, tpc_device.cuh)
@@ -135,13 +143,14 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
                 if (!n) continue;
                 uint32_t s0 = pref[b];
                 unsigned long long gb = gbase[b];
-                uint32_t* ra = bin.rec + (uint64_t)b * 3 * bin.cap;
+                uint32_t* ra = bin.block_of(b);
+                const uint64_t bcap = bin.cap_of(b);
                 for (uint32_t j = lane; j < n; j += 32) {
                     unsigned long long dst = gb + j;
-                    if (dst < bin.cap) {
+                    if (dst < bcap) {
                         __stcs(ra + dst, st_a[s0 + j]);
-                        __stcs(ra + bin.cap + dst, st_b[s0 + j]);
-                        __stcs(ra + 2 * bin.cap + dst, st_c[s0 + j]);
+                        __stcs(ra + bcap + dst, st_b[s0 + j]);
+                        __stcs(ra + 2 * bcap + dst, st_c[s0 + j]);
                     } else {
                         unsigned long long o = atomicAdd(bin.ov_count, 1ull);
                         if (o < bin.ov_cap) {
@@ -411,8 +420,8 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
             }
             if (hc) {
                 gbase[tid] = gb;
-                gptr[tid] = bin.rec + (uint64_t)tid * 3 * bin.cap + gb - my_pref;   // + stage index = the record's place
-                if (gb + hc > bin.cap) list_total[1] = 1;
+                gptr[tid] = bin.block_of(tid) + gb - my_pref;   // + stage index = the record's place
+                if (gb + hc > bin.cap_of(tid) || bin.capv) list_total[1] = 1;   // (per-slice capacities: the general copy-out)
             }
             __syncthreads();
             // copy-out: one thread per staged record (records of a slice are contiguous in the stage, so
@@ -429,11 +438,12 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
                 for (uint32_t idx = tid; idx < n; idx += kTileThreads) {
                     const uint32_t b = st_k[idx];
                     const unsigned long long dst = gbase[b] + (idx - pref[b]);
-                    if (dst < bin.cap) {
-                        uint32_t* ra = bin.rec + (uint64_t)b * 3 * bin.cap + dst;
+                    const uint64_t bcap = bin.cap_of(b);
+                    if (dst < bcap) {
+                        uint32_t* ra = bin.block_of(b) + dst;
                         __stcs(ra, st_a[idx]);
-                        __stcs(ra + bin.cap, st_b[idx]);
-                        __stcs(ra + 2 * bin.cap, st_c[idx]);
+                        __stcs(ra + bcap, st_b[idx]);
+                        __stcs(ra + 2 * bcap, st_c[idx]);
                     } else {
                         unsigned long long o = atomicAdd(bin.ov_count, 1ull);
                         if (o < bin.ov_cap) reinterpret_cast<uint4*>(bin.ov)[o] = make_uint4(st_a[idx], st_b[idx], st_c[idx], b);

@@ -169,19 +169,27 @@ static int apply_grid(const LaunchCtx& c) { return c.sm_count * (c.apply_ctas > 
         default: { constexpr int Q = 8; __VA_ARGS__; } break;  \
     }
 
-cudaError_t launch_apply_fill(const LaunchCtx& c, uint32_t* filter, const BinView& bv, uint32_t bucket, Counters* ctr) {
+// where slice `bucket`'s records live: uniform layout, or the per-slice one of a re-binned skewed round (host copies)
+struct SliceLayout {
+    const std::vector<unsigned long long>* off = nullptr;
+    const std::vector<unsigned long long>* capv = nullptr;
+    const uint32_t* base(const BinView& bv, uint32_t b) const { return bv.rec + 3 * (off ? (*off)[b] : (uint64_t)b * bv.cap); }
+    uint64_t cap(const BinView& bv, uint32_t b) const { return capv ? (*capv)[b] : bv.cap; }
+};
+
+cudaError_t launch_apply_fill(const LaunchCtx& c, uint32_t* filter, const BinView& bv, const SliceLayout& sl, uint32_t bucket, Counters* ctr) {
     uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
     TPC_APPLY_Q_SWITCH(bv.q, (k_apply_fill<Q><<<apply_grid(c), 256, 0, c.stream>>>(
-        slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap, (1u << bv.sib_bits) - 1u, ctr)));
+        slice, sl.base(bv, bucket), bv.count + bucket, sl.cap(bv, bucket), (1u << bv.sib_bits) - 1u, ctr)));
     ++*c.launches;
     return cudaGetLastError();
 }
 
-cudaError_t launch_apply_query(const LaunchCtx& c, const uint32_t* filter, const BinView& bv, uint32_t bucket, uint32_t* mask,
-                               uint64_t wave_base, Counters* ctr, uint32_t* hll, const MarkList& ml) {
+cudaError_t launch_apply_query(const LaunchCtx& c, const uint32_t* filter, const BinView& bv, const SliceLayout& sl, uint32_t bucket,
+                               uint32_t* mask, uint64_t wave_base, Counters* ctr, uint32_t* hll, const MarkList& ml) {
     const uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
     TPC_APPLY_Q_SWITCH(bv.q, (k_apply_query<Q><<<apply_grid(c), 256, 0, c.stream>>>(
-        slice, bv.rec + (uint64_t)bucket * 3 * bv.cap, bv.count + bucket, bv.cap, bv.sib_bits, mask, wave_base, ctr, hll,
+        slice, sl.base(bv, bucket), bv.count + bucket, sl.cap(bv, bucket), bv.sib_bits, mask, wave_base, ctr, hll,
         (uint64_t)bucket << bv.sib_bits, ml)));
     ++*c.launches;
     return cudaGetLastError();
@@ -259,6 +267,10 @@ struct tpc_session {
     unsigned long long* d_bin_count = nullptr;
     uint32_t* d_bin_ov = nullptr;
     BinView bin_view{};             // layout of the scratch, fixed for all rounds of a call
+    // per-slice layout of a re-binned skewed round (BinView::off / capv): host copies + device arrays
+    std::vector<unsigned long long> skew_off, skew_cap;
+    unsigned long long* d_skew = nullptr;   // [2][buckets]
+    uint32_t skew_rebins = 0;
     uint64_t bin_wave_tiles = 0, bin_nwaves = 0;
     bool bin_ready = false;
     bool used_binned = false;
@@ -414,7 +426,7 @@ void tpc_session_destroy(tpc_session* s) {
     if (s->windowed) { s->d_mask = nullptr; s->d_stubmask = nullptr; }   // (views of d_wmask / d_wstub)
     void* ptrs[] = {s->d_codes, s->d_nmask, s->d_rec_start, s->d_rec_len, s->d_sep_before, s->d_filter, s->d_mask,
                     s->d_stubmask, s->d_T, s->d_J, s->d_local, s->d_sorted, s->d_sort_tmp, s->d_ctr, s->d_id,
-                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch, s->d_marklist, s->d_marklist_counts, s->d_wmask, s->d_wstub, s->d_local_keys, s->d_bin_rec, s->d_bin_count, s->d_bin_ov, s->d_hll, s->d_own_extra};
+                    s->d_tile_rec, s->d_tile_stub, s->d_scan_scratch, s->d_marklist, s->d_marklist_counts, s->d_skew, s->d_wmask, s->d_wstub, s->d_local_keys, s->d_bin_rec, s->d_bin_count, s->d_bin_ov, s->d_hll, s->d_own_extra};
     for (void* p : ptrs)
         dev_free(p, s->stream);
     cudaStreamSynchronize(s->stream);
@@ -679,7 +691,9 @@ static int binned_release(tpc_session* s) {
 static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin, float* ms_fill, float* ms_query) {
     if (int rc = binned_setup(s, kp)) return rc;
     LaunchCtx lc = s->lctx();
-    const BinView bv = s->bin_view;
+    BinView bv = s->bin_view;       // (uniform layout; a skewed round switches this copy to per-slice capacities)
+    SliceLayout sl;
+    bool skew_layout = false;
     const uint32_t buckets = 1u << bv.bucket_bits;
     const uint64_t wave_tiles = s->bin_wave_tiles, nwaves = s->bin_nwaves;
     Events evs(3);
@@ -730,12 +744,42 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
             }
             CK(cudaEventRecord(e1, s->stream));
             for (uint32_t b = 0; b < buckets; ++b) {
-                if (pass == 0) CK(launch_apply_fill(lc, s->d_filter, bv, b, s->d_ctr));
-                else CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, base, s->d_ctr, s->d_hll, s->mark_list(true)));
+                if (pass == 0) CK(launch_apply_fill(lc, s->d_filter, bv, sl, b, s->d_ctr));
+                else CK(launch_apply_query(lc, s->d_filter, bv, sl, b, s->d_mask, base, s->d_ctr, s->d_hll, s->mark_list(true)));
             }
             CK(launch_apply_overflow(lc, s->d_filter, bv, pass, s->d_mask, base, s->d_ctr, s->d_hll, s->mark_list(pass == 1)));
             CK(cudaEventRecord(e2, s->stream));
             rc = finish_wave(ms_bin, pass == 0 ? ms_fill : ms_query);
+            if (rc == 0 && pass == 0 && nwaves == 1 && ov_now > bv.ov_cap && !skew_layout) {
+                // Skewed input: slices ran over their arrays AND the overflow list.  The reservation counters hold the exact
+                // number of records of every slice: re-bin this round into arrays of exactly those sizes (one more binning
+                // pass instead of the direct kernels for the whole round) and fill again -- the bits already set are correct.
+                std::vector<unsigned long long> cnt(buckets);
+                CK(cudaMemcpyAsync(cnt.data(), bv.count, buckets * 8, cudaMemcpyDeviceToHost, s->stream));
+                CK(cudaStreamSynchronize(s->stream));
+                s->skew_off.assign(buckets, 0);
+                s->skew_cap.assign(buckets, 0);
+                unsigned long long total = 0;
+                for (uint32_t b = 0; b < buckets; ++b) {
+                    s->skew_cap[b] = (cnt[b] + cnt[b] / 64 + 1024 + 31) / 32 * 32;
+                    s->skew_off[b] = total;
+                    total += s->skew_cap[b];
+                }
+                if (total * 12 <= s->bin_rec_bytes) {
+                    if (!s->d_skew) CK(dev_alloc(&s->d_skew, (uint64_t)2 * kBinMaxBuckets * 8, s->stream));
+                    CK(cudaMemcpyAsync(s->d_skew, s->skew_off.data(), buckets * 8, cudaMemcpyHostToDevice, s->stream));
+                    CK(cudaMemcpyAsync(s->d_skew + kBinMaxBuckets, s->skew_cap.data(), buckets * 8, cudaMemcpyHostToDevice, s->stream));
+                    bv.off = s->d_skew;
+                    bv.capv = s->d_skew + kBinMaxBuckets;
+                    sl.off = &s->skew_off;
+                    sl.capv = &s->skew_cap;
+                    skew_layout = true;
+                    ++s->skew_rebins;
+                    ov_total = 0;
+                    --wv;            // the same wave again, with the new layout
+                    continue;
+                }
+            }
         }
     }
     if (rc) return rc;
@@ -802,12 +846,13 @@ static int filter_passes_pipelined(tpc_session* s, uint32_t r, const KParams& kp
         s->pipe_round[h ^ 1] = r + 1;
         lc.apply_ctas = s->pipe_fill_ctas;   // share the SMs with the binning kernel
     }
-    for (uint32_t b = 0; b < buckets; ++b) CK(launch_apply_fill(lc, s->d_filter, bv, b, s->d_ctr));
+    const SliceLayout sl;   // (pipelined rounds keep the uniform layout; a skewed round falls back)
+    for (uint32_t b = 0; b < buckets; ++b) CK(launch_apply_fill(lc, s->d_filter, bv, sl, b, s->d_ctr));
     CK(launch_apply_overflow(lc, s->d_filter, bv, 0, s->d_mask, 0, s->d_ctr, s->d_hll, s->mark_list(false)));
     CK(cudaEventRecord(e2, s->stream));
     if (has_next) CK(cudaStreamWaitEvent(s->stream, s->pipe_ev[h ^ 1], 0));   // the query runs alone, at full occupancy
     lc.apply_ctas = s->apply_ctas;
-    for (uint32_t b = 0; b < buckets; ++b) CK(launch_apply_query(lc, s->d_filter, bv, b, s->d_mask, 0, s->d_ctr, s->d_hll, s->mark_list(true)));
+    for (uint32_t b = 0; b < buckets; ++b) CK(launch_apply_query(lc, s->d_filter, bv, sl, b, s->d_mask, 0, s->d_ctr, s->d_hll, s->mark_list(true)));
     CK(launch_apply_overflow(lc, s->d_filter, bv, 1, s->d_mask, 0, s->d_ctr, s->d_hll, s->mark_list(true)));
     CK(cudaEventRecord(e3, s->stream));
     unsigned long long ov_now = 0;
@@ -1212,6 +1257,7 @@ int tpc_session_stats(tpc_session* s, tpc_stats* out) {
     if (s->st.out_bytes && cudaEventElapsedTime(&t, s->ev[7], s->ev[8]) == cudaSuccess) s->st.ms_emit = t;
     s->st.ms_total = s->st.ms_bin + s->st.ms_fill + s->st.ms_query + s->st.ms_insert + s->st.ms_classify + s->st.ms_index + s->st.ms_emit;
     s->st.kernel_launches = s->launches;
+    s->st.skew_rebins = s->skew_rebins;
     *out = s->st;
     return 0;
 }
