@@ -5,5 +5,6 @@ O=gpurun_out
 mkdir -p $O
 free -g > $O/r2c5_c5_mem.txt
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-TPC_VERBOSE=1 timeout 540 $TR --master-port 29554 bench.py --gpus 8 --workload c5 --steps 1 --warmup 1 > $O/r2c5_bench_c5_n8.json 2> $O/r2c5_bench_c5_n8.err
+TPC_VERBOSE=1 timeout 560 $TR --master-port 29554 bench.py --gpus 8 --workload c5 --steps 1 --warmup 0 > $O/r2c5_bench_c5_n8.json 2> $O/r2c5_bench_c5_n8.err
+echo "rc=$?" >> $O/r2c5_c5_mem.txt
 echo done
