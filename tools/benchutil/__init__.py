@@ -39,6 +39,8 @@ def lib() -> C.CDLL:
         L.tpcb_slice_probe.restype = C.c_int
         L.tpcb_slice_probe.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.POINTER(C.c_double)]
+        L.tpcb_rank_probe.restype = C.c_int
+        L.tpcb_rank_probe.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -67,6 +69,13 @@ def random_access_probe(filter_bits: int, mode: int, touches: int = 1 << 30) -> 
     mode 0 = 32-byte loads, 1 = atomicOr, 2 = load + conditional atomicOr."""
     v = C.c_double()
     _check(lib().tpcb_random_access_probe(filter_bits, mode, touches, C.byref(v)))
+    return v.value
+
+
+def rank_probe(mode: int, buckets: int = 128, rounds: int = 2000) -> float:
+    """Records ranked per second by the inner step of a CTA-level counting sort (see tpcb_rank_probe)."""
+    v = C.c_double()
+    _check(lib().tpcb_rank_probe(mode, buckets, rounds, C.byref(v)))
     return v.value
 
 

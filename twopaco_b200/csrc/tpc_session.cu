@@ -155,28 +155,6 @@ cudaError_t launch_scan_exclusive(const LaunchCtx& c, unsigned long long* data, 
     return cudaGetLastError();
 }
 
-// L2 persistence (TPC_L2_PERSIST=1): an access-policy window over the slice of the next apply launch marks its lines
-// persisting and everything else on the stream (the record stream) streaming, so that set conflicts of the 64 MiB slice with
-// the in-flight stream do not evict slice lines (ncu: ~30 % of the slice is fetched twice without it).
-static bool g_l2_persist = false;
-static void set_slice_window(cudaStream_t st, const void* slice, size_t bytes) {
-    if (!g_l2_persist) return;
-    cudaStreamAttrValue attr{};
-    attr.accessPolicyWindow.base_ptr = const_cast<void*>(slice);
-    attr.accessPolicyWindow.num_bytes = bytes;
-    attr.accessPolicyWindow.hitRatio = 1.0f;
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
-}
-static void clear_slice_window(cudaStream_t st) {
-    if (!g_l2_persist) return;
-    cudaStreamAttrValue attr{};
-    attr.accessPolicyWindow.num_bytes = 0;
-    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
-    cudaCtxResetPersistingL2Cache();
-}
-
 static int apply_grid(const LaunchCtx& c) { return c.sm_count * (c.apply_ctas > 0 && c.apply_ctas < 4 ? c.apply_ctas : 4); }
 
 #define TPC_APPLY_Q_SWITCH(q, ...)                             \
@@ -201,7 +179,6 @@ struct SliceLayout {
 
 cudaError_t launch_apply_fill(const LaunchCtx& c, uint32_t* filter, const BinView& bv, const SliceLayout& sl, uint32_t bucket, Counters* ctr) {
     uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
-    set_slice_window(c.stream, slice, (size_t)32 << bv.sib_bits);
     TPC_APPLY_Q_SWITCH(bv.q, (k_apply_fill<Q><<<apply_grid(c), 256, 0, c.stream>>>(
         slice, sl.base(bv, bucket), bv.count + bucket, sl.cap(bv, bucket), (1u << bv.sib_bits) - 1u, ctr)));
     ++*c.launches;
@@ -211,7 +188,6 @@ cudaError_t launch_apply_fill(const LaunchCtx& c, uint32_t* filter, const BinVie
 cudaError_t launch_apply_query(const LaunchCtx& c, const uint32_t* filter, const BinView& bv, const SliceLayout& sl, uint32_t bucket,
                                uint32_t* mask, uint64_t wave_base, Counters* ctr, uint32_t* hll, const MarkList& ml) {
     const uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
-    set_slice_window(c.stream, slice, (size_t)32 << bv.sib_bits);
     TPC_APPLY_Q_SWITCH(bv.q, (k_apply_query<Q><<<apply_grid(c), 256, 0, c.stream>>>(
         slice, sl.base(bv, bucket), bv.count + bucket, sl.cap(bv, bucket), bv.sib_bits, mask, wave_base, ctr, hll,
         (uint64_t)bucket << bv.sib_bits, ml)));
@@ -221,7 +197,6 @@ cudaError_t launch_apply_query(const LaunchCtx& c, const uint32_t* filter, const
 
 cudaError_t launch_apply_overflow(const LaunchCtx& c, uint32_t* filter, const BinView& bv, int do_query, uint32_t* mask,
                                   uint64_t wave_base, Counters* ctr, uint32_t* hll, const MarkList& ml) {
-    clear_slice_window(c.stream);   // (runs after the last slice of a pass)
     k_apply_overflow<<<c.sm_count, 256, 0, c.stream>>>(filter, bv.ov, bv.ov_count, bv.ov_cap, bv.sib_bits, bv.q, do_query, mask,
                                                        wave_base, ctr, hll, ml);
     ++*c.launches;
@@ -430,14 +405,6 @@ int tpc_session_create(const tpc_params* params, void* stream, tpc_session** out
     if (const char* e = getenv("TPC_PIPE_FILL_CTAS")) s->pipe_fill_ctas = std::max(1, atoi(e));
     if (const char* e = getenv("TPC_BIN_CTAS")) s->bin_ctas = atoi(e);
     if (const char* e = getenv("TPC_APPLY_CTAS")) s->apply_ctas = atoi(e);
-    g_l2_persist = getenv("TPC_L2_PERSIST") && atoi(getenv("TPC_L2_PERSIST")) != 0;
-    if (g_l2_persist) {
-        int max_persist = 0, cur_dev = 0;
-        cudaGetDevice(&cur_dev);
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cur_dev);
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
-        if (getenv("TPC_VERBOSE")) fprintf(stderr, "[tpc] L2 persisting carve-out: %d MiB\n", max_persist >> 20);
-    }
     s->rounds_eff = params->rounds;
     cudaGetDevice(&s->device);
     configure_pool(s->device);
