@@ -819,3 +819,31 @@ def test_windowed_run_edge_cases(monkeypatch):
     # longer k-mers keep position-identified slots, which read the genome back: not available windowed
     with pytest.raises(api.TpcError, match="k <= 31"):
         api.junctions_host(api.pack_records(recs), k=63, filter_bits=18)
+
+
+@pytest.mark.parametrize("name", ["family_k25", "family_k63", "selftest_s2_k9", "edge_mixed_k5", "family_seam_k25"])
+def test_list_driven_direct_passes(name, golden, monkeypatch):
+    """Hash-range rounds / shards on the DIRECT filter kernels: owned positions compacted per tile and processed densely
+    (k_direct_list; default) or every position rolled with an inline ownership test (k_fill / k_query, TPC_DIRECT_LIST=0)."""
+    spec, g = CASES[name], golden[name]
+    with case_files(spec) as (paths, _, _):
+        recs = api.read_fasta(paths)
+    gen = api.pack_records(recs)
+    monkeypatch.setenv("TPC_FILTER_MODE", "direct")
+    images = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TPC_DIRECT_LIST", flag)
+        img, st = api.junctions_host(gen, k=spec["k"], filter_bits=18, q=3, rounds=3)
+        assert st.ms_bin == 0 and canon_md5(bytes(img)) == g["canon_md5"] and st.junctions == g["distinct_junctions"]
+        images.append(bytes(img))
+    assert images[0] == images[1]
+    # shards: both shards' junction counts add up
+    monkeypatch.setenv("TPC_DIRECT_LIST", "1")
+    total = 0
+    for i in range(3):
+        s = api.Session(k=spec["k"], filter_bits=18, shard_index=i, shard_count=3)
+        s.set_genome_host(gen)
+        s.find_candidates()
+        total += s.local_junctions()[1]
+        s.close()
+    assert total == g["distinct_junctions"]

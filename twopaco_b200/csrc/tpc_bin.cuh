@@ -173,71 +173,47 @@ k_bin(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_
 // CTA-wide list and runs the expensive part (64-bit hash, record, counting sort by slice) densely
 // on it.  One scan serves all the rounds of this GPU: the local round that owns a position
 // (1 + round, 0 = none / not a definite k-mer) is written as P bit planes of 1 bit per position.
+// ownership of the 32 positions of code word w: pl[j] = bit plane j of the owning local round (1 + part - part_base when that is
+// < nlocal, else 0) -- shared by k_own (planes for all the rounds of a call) and the list-driven direct kernels (P = 1, one part)
 template <int W, int P>
-__global__ void __launch_bounds__(kTileThreads)
-k_own(GenomeView g, KParams kp, uint32_t part_base, uint32_t nlocal, uint64_t word_begin, uint64_t word_end, OwnPlanes op) {
-    for (uint64_t w = word_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < word_end;
-         w += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t pl[P];
+__device__ __forceinline__ void own_planes_of_word(const GenomeView& g, const KParams& kp, uint32_t part_base, uint32_t nlocal, uint64_t w,
+                                                   uint32_t (&pl)[P]) {
 #pragma unroll
-        for (int j = 0; j < P; ++j) pl[j] = 0;
-        if (w * 32 < g.npos) {
-            {
-                uint32_t valid = ~0u;
-                if (w == 0 || any_n(g.nmask, w * 32, 32 + kp.k)) {
-                    valid = 0;
-                    uint32_t run = 0;
+    for (int j = 0; j < P; ++j) pl[j] = 0;
+    if (w * 32 < g.npos) {
+        {
+            uint32_t valid = ~0u;
+            if (w == 0 || any_n(g.nmask, w * 32, 32 + kp.k)) {
+                valid = 0;
+                uint32_t run = 0;
 #pragma unroll 1
-                    for (uint32_t j = 0; j + 1 < kp.k; ++j) run = load_n(g.nmask, w * 32 + j) ? 0 : run + 1;
+                for (uint32_t j = 0; j + 1 < kp.k; ++j) run = load_n(g.nmask, w * 32 + j) ? 0 : run + 1;
 #pragma unroll 1
-                    for (uint32_t i = 0; i < 32; ++i) {
-                        run = load_n(g.nmask, w * 32 + i + kp.k - 1) ? 0 : run + 1;
-                        if (run >= kp.k) valid |= 1u << i;
-                    }
+                for (uint32_t i = 0; i < 32; ++i) {
+                    run = load_n(g.nmask, w * 32 + i + kp.k - 1) ? 0 : run + 1;
+                    if (run >= kp.k) valid |= 1u << i;
                 }
-                if (kp.k >= kOwnMid) {
-                    // ownership key = canonical middle 11-mer (owner_fold): A = the 64-base window shifted to the
-                    // middle of position 0's k-mer, B = its reverse complement; position i's middle 11-mer is bases
-                    // i.. of A and its reverse complement bases 53-i.. of B -- one constant funnel shift each
-                    // (any k >= 11, one to four words per k-mer: only the three code words around the middle are read)
-                    const uint32_t off = (kp.k - kOwnMid) >> 1, off2 = 2 * (off & 31);
-                    const uint64_t* cw = g.codes + w + (off >> 5);
-                    const uint64_t c0 = __ldg(cw), c1 = __ldg(cw + 1), c2 = __ldg(cw + 2);
-                    const uint64_t a0 = off2 ? (c0 >> off2) | (c1 << (64 - off2)) : c0;
-                    const uint64_t a1 = off2 ? (c1 >> off2) | (c2 << (64 - off2)) : c1;
-                    const uint64_t b0 = pairrev64(~a1), b1 = pairrev64(~a0);
-                    const uint32_t A[4] = {(uint32_t)a0, (uint32_t)(a0 >> 32), (uint32_t)a1, (uint32_t)(a1 >> 32)};
-                    const uint32_t B[5] = {(uint32_t)b0, (uint32_t)(b0 >> 32), (uint32_t)b1, (uint32_t)(b1 >> 32), 0u};
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        constexpr int kTop = 32 - 2 * (int)kOwnMid;
-                        const int sa = 2 * i, sb = 2 * (53 - i);
-                        const uint32_t m = __funnelshift_r(A[sa >> 5], A[(sa >> 5) + 1], sa & 31) << kTop;
-                        const uint32_t y = __funnelshift_r(B[sb >> 5], B[(sb >> 5) + 1], sb & 31) << kTop;
-                        const uint32_t local = owner_part(owner_fold_mid(m, y), kp.nparts) - part_base;
-                        if (P == 1) pl[0] |= (local < nlocal ? 1u : 0u) << i;
-                        else {
-                            const uint32_t id = local < nlocal ? local + 1u : 0u;
-#pragma unroll
-                            for (int j = 0; j < P; ++j) pl[j] |= ((id >> j) & 1u) << i;
-                        }
-                    }
-                } else {
-                // k < 11 (one word per k-mer): both strands of every position by constant shifts out of two code
-                // words and their reverse complement, multiplicative fold of the canonical k-mer
-                const uint64_t c0 = __ldg(g.codes + w), c1 = __ldg(g.codes + w + 1);
-                const uint32_t k2 = 2 * kp.k;
-                const uint64_t kmask = (~0ull) >> (64 - k2);
-                const uint64_t rh = pairrev64(~c0), rl = pairrev64(~c1);
-                const uint32_t s0 = 64 - k2;
-                const uint64_t r_lo = (rl >> s0) | (rh << (64 - s0)), r_hi = rh >> s0;
+            }
+            if (kp.k >= kOwnMid) {
+                // ownership key = canonical middle 11-mer (owner_fold): A = the 64-base window shifted to the
+                // middle of position 0's k-mer, B = its reverse complement; position i's middle 11-mer is bases
+                // i.. of A and its reverse complement bases 53-i.. of B -- one constant funnel shift each
+                // (any k >= 11, one to four words per k-mer: only the three code words around the middle are read)
+                const uint32_t off = (kp.k - kOwnMid) >> 1, off2 = 2 * (off & 31);
+                const uint64_t* cw = g.codes + w + (off >> 5);
+                const uint64_t c0 = __ldg(cw), c1 = __ldg(cw + 1), c2 = __ldg(cw + 2);
+                const uint64_t a0 = off2 ? (c0 >> off2) | (c1 << (64 - off2)) : c0;
+                const uint64_t a1 = off2 ? (c1 >> off2) | (c2 << (64 - off2)) : c1;
+                const uint64_t b0 = pairrev64(~a1), b1 = pairrev64(~a0);
+                const uint32_t A[4] = {(uint32_t)a0, (uint32_t)(a0 >> 32), (uint32_t)a1, (uint32_t)(a1 >> 32)};
+                const uint32_t B[5] = {(uint32_t)b0, (uint32_t)(b0 >> 32), (uint32_t)b1, (uint32_t)(b1 >> 32), 0u};
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const uint64_t x = (i ? ((c0 >> (2 * i)) | (c1 << (64 - 2 * i))) : c0) & kmask;
-                    const uint64_t y = (i ? ((r_lo >> (64 - 2 * i)) | (r_hi << (2 * i))) : r_hi) & kmask;
-                    Kmer<1> canon;
-                    canon.w[0] = x < y ? x : y;
-                    const uint32_t local = owner_part(owner_fold<1>(canon, kp.k), kp.nparts) - part_base;
+                    constexpr int kTop = 32 - 2 * (int)kOwnMid;
+                    const int sa = 2 * i, sb = 2 * (53 - i);
+                    const uint32_t m = __funnelshift_r(A[sa >> 5], A[(sa >> 5) + 1], sa & 31) << kTop;
+                    const uint32_t y = __funnelshift_r(B[sb >> 5], B[(sb >> 5) + 1], sb & 31) << kTop;
+                    const uint32_t local = owner_part(owner_fold_mid(m, y), kp.nparts) - part_base;
                     if (P == 1) pl[0] |= (local < nlocal ? 1u : 0u) << i;
                     else {
                         const uint32_t id = local < nlocal ? local + 1u : 0u;
@@ -245,14 +221,101 @@ k_own(GenomeView g, KParams kp, uint32_t part_base, uint32_t nlocal, uint64_t wo
                         for (int j = 0; j < P; ++j) pl[j] |= ((id >> j) & 1u) << i;
                     }
                 }
-                }
+            } else {
+            // k < 11 (one word per k-mer): both strands of every position by constant shifts out of two code
+            // words and their reverse complement, multiplicative fold of the canonical k-mer
+            const uint64_t c0 = __ldg(g.codes + w), c1 = __ldg(g.codes + w + 1);
+            const uint32_t k2 = 2 * kp.k;
+            const uint64_t kmask = (~0ull) >> (64 - k2);
+            const uint64_t rh = pairrev64(~c0), rl = pairrev64(~c1);
+            const uint32_t s0 = 64 - k2;
+            const uint64_t r_lo = (rl >> s0) | (rh << (64 - s0)), r_hi = rh >> s0;
 #pragma unroll
-                for (int j = 0; j < P; ++j) pl[j] &= valid;
+            for (int i = 0; i < 32; ++i) {
+                const uint64_t x = (i ? ((c0 >> (2 * i)) | (c1 << (64 - 2 * i))) : c0) & kmask;
+                const uint64_t y = (i ? ((r_lo >> (64 - 2 * i)) | (r_hi << (2 * i))) : r_hi) & kmask;
+                Kmer<1> canon;
+                canon.w[0] = x < y ? x : y;
+                const uint32_t local = owner_part(owner_fold<1>(canon, kp.k), kp.nparts) - part_base;
+                if (P == 1) pl[0] |= (local < nlocal ? 1u : 0u) << i;
+                else {
+                    const uint32_t id = local < nlocal ? local + 1u : 0u;
+#pragma unroll
+                    for (int j = 0; j < P; ++j) pl[j] |= ((id >> j) & 1u) << i;
+                }
             }
+            }
+#pragma unroll
+            for (int j = 0; j < P; ++j) pl[j] &= valid;
         }
+    }
+}
+
+template <int W, int P>
+__global__ void __launch_bounds__(kTileThreads)
+k_own(GenomeView g, KParams kp, uint32_t part_base, uint32_t nlocal, uint64_t word_begin, uint64_t word_end, OwnPlanes op) {
+    for (uint64_t w = word_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < word_end;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t pl[P];
+        own_planes_of_word<W, P>(g, kp, part_base, nlocal, w, pl);
 #pragma unroll
         for (int j = 0; j < P; ++j) op.p[j][w] = pl[j];
     }
+}
+
+// ---- list-driven direct filter passes (hash-range shards / rounds WITHOUT the binned path: filters of more than 256
+// slices, windowed runs).  k_fill / k_query roll the k-mer of EVERY position and test its ownership inline -- with 1/nparts
+// of the lanes going on to the hash and the filter sector; at 32 parts (BASELINE config 5) the scan, not the random
+// sector traffic, takes the time.  Here ownership is decided per word by the cheap middle-11-mer key (own_planes_of_word,
+// no rolling chain), the owned positions of a tile are compacted into a CTA-wide list, and the hash + sector touch run
+// densely on it, one list entry per thread, the tile's genome staged in shared memory one tile ahead.
+template <int W, int Q, bool QUERY>
+__global__ void __launch_bounds__(kTileThreads)
+k_direct_list(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t tile_begin, uint64_t tile_end,
+              uint32_t* __restrict__ mask, Counters* ctr, uint32_t* __restrict__ hll) {
+    __shared__ TileStage ts;
+    __shared__ unsigned long long red[8];
+    unsigned long long acc = 0;
+    auto own_of = [&](uint64_t t) -> uint32_t {
+        uint32_t pl[1];
+        own_planes_of_word<W, 1>(g, kp, kp.part, 1u, t * kTileThreads + threadIdx.x, pl);
+        return pl[0];
+    };
+    uint64_t tile = tile_begin + blockIdx.x;
+    uint32_t own_next = 0;
+    int buf = 0;
+    if (tile < tile_end) { own_next = own_of(tile); tile_request(ts, g, tile, 0); }
+    for (; tile < tile_end; tile += gridDim.x, buf ^= 1) {
+        const uint32_t own = own_next;
+        TileGeom tg;
+        const uint32_t total = tile_compact(ts, tile, buf, own, tg, [&]() {
+            if (tile + gridDim.x < tile_end) { own_next = own_of(tile + gridDim.x); tile_request(ts, g, tile + gridDim.x, buf ^ 1); }
+        });
+        const uint64_t* s_codes = ts.codes[buf];
+        const uint64_t* s_nmask = ts.nmask[buf];
+        for (uint32_t e = threadIdx.x; e < total; e += kTileThreads) {
+            const uint32_t tp = ts.list[e];
+            const uint64_t p = tile * kTilePos + tp;
+            const uint32_t lp = tp + tg.c_off, mp = tp + tg.m_off;
+            const Kmer<W> X = extract_kmer_smem<W>(s_codes, lp, kp.k);
+            const Kmer<W> Y = revcomp<W>(X, kp.k);
+            const bool fwd = kmer_less<W>(X, Y);
+            const uint64_t h = kmer_hash<W>(kmer_select<W>(fwd, X, Y), kp.seed);
+            uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
+            const uint32_t vm = vertex_mask<Q>(h);
+            if (!QUERY) {
+                const uint32_t code = occurrence_code(fwd, stage_base(s_codes, lp - 1), stage_base(s_codes, lp + kp.k),
+                                                      stage_n(s_nmask, mp - 1), stage_n(s_nmask, mp + kp.k));
+                acc += fill_vertex(sec, vm, code);
+            } else if (query_vertex(sec, vm)) {
+                atomicOr(mask + (p >> 5), 1u << (p & 31));
+                hll_add(hll, vm, hash_sector(h, kp.sector_shift));
+                ++acc;
+            }
+        }
+    }
+    unsigned long long t = block_sum(acc, red);
+    if (threadIdx.x == 0 && t) atomicAdd(QUERY ? &ctr->marks : &ctr->filter_new, t);
 }
 
 constexpr int kBinListMax = kTilePos;

@@ -36,6 +36,15 @@ template <int W>
 cudaError_t Launch<W>::fill(const LaunchCtx& c, GenomeView g, uint32_t* filter, KParams kp, uint64_t tile_begin, uint64_t tile_end,
                             Counters* ctr) {
     if (tile_end <= tile_begin) return cudaSuccess;
+    const bool no_list = getenv("TPC_DIRECT_LIST") && atoi(getenv("TPC_DIRECT_LIST")) == 0;   // (tests: the inline kernels)
+    if (kp.nparts > 1 && !no_list) {   // sparse ownership: compact the owned positions first (k_direct_list)
+        TPC_Q_SWITCH(kp.q, {
+            int grid = persistent_grid(k_direct_list<W, Q, false>, kTileThreads, c.sm_count, tile_end - tile_begin);
+            k_direct_list<W, Q, false><<<grid, kTileThreads, 0, c.stream>>>(g, filter, kp, tile_begin, tile_end, nullptr, ctr, nullptr);
+        });
+        ++*c.launches;
+        return cudaGetLastError();
+    }
     TPC_Q_SWITCH(kp.q, {
         int grid = persistent_grid(k_fill<W, Q>, kTileThreads, c.sm_count, tile_end - tile_begin);
         k_fill<W, Q><<<grid, kTileThreads, 0, c.stream>>>(g, filter, kp, tile_begin, tile_end, ctr);
@@ -48,6 +57,17 @@ template <int W>
 cudaError_t Launch<W>::query(const LaunchCtx& c, GenomeView g, const uint32_t* filter, KParams kp, uint64_t tile_begin, uint64_t tile_end,
                              uint32_t* mask, int accumulate, Counters* ctr, uint32_t* hll) {
     if (tile_end <= tile_begin) return cudaSuccess;
+    const bool no_list = getenv("TPC_DIRECT_LIST") && atoi(getenv("TPC_DIRECT_LIST")) == 0;
+    if (kp.nparts > 1 && !no_list) {
+        // (marks are OR-ed in: the mask words of the tiles must have been cleared -- find_candidates and the windowed driver do)
+        if (!accumulate) cudaMemsetAsync(mask + tile_begin * kTileThreads, 0, (tile_end - tile_begin) * kTileThreads * 4, c.stream);
+        TPC_Q_SWITCH(kp.q, {
+            int grid = persistent_grid(k_direct_list<W, Q, true>, kTileThreads, c.sm_count, tile_end - tile_begin);
+            k_direct_list<W, Q, true><<<grid, kTileThreads, 0, c.stream>>>(g, const_cast<uint32_t*>(filter), kp, tile_begin, tile_end, mask, ctr, hll);
+        });
+        ++*c.launches;
+        return cudaGetLastError();
+    }
     TPC_Q_SWITCH(kp.q, {
         int grid = persistent_grid(k_query<W, Q>, kTileThreads, c.sm_count, tile_end - tile_begin);
         k_query<W, Q><<<grid, kTileThreads, 0, c.stream>>>(g, filter, kp, tile_begin, tile_end, mask, accumulate, ctr, hll);
