@@ -325,7 +325,10 @@ constexpr size_t bin_list_smem_bytes(int R) {
            2 * (kTileCodeWords + kTileMaskWords) * 8;
 }
 
-template <int W, int R>
+// FUSED: a GPU that runs a single round (4 and more hash-range shards at C3) needs no ownership planes: the ownership word
+// of a thread's 32 positions is computed here (own_planes_of_word, the work of k_own) in the issue slots this kernel leaves
+// idle while it waits on shared memory and barriers, instead of a separate scan that writes a plane this kernel reads back.
+template <int W, int R, bool FUSED>
 __global__ void __launch_bounds__(kTileThreads, (R <= 8 ? 4 : 2))
 k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_end, uint64_t wave_base, OwnPlanes op) {
     constexpr uint32_t kStage = kTileThreads * R;
@@ -358,11 +361,19 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
         for (int j = tid; j < kTileMaskWords; j += kTileThreads) tile_cp_async8(sm + j, g.nmask + mb + j);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    auto own_of = [&](uint64_t w) -> uint32_t {
+        if (FUSED) {
+            uint32_t pl[1];
+            own_planes_of_word<W, 1>(g, kp, kp.part, 1u, w, pl);
+            return pl[0];
+        }
+        return own_word(op, w);
+    };
     uint64_t tile = tile_begin + blockIdx.x;
     uint32_t own_next = 0;
     int buf = 0;
     if (tile < tile_end) {
-        own_next = own_word(op, tile * kTileThreads + tid);
+        own_next = own_of(tile * kTileThreads + tid);
         request_tile(tile, 0);
     }
     for (; tile < tile_end; tile += gridDim.x, buf ^= 1) {
@@ -383,7 +394,7 @@ k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t 
         __syncthreads();  // ... everybody's; the previous tile's readers of list / warp_tot / the other buffer are done
         if (lane == 31) warp_tot[wid] = incl;
         if (tile + gridDim.x < tile_end) {                     // next tile: in flight during this tile's dense phase
-            own_next = own_word(op, (tile + gridDim.x) * kTileThreads + tid);
+            own_next = own_of((tile + gridDim.x) * kTileThreads + tid);
             request_tile(tile + gridDim.x, buf ^ 1);
         }
         uint64_t n_any = 0;

@@ -85,17 +85,24 @@ cudaError_t Launch<W>::valid_mask(const LaunchCtx& c, GenomeView g, KParams kp, 
     return cudaGetLastError();
 }
 
+template <int W, int R, bool FUSED>
+static void launch_bin_list_v(const LaunchCtx& c, GenomeView g, KParams kp, const BinView& bv, uint64_t tile_begin, uint64_t tile_end,
+                              uint64_t wave_base, const OwnPlanes& op) {
+    constexpr size_t smem = bin_list_smem_bytes(R);
+    // the attribute is per device (a process may hold sessions on several GPUs) and setting it is cheap
+    cudaFuncSetAttribute(k_bin_list<W, R, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_list<W, R, FUSED>, kTileThreads, smem);
+    if (c.bin_ctas > 0 && per_sm > c.bin_ctas) per_sm = c.bin_ctas;
+    uint64_t grid = std::min<uint64_t>((uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count, tile_end - tile_begin);
+    k_bin_list<W, R, FUSED><<<(int)grid, kTileThreads, smem, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base, op);
+}
+// planes.n == 0: no ownership planes exist, the kernel decides ownership itself (single-round GPUs)
 template <int W, int R>
 static void launch_bin_list(const LaunchCtx& c, GenomeView g, KParams kp, const BinView& bv, uint64_t tile_begin, uint64_t tile_end,
                             uint64_t wave_base, const OwnPlanes& op) {
-    constexpr size_t smem = bin_list_smem_bytes(R);
-    // the attribute is per device (a process may hold sessions on several GPUs) and setting it is cheap
-    cudaFuncSetAttribute(k_bin_list<W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bin_list<W, R>, kTileThreads, smem);
-    if (c.bin_ctas > 0 && per_sm > c.bin_ctas) per_sm = c.bin_ctas;
-    uint64_t grid = std::min<uint64_t>((uint64_t)(per_sm < 1 ? 1 : per_sm) * c.sm_count, tile_end - tile_begin);
-    k_bin_list<W, R><<<(int)grid, kTileThreads, smem, c.stream>>>(g, kp, bv, tile_begin, tile_end, wave_base, op);
+    if (op.n == 0) launch_bin_list_v<W, R, true>(c, g, kp, bv, tile_begin, tile_end, wave_base, op);
+    else launch_bin_list_v<W, R, false>(c, g, kp, bv, tile_begin, tile_end, wave_base, op);
 }
 
 template <int W, int P>

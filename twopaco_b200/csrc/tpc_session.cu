@@ -717,12 +717,15 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
     OwnPlanes op = s->own;
     op.id = s->own_shared ? kp.part - part_base + 1 : 1;
     if (!s->own_shared) op.n = 1;
+    // a GPU that runs one round in one wave reads its ownership exactly once: k_bin_list computes it itself (no k_own, no plane)
+    const bool fused_own = sharded && s->rounds_eff == 1 && nwaves == 1 && !(getenv("TPC_FUSED_OWN") && atoi(getenv("TPC_FUSED_OWN")) == 0);
+    if (fused_own) op.n = 0;
     auto bin_range = [&](uint64_t t0, uint64_t t1, uint64_t base) -> int {
         for (uint64_t a = t0; a < t1;) {
             const uint64_t b = next_cut(s, a, t1);
             if (int wrc = wait_genome(s, b)) return wrc;
-            if (sharded && !s->own_shared) CK(W_DISPATCH(s, own(lc, s->g, kp, kp.part, 1, a, b, op)));
-            if (sharded && s->own_shared && s->own_done_tiles < b) {
+            if (sharded && !s->own_shared && !fused_own) CK(W_DISPATCH(s, own(lc, s->g, kp, kp.part, 1, a, b, op)));
+            if (sharded && s->own_shared && !fused_own && s->own_done_tiles < b) {
                 CK(W_DISPATCH(s, own(lc, s->g, kp, part_base, s->rounds_eff, s->own_done_tiles, b, s->own)));
                 s->own_done_tiles = b;
             }
