@@ -26,8 +26,9 @@ extern "C" {
 #define TPC_ABI_VERSION 3
 #define TPC_INVALID_VERTEX INT64_MAX          /* src/graphconstructor/common.cpp:5 */
 #define TPC_SEPARATOR_POS 0xFFFFFFFFu         /* src/common/junctionapi.h:36-37 */
-#define TPC_MAX_K 127                         /* 4 x 64-bit words per packed k-mer in this build
-                                                 (reference: MAX_CAPACITY 20, vertexenumerator.h:4) */
+#define TPC_MAX_K 603                         /* up to 19 x 64-bit words per packed k-mer: the reference's limit
+                                                 (MAX_CAPACITY 20, vertexenumerator.h:4; capacity = ceil((k + 4) / 32)
+                                                 <= 19, candidateoccurence.h:129-133; larger k: "K is too big") */
 #define TPC_STUB_ID_OFFSET 42                 /* vertexenumerator.h:419 */
 
 typedef struct tpc_handle tpc_handle;         /* result of tpc_build (a VertexEnumerator) */

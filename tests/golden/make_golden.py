@@ -35,8 +35,13 @@ def canon_md5(image: bytes) -> str:
 
 def main() -> None:
     assert O.have_reference(), "build oracle/_ref first: make -C oracle"
-    out = {}
+    # `make_golden.py <case> ...` regenerates only the named cases and keeps the other entries of golden.json
+    only = set(sys.argv[1:])
+    path = ROOT / "tests" / "golden" / "golden.json"
+    out = json.loads(path.read_text()) if only and path.exists() else {}
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         files, k = build_case(spec), spec["k"]
         with tempfile.TemporaryDirectory() as d:
             paths = []
@@ -66,7 +71,7 @@ def main() -> None:
                 ent["canon_stream"] = [[int(a), int(b), int(c)] for a, b, c in zip(seq, pos, cid)]
             out[name] = ent
             print(name, ent["records"], ent["distinct_junctions"], ent["canon_md5"])
-    with open(ROOT / "tests" / "golden" / "golden.json", "w") as fh:
+    with open(path, "w") as fh:
         json.dump(out, fh, indent=1, sort_keys=True)
 
 

@@ -90,7 +90,7 @@ def test_parameter_validation_and_no_cpu_fallback():
     with pytest.raises(api.TpcError, match="must be odd"):
         api.Session(k=24, filter_bits=20)
     with pytest.raises(api.TpcError, match="K is too big"):
-        api.Session(k=129, filter_bits=20)
+        api.Session(k=605, filter_bits=20)   # reference: capacity ceil((k + 4) / 32) reaches MAX_CAPACITY 20
     if not torch.cuda.is_available():
         # the product path must fail loudly without a GPU
         with pytest.raises(api.TpcError, match="no CUDA device"):

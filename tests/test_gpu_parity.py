@@ -41,7 +41,7 @@ def test_create_enumerator_matches_reference_golden(name, golden, tmp_path):
 
 
 @pytest.mark.parametrize("rounds", [2, 3, 4])
-@pytest.mark.parametrize("name", ["selftest_s1_k7", "selftest_s2_k9", "family_k25", "family_k63", "edge_mixed_k5"])
+@pytest.mark.parametrize("name", ["selftest_s1_k7", "selftest_s2_k9", "family_k25", "family_k63", "family_k161", "edge_mixed_k5"])
 def test_rounds_do_not_change_the_result(name, rounds, golden, tmp_path):
     """-r: hash-range rounds (vertexenumerator.h:228-392) -- the reference's --test sweeps 1..4."""
     spec, g = CASES[name], golden[name]
@@ -65,11 +65,11 @@ def test_filter_shape_never_changes_the_result(q, f, golden):
     assert st.junctions == g["distinct_junctions"] and st.candidate_kmers >= st.junctions
 
 
-def test_get_id_surface(golden):
+@pytest.mark.parametrize("k", [9, 161])
+def test_get_id_surface(k, golden):
     """VertexEnumerator::GetId (vertexenumerator.h:98-102; test.cpp:234-242): every junction
     k-mer has an id, its reverse complement the negated id, anything else INVALID_VERTEX."""
-    recs = synth.reference_selftest_set(77)
-    k = 9
+    recs = synth.reference_selftest_set(77) if k == 9 else synth.founder_family(78, 4, 1, 30_000, 0.002, n_runs=1)
     oracle_img, nj, _ = O.find_junctions(recs, k)
     s = api.Session(k=k, filter_bits=20)
     s.set_genome_host(api.pack_records(recs))
@@ -90,7 +90,7 @@ def test_get_id_surface(golden):
             assert s.get_id(kmer.decode()) == api.INVALID_VERTEX
     assert seen > 50
     assert s.get_id("ACGT") == api.INVALID_VERTEX          # wrong length
-    assert s.get_id("ACGTNACGT") == api.INVALID_VERTEX     # not definite
+    assert s.get_id("ACGTNACGT" + "A" * (k - 9)) == api.INVALID_VERTEX     # not definite
     s.close()
 
 
@@ -325,7 +325,8 @@ def test_cli_selftest_mode(tmp_path):
 
 # ---- binned filter passes (tpc_bin.cuh): forced on small inputs via the debug environment knobs --------
 @pytest.mark.parametrize("slice_log2,buffer_mb", [(13, 0), (12, 1), (16, 1), (10, 0)])
-@pytest.mark.parametrize("name", ["family_k25", "family_k63", "family_k127", "selftest_s3_k9", "edge_mixed_k5", "family_seam_k25"])
+@pytest.mark.parametrize("name", ["family_k25", "family_k63", "family_k127", "family_k603", "selftest_s3_k9", "edge_mixed_k5",
+                                  "family_seam_k25"])
 def test_binned_filter_passes_match_golden(name, slice_log2, buffer_mb, golden, monkeypatch):
     """Partition-by-filter-slice path: single wave (records shared by fill and query), several
     waves (re-binned per pass, tiny buffer), many / few slices, overflow of skewed slices."""
@@ -345,7 +346,8 @@ def test_binned_filter_passes_match_golden(name, slice_log2, buffer_mb, golden, 
     assert st.junctions == g["distinct_junctions"]
 
 
-@pytest.mark.parametrize("name", ["family_k29", "family_k33", "family_k65", "family_k75", "family_k97"])
+@pytest.mark.parametrize("name", ["family_k29", "family_k33", "family_k65", "family_k75", "family_k97",
+                                  "family_k129", "family_k257", "family_k331", "family_k603"])
 def test_kmer_word_count_boundaries_on_the_sharded_binned_path(name, golden, monkeypatch):
     """k at the word-count boundaries of the packed k-mer (and at the limits of the one-window extraction of
     k_bin_list / the ownership window of k_own) through k_own + k_bin_list + the apply kernels, 3 sub-rounds."""

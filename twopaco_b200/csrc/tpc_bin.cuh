@@ -273,7 +273,7 @@ template <int W, int Q, bool QUERY>
 __global__ void __launch_bounds__(kTileThreads)
 k_direct_list(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t tile_begin, uint64_t tile_end,
               uint32_t* __restrict__ mask, Counters* ctr, uint32_t* __restrict__ hll) {
-    __shared__ TileStage ts;
+    __shared__ TileStage<W> ts;
     __shared__ unsigned long long red[8];
     unsigned long long acc = 0;
     auto own_of = [&](uint64_t t) -> uint32_t {
@@ -302,7 +302,7 @@ k_direct_list(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t 
             const bool fwd = kmer_less<W>(X, Y);
             const uint64_t h = kmer_hash<W>(kmer_select<W>(fwd, X, Y), kp.seed);
             uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
-            const uint32_t vm = vertex_mask<Q>(h);
+            const uint32_t vm = vertex_mask<Q>(h, kp.q);
             if (!QUERY) {
                 const uint32_t code = occurrence_code(fwd, stage_base(s_codes, lp - 1), stage_base(s_codes, lp + kp.k),
                                                       stage_n(s_nmask, mp - 1), stage_n(s_nmask, mp + kp.k));
@@ -320,9 +320,10 @@ k_direct_list(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t 
 
 constexpr int kBinListMax = kTilePos;
 // R = records per thread per staging round (stage = 256 R records); small R = more CTAs per SM
+template <int W>
 constexpr size_t bin_list_smem_bytes(int R) {
     return kBinMaxBuckets * 8 * 2 + kBinMaxBuckets * 4 * 2 + 8 * 4 + 16 + (size_t)kTileThreads * R * (4 * 3 + 1) + kBinListMax * 2 +
-           2 * (kTileCodeWords + kTileMaskWords) * 8;
+           2 * (TileWords<W>::code + TileWords<W>::mask) * 8;
 }
 
 // FUSED: a GPU that runs a single round (4 and more hash-range shards at C3) needs no ownership planes: the ownership word
@@ -332,6 +333,7 @@ template <int W, int R, bool FUSED>
 __global__ void __launch_bounds__(kTileThreads, (R <= 8 ? 4 : 2))
 k_bin_list(GenomeView g, KParams kp, BinView bin, uint64_t tile_begin, uint64_t tile_end, uint64_t wave_base, OwnPlanes op) {
     constexpr uint32_t kStage = kTileThreads * R;
+    constexpr int kTileCodeWords = TileWords<W>::code, kTileMaskWords = TileWords<W>::mask;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* gbase = reinterpret_cast<unsigned long long*>(smem_raw);    // records reserved before this chunk, per slice
     uint32_t** gptr = reinterpret_cast<uint32_t**>(gbase + kBinMaxBuckets);         // where staged record 0 would go, per slice

@@ -282,9 +282,11 @@ __device__ __forceinline__ uint32_t mask_from_seed_rt(uint32_t seed32, uint32_t 
         default: return mask_from_seed<8>(seed32);
     }
 }
+// Q = 0: the number of bits is a run-time value (kernels of the long k-mers, W > 4, are compiled once for every q)
 template <int Q>
-__device__ __forceinline__ uint32_t vertex_mask(uint64_t h) {
-    return mask_from_seed<Q>(mask_seed(h));
+__device__ __forceinline__ uint32_t vertex_mask(uint64_t h, uint32_t q) {
+    if (Q == 0) return mask_from_seed_rt(mask_seed(h), q);
+    return mask_from_seed<(Q ? Q : 1)>(mask_seed(h));
 }
 
 // ---- per-thread window over 32 consecutive positions ------------------------------------

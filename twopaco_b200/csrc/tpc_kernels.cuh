@@ -119,7 +119,7 @@ k_fill(GenomeView g, uint32_t* __restrict__ filter, KParams kp, uint64_t tile_be
                     uint64_t h = kmer_hash<W>(canon, kp.seed);
                     uint32_t code = occurrence_code(fwd, prv, nxt, (win.prev_n >> i) & 1u, (win.next_n >> i) & 1u);
                     uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
-                    fresh += fill_vertex(sec, vertex_mask<Q>(h), code);
+                    fresh += fill_vertex(sec, vertex_mask<Q>(h, kp.q), code);
                 }
             }
             roll<W>(win.X, win.Y, nxt, kp.k);
@@ -156,7 +156,7 @@ k_query(GenomeView g, const uint32_t* __restrict__ filter, KParams kp, uint64_t 
                     if (kp.nparts == 1 || owner_part(owner_fold<W>(canon, kp.k), kp.nparts) == kp.part) {
                         uint64_t h = kmer_hash<W>(canon, kp.seed);
                         const uint32_t* sec = filter + (hash_sector(h, kp.sector_shift) << 3);
-                        uint32_t vm = vertex_mask<Q>(h);
+                        uint32_t vm = vertex_mask<Q>(h, kp.q);
                         if (query_vertex(sec, vm)) {
                             out |= 1u << i;
                             hll_add(hll, vm, hash_sector(h, kp.sector_shift));
@@ -285,7 +285,7 @@ __device__ __forceinline__ bool insert_occurrence(const GenomeView& g, const KPa
 template <int W>
 __global__ void __launch_bounds__(kTileThreads)
 k_insert(GenomeView g, const uint32_t* __restrict__ mask, KParams kp, uint64_t tile_begin, uint64_t ntiles, TableView T, Counters* ctr, OwnPlanes op) {
-    __shared__ TileStage ts;
+    __shared__ TileStage<W> ts;
     unsigned long long claimed = 0;
     // this round's marks of a tile (software-pipelined: the next tile's words are requested while this one is processed)
     auto marks_of = [&](uint64_t t) -> uint32_t {

@@ -20,8 +20,10 @@ static int persistent_grid(Kern kern, int threads, int sm_count, uint64_t work_i
     return (int)g;
 }
 
+// (the kernels of the long k-mers, W > 4, take q at run time: one instantiation instead of eight)
 #define TPC_Q_SWITCH(q, ...)                                   \
-    switch (q) {                                               \
+    if constexpr (W > 4) { constexpr int Q = 0; __VA_ARGS__; } \
+    else switch (q) {                                          \
         case 1: { constexpr int Q = 1; __VA_ARGS__; } break;   \
         case 2: { constexpr int Q = 2; __VA_ARGS__; } break;   \
         case 3: { constexpr int Q = 3; __VA_ARGS__; } break;   \
@@ -88,7 +90,7 @@ cudaError_t Launch<W>::valid_mask(const LaunchCtx& c, GenomeView g, KParams kp, 
 template <int W, int R, bool FUSED>
 static void launch_bin_list_v(const LaunchCtx& c, GenomeView g, KParams kp, const BinView& bv, uint64_t tile_begin, uint64_t tile_end,
                               uint64_t wave_base, const OwnPlanes& op) {
-    constexpr size_t smem = bin_list_smem_bytes(R);
+    constexpr size_t smem = bin_list_smem_bytes<W>(R);
     // the attribute is per device (a process may hold sessions on several GPUs) and setting it is cheap
     cudaFuncSetAttribute(k_bin_list<W, R, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
@@ -139,9 +141,13 @@ cudaError_t Launch<W>::bin(const LaunchCtx& c, GenomeView g, KParams kp, const B
         if (force_r) expect = (uint32_t)force_r * kTileThreads;
         // (a 2048-record stage with 4 CTAs per SM beats a 4096-record stage with 2: the barriers and the global
         // reservations of one CTA are hidden by the others)
-        if (expect <= 4 * kTileThreads) launch_bin_list<W, 4>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
-        else if (force_r != 16) launch_bin_list<W, 8>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
-        else launch_bin_list<W, 16>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
+        if constexpr (W > 4) {   // long k-mers: one stage size (the others only matter for the throughput of the short ones)
+            launch_bin_list<W, 8>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
+        } else {
+            if (expect <= 4 * kTileThreads) launch_bin_list<W, 4>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
+            else if (force_r != 16) launch_bin_list<W, 8>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
+            else launch_bin_list<W, 16>(c, g, kp, bv, tile_begin, tile_end, wave_base, *planes);
+        }
     } else {
         cudaFuncSetAttribute(k_bin<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBinSmemBytes);
         int per_sm = 0;

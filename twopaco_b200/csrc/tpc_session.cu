@@ -348,8 +348,17 @@ struct tpc_session {
     RecordTable rtable() const { return RecordTable{d_rec_start, d_rec_len, d_sep_before, (uint64_t)rec_start.size()}; }
 };
 
-#define W_DISPATCH(s, EXPR)                          \
-    ((s)->W == 1 ? Launch<1>::EXPR : (s)->W == 2 ? Launch<2>::EXPR : (s)->W == 3 ? Launch<3>::EXPR : Launch<4>::EXPR)
+// one explicit instantiation of the kernels per k-mer word count (tpc_w1.cu .. tpc_w4.cu, tpc_wn.cu for 5..19 = k <= 603,
+// the reference's MAX_CAPACITY, vertexenumerator.h:4 / vertexenumerator.cpp:17-54)
+#define W_CASE(n, EXPR) (s_->W == n) ? Launch<n>::EXPR
+#define W_DISPATCH(s, EXPR)                                                                                                   \
+    ([&]() -> cudaError_t {                                                                                                   \
+        const tpc_session* s_ = (s);                                                                                          \
+        return W_CASE(1, EXPR) : W_CASE(2, EXPR) : W_CASE(3, EXPR) : W_CASE(4, EXPR) : W_CASE(5, EXPR) : W_CASE(6, EXPR)      \
+             : W_CASE(7, EXPR) : W_CASE(8, EXPR) : W_CASE(9, EXPR) : W_CASE(10, EXPR) : W_CASE(11, EXPR) : W_CASE(12, EXPR)   \
+             : W_CASE(13, EXPR) : W_CASE(14, EXPR) : W_CASE(15, EXPR) : W_CASE(16, EXPR) : W_CASE(17, EXPR)                   \
+             : W_CASE(18, EXPR) : Launch<19>::EXPR;                                                                           \
+    }())
 
 static uint32_t ceil_log2(uint64_t x) {
     uint32_t l = 0;
@@ -364,11 +373,11 @@ uint32_t tpc_abi_version(void) { return TPC_ABI_VERSION; }
 
 uint64_t tpc_code_words(uint64_t n_positions) {
     uint64_t tiles = (n_positions + kTilePos - 1) / kTilePos;
-    return tiles * kTileThreads + 8;
+    return tiles * kTileThreads + kCodePadWords;
 }
 uint64_t tpc_mask_words(uint64_t n_positions) {
     uint64_t tiles = (n_positions + kTilePos - 1) / kTilePos;
-    return tiles * (kTileThreads / 2) + 8;
+    return tiles * (kTileThreads / 2) + kMaskPadWords;
 }
 uint64_t tpc_positions_for(const uint64_t* rec_len, uint64_t n_records) {
     uint64_t p = 1;
@@ -1231,7 +1240,7 @@ int tpc_session_get_id(tpc_session* s, const char* kmer, int64_t* id) {
     uint32_t k = s->prm.k;
     *id = TPC_INVALID_VERTEX;
     if (strlen(kmer) != k) return 0;
-    uint64_t words[4] = {0, 0, 0, 0};
+    uint64_t words[(TPC_MAX_K + 31) / 32] = {};
     for (uint32_t j = 0; j < k; ++j) {
         uint64_t c;
         switch (kmer[j]) {

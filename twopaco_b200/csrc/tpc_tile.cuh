@@ -28,12 +28,18 @@ __device__ __forceinline__ uint32_t own_word(const OwnPlanes& op, uint64_t w) {
     return own;
 }
 
-constexpr int kTileCodeWords = kTileThreads + 8;        // tile + one word before + read-ahead (k <= 127)
-constexpr int kTileMaskWords = kTileThreads / 2 + 4;
+// staged words of a tile: the tile + one word before + the read-ahead of the longest k-mer of W words that starts in
+// the tile (W <= 4: k <= 127; W <= 19: k <= 603 -- the kernels of the short k-mers keep their shared-memory footprint)
+template <int W> struct TileWords { static constexpr int code = kTileThreads + (W <= 4 ? 8 : 24), mask = kTileThreads / 2 + (W <= 4 ? 4 : 12); };
+// read-ahead padding behind the last tile of the packed genome / the n-mask (tpc_code_words, tpc_mask_words): covers
+// the staging above and the W + 1 words Window::load reads from the last word of the last tile
+constexpr int kCodePadWords = 32;
+constexpr int kMaskPadWords = 16;
 
+template <int W>
 struct TileStage {
-    uint64_t codes[2][kTileCodeWords];   // double-buffered: code words cw_base .. of the tile
-    uint64_t nmask[2][kTileMaskWords];   // n-mask words mw_base ..
+    uint64_t codes[2][TileWords<W>::code];   // double-buffered: code words cw_base .. of the tile
+    uint64_t nmask[2][TileWords<W>::mask];   // n-mask words mw_base ..
     uint16_t list[kTilePos];             // tile-local positions of the set bits, in position order
     uint32_t warp_tot[kTileThreads / 32];
     uint32_t total;
@@ -52,10 +58,11 @@ __device__ __forceinline__ void tile_cp_async8(void* smem, const void* gmem) {
 
 // Request the packed-genome words of `tile` into buffer `buf` (all threads of the CTA call this; one
 // cp.async group per call).  tile_compact of that tile waits for them.
-__device__ __forceinline__ void tile_request(TileStage& ts, const GenomeView& g, uint64_t tile, int buf) {
+template <int W>
+__device__ __forceinline__ void tile_request(TileStage<W>& ts, const GenomeView& g, uint64_t tile, int buf) {
     const uint64_t tw0 = tile * kTileThreads, cw_base = tw0 ? tw0 - 1 : 0, mw_base = cw_base >> 1;
-    for (int j = threadIdx.x; j < kTileCodeWords; j += kTileThreads) tile_cp_async8(&ts.codes[buf][j], g.codes + cw_base + j);
-    for (int j = threadIdx.x; j < kTileMaskWords; j += kTileThreads) tile_cp_async8(&ts.nmask[buf][j], g.nmask + mw_base + j);
+    for (int j = threadIdx.x; j < TileWords<W>::code; j += kTileThreads) tile_cp_async8(&ts.codes[buf][j], g.codes + cw_base + j);
+    for (int j = threadIdx.x; j < TileWords<W>::mask; j += kTileThreads) tile_cp_async8(&ts.nmask[buf][j], g.nmask + mw_base + j);
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
@@ -64,8 +71,8 @@ __device__ __forceinline__ void tile_request(TileStage& ts, const GenomeView& g,
 // is free (the caller loads the next tile's bit word and calls tile_request there), so that the next
 // tile's HBM latency overlaps this tile's work.  Returns the number of set bits of the tile; ts.list
 // holds them; ts.codes[buf] / ts.nmask[buf] hold the tile's genome.
-template <typename Prefetch>
-__device__ __forceinline__ uint32_t tile_compact(TileStage& ts, uint64_t tile, int buf, uint32_t bits, TileGeom& tg,
+template <int W, typename Prefetch>
+__device__ __forceinline__ uint32_t tile_compact(TileStage<W>& ts, uint64_t tile, int buf, uint32_t bits, TileGeom& tg,
                                                  Prefetch prefetch_next) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t tw0 = tile * kTileThreads;              // first code word of the tile
