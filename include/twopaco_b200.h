@@ -275,6 +275,23 @@ int tpc_graphdump_file(const char *image_path, const char *format, const char *o
 int tpc_canonical_image_device(const uint8_t *dev_image, uint64_t image_bytes, void *stream, uint8_t *dev_out,
                                uint64_t *n_classes);
 
+/* `graphdump -f gfa1 | gfa2 | fasta` on the GPU (graphdump.cpp:47-113, 175-582): the compacted
+ * de Bruijn graph as text -- segments (non-branching paths between consecutive junction occurrences, ids packed from the
+ * junction id, its sign and the first edge character), their occurrences, links and the path of every input sequence.
+ *   tpc_graphdump_gfa_device : format 3 (gfa1), 4 (gfa2) or 5 (fasta); the image and the UPPER-CASED characters of all
+ *                          input records (back to back, record c = [seq_start[c], seq_start[c + 1]); seq_start and the
+ *                          names are host arrays) in device memory.  Produces everything the reference prints after the
+ *                          header lines; *dev_text is allocated by the callee (tpc_device_free).
+ *   tpc_graphdump_gfa_file   : image file + the FASTA files given with -s -> text file (NULL or "-" = stdout), byte for byte
+ *                          what the reference prints (header lines included); prefix != 0 == --prefix.
+ * Errors: "The input is corrupted" (graphdump.cpp:461; also for images whose sequences do not match the FASTA files),
+ * "A vertex id is too large, cannot generate GFA" (:58). */
+int tpc_graphdump_gfa_device(const uint8_t *dev_image, uint64_t image_bytes, uint32_t format, uint32_t k,
+                             const uint8_t *dev_seq_chars, const uint64_t *seq_start, const char *const *seq_name,
+                             uint64_t n_seq, void *stream, uint8_t **dev_text, uint64_t *text_bytes);
+int tpc_graphdump_gfa_file(const char *image_path, const char *format, uint32_t k, const char *const *seq_paths,
+                           size_t n_seq_paths, int prefix, const char *out_path);
+
 /* Sessions allocate from the current device's stream-ordered pool, which keeps freed memory for the next run; this
  * hands it back to the driver (e.g. before another process uses the GPU). */
 int tpc_release_cached_memory(void);

@@ -665,6 +665,80 @@ def test_gpu_graphdump_seq_and_group(name, tmp_path):
     assert api.graphdump(b"", "seq") == b"" and api.graphdump(b"", "group") == b""
 
 
+@pytest.mark.parametrize("name", ["example_k11", "family_k25", "family_twofiles_k25", "gfa_mixed_k11", "gfa_mixed_k5"])
+def test_gpu_graphdump_gfa1_gfa2_fasta(name, tmp_path, monkeypatch):
+    """tpc_graphdump_gfa_file == what the reference's graphdump prints for -f gfa1 / gfa2 / fasta (graphdump.cpp:377-582): the committed
+    fixtures of the unmodified binary (tests/golden/gfa_golden.json) for our image, and for a relabelled image (random ids and
+    signs, as a differently seeded reference run writes them) the live binary when it travelled and the pinned restatement."""
+    import hashlib
+    import json
+    import subprocess
+    from oracle import graphdump_gfa as G
+    from tests.cases import GFA_CASES, GFA_FORMATS, GOLDEN_DIR, build_case
+    spec = GFA_CASES[name]
+    g = json.loads((GOLDEN_DIR / "gfa_golden.json").read_text())[name]
+    monkeypatch.chdir(tmp_path)
+    names = []
+    for fname, content in build_case(spec):
+        (tmp_path / fname).write_bytes(content)
+        names.append(fname)
+    img, _ = api.junctions_host(api.pack_records(api.read_fasta(names)), k=spec["k"], filter_bits=20)
+    img = bytes(img)
+    assert hashlib.md5(img).hexdigest() == g["image_md5"], "image differs from the oracle's: the fixtures do not apply"
+    seq, pos, ids = O.decode(img)
+    rng = np.random.default_rng(11)
+    uniq = np.unique(np.abs(ids))
+    perm = dict(zip(uniq.tolist(), (rng.permutation(len(uniq)) + 7).tolist()))
+    flip = {u: int(rng.integers(0, 2)) * 2 - 1 for u in uniq.tolist()}
+    rec = np.frombuffer(img, dtype=O.REC_DTYPE).copy()
+    sep = (rec["pos"] == O.SEP_POS) | (rec["id"] == O.SEP_ID)
+    rec["id"][~sep] = [perm[abs(v)] * (1 if v > 0 else -1) * flip[abs(v)] for v in ids.tolist()]
+    (tmp_path / "image.dbg").write_bytes(img)
+    (tmp_path / "relabelled.dbg").write_bytes(rec.tobytes())
+    for fmt, prefix in GFA_FORMATS:
+        api.graphdump_gfa_file("image.dbg", fmt, spec["k"], names, prefix, "out.txt")
+        text = (tmp_path / "out.txt").read_bytes()
+        want = g[fmt + ("_prefix" if prefix else "")]
+        assert len(text) == want["bytes"] and hashlib.md5(text).hexdigest() == want["md5"], (fmt, prefix)
+        api.graphdump_gfa_file("relabelled.dbg", fmt, spec["k"], names, prefix, "out2.txt")
+        text2 = (tmp_path / "out2.txt").read_bytes()
+        assert text2 == G.graphdump_text(rec.tobytes(), fmt, spec["k"], names, prefix), (fmt, prefix)
+        if O.REF_GRAPHDUMP.exists():
+            cmd = [str(O.REF_GRAPHDUMP), "-f", fmt, "-k", str(spec["k"])] + [a for n in names for a in ("-s", n)] + (["--prefix"] if prefix else [])
+            q = subprocess.run(cmd + ["relabelled.dbg"], capture_output=True)
+            assert q.returncode == 0 and q.stdout == text2, (fmt, prefix)
+    # the `graphdump` command line of this build prints the same bytes
+    cli = os.path.join(os.path.dirname(CLI), "graphdump")
+    if os.path.exists(cli):
+        q = subprocess.run([cli, "-f", "gfa2", "-k", str(spec["k"])] + [a for n in names for a in ("-s", n)] + ["--prefix", "image.dbg"], capture_output=True)
+        assert q.returncode == 0 and hashlib.md5(q.stdout).hexdigest() == g["gfa2_prefix"]["md5"], q.stderr
+        q = subprocess.run([cli, "-f", "seq", "-k", str(spec["k"]), "image.dbg"], capture_output=True)
+        assert q.returncode == 0 and q.stdout == api.graphdump(img, "seq")
+        q = subprocess.run([cli, "-f", "gfa1", "-k", str(spec["k"]), "image.dbg"], capture_output=True)
+        assert q.returncode == 1 and b"seqfilename" in q.stderr
+
+
+def test_gpu_graphdump_gfa_errors(tmp_path, monkeypatch):
+    from tests.cases import EDGE_LEADING_SHORT
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "x.fa").write_bytes(EDGE_LEADING_SHORT)       # sequences shorter than k have no records: graphdump.cpp:459-462
+    img, _ = api.junctions_host(api.pack_records(api.read_fasta(["x.fa"])), k=5, filter_bits=16)
+    (tmp_path / "x.dbg").write_bytes(bytes(img))
+    with pytest.raises(api.TpcError, match="The input is corrupted"):
+        api.graphdump_gfa_file("x.dbg", "gfa1", 5, ["x.fa"], False, "o.txt")
+    with pytest.raises(api.TpcError, match="format must be"):
+        api.graphdump_gfa_file("x.dbg", "seq", 5, ["x.fa"], False, "o.txt")
+    with pytest.raises(api.TpcError, match="Can't open file"):
+        api.graphdump_gfa_file("x.dbg", "gfa2", 5, ["missing.fa"], False, "o.txt")
+    (tmp_path / "big.dbg").write_bytes(np.array([(0, 1 << 31), (7, 5)], dtype=O.REC_DTYPE).tobytes())
+    (tmp_path / "y.fa").write_bytes(b">y\nACGTACGTTGCATGCATGCAAGC\n")
+    with pytest.raises(api.TpcError, match="A vertex id is too large"):
+        api.graphdump_gfa_file("big.dbg", "gfa1", 5, ["y.fa"], False, "o.txt")
+    (tmp_path / "empty.dbg").write_bytes(b"")
+    api.graphdump_gfa_file("empty.dbg", "gfa1", 5, ["y.fa"], False, "o.txt")
+    assert (tmp_path / "o.txt").read_bytes() == b"H\tVN:Z:1.0\nS\ty\t*\tUR:Z:y.fa\n"
+
+
 DROPIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "twopaco_dropin")
 
 

@@ -83,3 +83,31 @@ def test_oracle_vs_live_reference(seed, k, r, tmp_path):
     ref_img, _ = O.run_reference([str(p)], k, 22, q=3, r=r, t=2)
     img, _, _ = O.find_junctions(O.parse_fasta(str(p)), k)
     assert O.canon_equal(img, ref_img)
+
+
+# ---- graphdump -f gfa1 / gfa2 / fasta: pin the Python restatement (oracle/graphdump_gfa.py) to the reference binary's output
+@pytest.mark.parametrize("name", ["example_k11", "family_twofiles_k25", "gfa_mixed_k11", "gfa_mixed_k5"])
+def test_gfa_restatement_matches_reference_golden(name, monkeypatch):
+    import json
+    from oracle import graphdump_gfa as G
+    from tests.cases import GFA_CASES, GFA_FORMATS
+    spec = GFA_CASES[name]
+    g = json.loads((GOLDEN_DIR / "gfa_golden.json").read_text())[name]
+    with case_files(spec) as (paths, files, d):
+        monkeypatch.chdir(d)                      # gfa1 prints the FASTA file names as they were given
+        img, _, _ = oracle_on_paths(paths, spec["k"])
+        assert hashlib.md5(img).hexdigest() == g["image_md5"]
+        for fmt, prefix in GFA_FORMATS:
+            text = G.graphdump_text(img, fmt, spec["k"], [f for f, _ in files], prefix)
+            want = g[fmt + ("_prefix" if prefix else "")]
+            assert len(text) == want["bytes"] and hashlib.md5(text).hexdigest() == want["md5"], (fmt, prefix)
+
+
+def test_gfa_restatement_rejects_what_the_reference_rejects(tmp_path, monkeypatch):
+    from oracle import graphdump_gfa as G
+    from tests.cases import EDGE_LEADING_SHORT
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "x.fa").write_bytes(EDGE_LEADING_SHORT)       # sequences shorter than k: no records for them
+    img, _, _ = O.find_junctions(O.parse_fasta("x.fa"), 5)
+    with pytest.raises(G.GraphdumpError, match="corrupted"):
+        G.graphdump_text(img, "gfa1", 5, ["x.fa"])

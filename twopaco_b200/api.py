@@ -94,6 +94,9 @@ SIGNATURES = {
     "tpc_image_digest_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64 * 2)]),
     "tpc_graphdump_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "tpc_graphdump_file": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p]),
+    "tpc_graphdump_gfa_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_char_p),
+                                           C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "tpc_graphdump_gfa_file": (C.c_int, [C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p), C.c_size_t, C.c_int, C.c_char_p]),
     "tpc_canonical_image_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "tpc_release_cached_memory": (C.c_int, []),
     "tpc_device_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
@@ -418,6 +421,13 @@ def graphdump(image, fmt: str = "seq") -> bytes:
 
 def graphdump_file(image_path: str, fmt: str, out_path: str | None = None) -> None:
     _check(lib().tpc_graphdump_file(os.fsencode(image_path), fmt.encode(), os.fsencode(out_path) if out_path else None))
+
+
+def graphdump_gfa_file(image_path: str, fmt: str, k: int, seq_paths: list[str], prefix: bool = False, out_path: str | None = None) -> None:
+    """GPU `graphdump -f gfa1|gfa2|fasta -k k -s <fasta>... [--prefix] image` -> text file (None = stdout)."""
+    arr = (C.c_char_p * max(len(seq_paths), 1))(*[os.fsencode(p) for p in seq_paths])
+    _check(lib().tpc_graphdump_gfa_file(os.fsencode(image_path), fmt.encode(), k, arr, len(seq_paths), int(prefix),
+                                        os.fsencode(out_path) if out_path else None))
 
 
 def canonical_image(image) -> tuple[bytes, int]:
