@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TPC_ABI_VERSION 3
+#define TPC_ABI_VERSION 4
 #define TPC_INVALID_VERTEX INT64_MAX          /* src/graphconstructor/common.cpp:5 */
 #define TPC_SEPARATOR_POS 0xFFFFFFFFu         /* src/common/junctionapi.h:36-37 */
 #define TPC_MAX_K 603                         /* up to 19 x 64-bit words per packed k-mer: the reference's limit
@@ -76,6 +76,8 @@ typedef struct tpc_stats {
     float ms_wall_index, ms_wall_emit;   /* the same for set_junctions and emit_count + emit_write */
     uint32_t skew_rebins;        /* binned path: rounds whose slices overflowed (repeat-rich input) and were re-binned into
                                     arrays sized from the exact per-slice record counts */
+    uint64_t h2d_bytes;          /* host-buffer entry points: genome bytes actually copied host -> device (uniform blocks of
+                                    the n-mask are set on the device instead of copied) */
 } tpc_stats;
 
 /* ------------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in the header but not exported"
     assert declared == set(api.SIGNATURES), declared ^ set(api.SIGNATURES)
-    assert L.tpc_abi_version() == 3
+    assert L.tpc_abi_version() == 4
 
 
 def numpy_pack(records):

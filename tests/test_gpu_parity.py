@@ -453,6 +453,22 @@ def test_host_buffer_run_with_chunked_upload(mode, monkeypatch):
         assert out_host[:info["slice_bytes"]].numpy().tobytes() == ref
 
 
+def test_sparse_n_mask_upload(monkeypatch):
+    """tpc_junctions_host sets the uniform 64 KiB blocks of the n-mask on the device instead of copying them (all-zero inside the
+    sequences, all-one inside long N runs) -- same image as copying everything, and the same as the oracle's; several upload chunks."""
+    fam = synth.founder_family(seed=91, genomes=3, records_per_genome=2, record_len=1_500_000, p=0.002, n_runs=2)
+    recs = fam[:2] + [b"ACGTTGCATGCAAGCTTGACCATGCAT" + b"N" * 1_300_000 + fam[2][:400_000]] + fam[3:] + [b"N" * 700_000]
+    g = api.pack_records(recs)
+    ref, nj, nm = O.find_junctions(recs, 25)
+    img, st = api.junctions_host(g, k=25, filter_bits=26)
+    total = g.codes.nbytes + g.n_mask.nbytes
+    assert bytes(img) == ref and st.junctions == nj
+    assert g.codes.nbytes < st.h2d_bytes <= total - 6 * 65536, (st.h2d_bytes, total)   # >= 3 all-zero and >= 3 all-one blocks
+    monkeypatch.setenv("TPC_SPARSE_MASK", "0")
+    img0, st0 = api.junctions_host(g, k=25, filter_bits=26)
+    assert bytes(img0) == ref and st0.h2d_bytes == total
+
+
 def test_genome_events_are_validated():
     recs = [b"ACGTTGCATGCATGCATTTGACCA" * 50]
     g = api.pack_records(recs)

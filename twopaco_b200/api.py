@@ -38,7 +38,7 @@ class Stats(C.Structure):
                 ("ms_index", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float),
                 ("kernel_launches", C.c_uint32), ("bin_waves", C.c_uint32), ("sub_rounds", C.c_uint32),
                 ("ms_bin_overlapped", C.c_float), ("ms_wall_candidates", C.c_float), ("ms_wall_index", C.c_float),
-                ("ms_wall_emit", C.c_float), ("skew_rebins", C.c_uint32)]
+                ("ms_wall_emit", C.c_float), ("skew_rebins", C.c_uint32), ("h2d_bytes", C.c_uint64)]
 
     def asdict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

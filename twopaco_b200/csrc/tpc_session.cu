@@ -10,6 +10,7 @@
 #include <functional>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -302,6 +303,7 @@ struct tpc_session {
 
     // position-windowed sessions (tpc_windowed.inl): the genome streams through HBM window by window from `wp`;
     // g / d_mask / d_stubmask then are VIRTUAL views of the current window's buffers
+    uint64_t h2d_bytes = 0;   // bytes the session copied host -> device for the genome (set_genome_host)
     bool windowed = false;
     WindowProvider* wp = nullptr;
     uint64_t window_tiles = 0, w_npos = 0;
@@ -490,6 +492,30 @@ static int wait_genome(tpc_session* s, uint64_t tile_end) {
     return 0;
 }
 
+// The n-mask (1 bit per position) is a third of the packed genome's bytes and almost everywhere uniform: zero inside the
+// sequences, ones only at record separators, N runs and the padding.  Classify it in blocks of 64 KiB (all host threads,
+// one upload chunk at a time, while the previous chunk's words cross PCIe): runs of all-zero / all-one blocks become a
+// cudaMemsetAsync on the device, only the mixed blocks are copied.  -> block kinds of words [m0, m1): 0 / 1 = uniform, 2 = mixed
+constexpr uint64_t kMaskBlockWords = 8192;
+static void classify_mask_blocks(const uint64_t* n_mask, uint64_t m0, uint64_t m1, std::vector<uint8_t>* kind) {
+    const uint64_t nb = (m1 - m0 + kMaskBlockWords - 1) / kMaskBlockWords;
+    kind->assign(nb, 2);
+    auto work = [&](uint64_t b0, uint64_t b1) {
+        for (uint64_t b = b0; b < b1; ++b) {
+            const uint64_t lo = m0 + b * kMaskBlockWords, hi = std::min(m1, lo + kMaskBlockWords);
+            uint64_t any = 0, all = ~0ull;
+            for (uint64_t i = lo; i < hi; ++i) { any |= n_mask[i]; all &= n_mask[i]; }
+            (*kind)[b] = any == 0 ? 0 : all == ~0ull ? 1 : 2;
+        }
+    };
+    static const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    const unsigned nt = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, nb / 64));
+    if (nt <= 1) { work(0, nb); return; }
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; ++t) pool.emplace_back(work, nb * t / nt, nb * (t + 1) / nt);
+    for (std::thread& t : pool) t.join();
+}
+
 int tpc_session_set_genome_host(tpc_session* s, const tpc_genome* g) {
     if (!s || !g) return set_error("null argument");
     if (s->g.codes) return set_error("genome already set");
@@ -504,12 +530,31 @@ int tpc_session_set_genome_host(tpc_session* s, const tpc_genome* g) {
     CK(cudaEventRecord(s->ev[9], s->stream));                 // allocations are stream-ordered
     CK(cudaStreamWaitEvent(s->copy_stream, s->ev[9], 0));
     const uint64_t chunks = std::max<uint64_t>(1, std::min<uint64_t>(16, s->ntiles / 512));
+    const bool sparse_mask = !(getenv("TPC_SPARSE_MASK") && atoi(getenv("TPC_SPARSE_MASK")) == 0);   // (=0: copy everything, tests / tuning)
+    std::vector<uint8_t> kind;
+    s->h2d_bytes = 0;
     for (uint64_t c = 0; c < chunks; ++c) {
         uint64_t t0 = s->ntiles * c / chunks, t1 = s->ntiles * (c + 1) / chunks;
         uint64_t c0 = t0 * kTileThreads, c1 = c + 1 == chunks ? cw : t1 * kTileThreads;
         uint64_t m0 = t0 * (kTileThreads / 2), m1 = c + 1 == chunks ? mw : t1 * (kTileThreads / 2);
         CK(cudaMemcpyAsync(s->d_codes + c0, g->codes + c0, (c1 - c0) * 8, cudaMemcpyHostToDevice, s->copy_stream));
-        CK(cudaMemcpyAsync(s->d_nmask + m0, g->n_mask + m0, (m1 - m0) * 8, cudaMemcpyHostToDevice, s->copy_stream));
+        s->h2d_bytes += (c1 - c0) * 8;
+        if (!sparse_mask) {
+            CK(cudaMemcpyAsync(s->d_nmask + m0, g->n_mask + m0, (m1 - m0) * 8, cudaMemcpyHostToDevice, s->copy_stream));
+            s->h2d_bytes += (m1 - m0) * 8;
+        } else {
+            classify_mask_blocks(g->n_mask, m0, m1, &kind);   // (the codes of this chunk are crossing PCIe meanwhile)
+            for (uint64_t b = 0; b < kind.size();) {
+                uint64_t e = b + 1;
+                while (e < kind.size() && kind[e] == kind[b]) ++e;
+                const uint64_t lo = m0 + b * kMaskBlockWords, hi = std::min(m1, m0 + e * kMaskBlockWords);
+                if (kind[b] == 2) {
+                    CK(cudaMemcpyAsync(s->d_nmask + lo, g->n_mask + lo, (hi - lo) * 8, cudaMemcpyHostToDevice, s->copy_stream));
+                    s->h2d_bytes += (hi - lo) * 8;
+                } else CK(cudaMemsetAsync(s->d_nmask + lo, kind[b] ? 0xFF : 0, (hi - lo) * 8, s->copy_stream));
+                b = e;
+            }
+        }
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaEventRecord(e, s->copy_stream));
@@ -1270,6 +1315,7 @@ int tpc_session_stats(tpc_session* s, tpc_stats* out) {
     s->st.ms_total = s->st.ms_bin + s->st.ms_fill + s->st.ms_query + s->st.ms_insert + s->st.ms_classify + s->st.ms_index + s->st.ms_emit;
     s->st.kernel_launches = s->launches;
     s->st.skew_rebins = s->skew_rebins;
+    s->st.h2d_bytes = s->h2d_bytes;
     *out = s->st;
     return 0;
 }
