@@ -86,6 +86,8 @@ class ClockSampler:
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int, enabled: bool = True):
+        self.interval_ms = int(os.environ.get("TPC_BENCH_CLOCK_MS", "50"))   # (0 = no sampling: tuning aid)
+        enabled = enabled and self.interval_ms > 0
         self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
         self.t0 = self.t1 = None
 
@@ -94,7 +96,7 @@ class ClockSampler:
             return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", str(self.interval_ms)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:

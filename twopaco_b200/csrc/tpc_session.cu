@@ -1455,17 +1455,27 @@ int tpc_junctions_host(const tpc_params* params, const tpc_genome* host_genome, 
         tpc_session_destroy(s);
         return rc;
     }
+    const bool verbose = getenv("TPC_VERBOSE") != nullptr;
+    const double t_start = now_ms();
+    auto vlog = [&](const char* what) {
+        if (verbose) fprintf(stderr, "[tpc junctions_host] +%9.3f ms  %s\n", now_ms() - t_start, what);
+    };
+    vlog("session created");
     int rc = tpc_session_set_genome_host(s, host_genome);
+    vlog("genome upload enqueued");
     uint64_t bytes = 0;
     if (rc == 0) rc = tpc_session_run_to_count(s, &bytes);
+    vlog("candidates, index, emit count done");
     if (out_bytes) *out_bytes = bytes;
     if (rc == 0 && bytes > out_capacity) {
         set_error("output buffer too small: need %llu bytes", (unsigned long long)bytes);
         rc = 2;
     }
     if (rc == 0) rc = tpc_session_write_host(s, out_image, bytes);
+    vlog("image written to the host buffer");
     if (stats) tpc_session_stats(s, stats);
     tpc_session_destroy(s);
+    vlog("session destroyed");
     return rc;
 }
 
