@@ -265,6 +265,11 @@ struct tpc_session {
     uint64_t bin_budget_bytes = 0; // 0 = 70 % of free HBM (env TPC_BIN_BUFFER_MB)
     uint32_t* d_bin_rec = nullptr;  // record scratch of the call: the rounds' record waves, then (between the
     uint64_t bin_rec_bytes = 0;     //   filter passes and the next round) the round's candidate table
+    // The scratch is kept between find_candidates calls of a session when plenty of memory stays free beside it (the next call
+    // then reuses it instead of asking the pool for tens of GB again, which can cost tens of ms when the pool has to remap)
+    bool bin_keep = false;
+    uint64_t bin_count_bytes = 0, bin_ov_bytes = 0, own_extra_bytes = 0;
+    uint64_t kept_scratch_bytes() const { return d_bin_rec && !bin_ready ? bin_rec_bytes + bin_count_bytes + bin_ov_bytes : 0; }
     unsigned long long* d_bin_count = nullptr;
     uint32_t* d_bin_ov = nullptr;
     BinView bin_view{};             // layout of the scratch, fixed for all rounds of a call
@@ -620,7 +625,7 @@ static uint32_t own_planes_for(uint32_t rounds_local) {  // bits needed for ids 
 static uint32_t choose_sub_rounds(tpc_session* s) {
     s->pipe = false;
     const bool can_pipe = s->pipe_env && binned_applies(s, nullptr) && !s->bin_budget_bytes;
-    const uint64_t avail = available_bytes(s->device);
+    const uint64_t avail = available_bytes(s->device) + s->kept_scratch_bytes() + s->own_extra_bytes;   // (what a first call sees)
     const uint64_t plane_bytes = s->ntiles * kTileThreads * 4;
     const uint64_t base = (uint64_t)s->prm.rounds * s->prm.shard_count;
     // does the record scratch of one round (x2 when two rounds are in flight) fit with S sub-rounds?
@@ -672,7 +677,7 @@ static int binned_setup(tpc_session* s, const KParams& kp) {
     if (!binned_applies(s, &bv)) return -1;
     bv.q = kp.q;
     const uint32_t buckets = 1u << bv.bucket_bits;
-    uint64_t budget = s->bin_budget_bytes ? s->bin_budget_bytes : (uint64_t)(available_bytes(s->device) * 0.92);
+    uint64_t budget = s->bin_budget_bytes ? s->bin_budget_bytes : (uint64_t)((available_bytes(s->device) + s->kept_scratch_bytes()) * 0.92);
     uint64_t wave_tiles = 0, nwaves = 0;
     for (int attempt = 0;; ++attempt) {
         // records of one wave must fit the budget: 12 B per record + 8 % slack per slice + overflow area
@@ -688,7 +693,10 @@ static int binned_setup(tpc_session* s, const KParams& kp) {
         bv.ov_cap = std::max<uint64_t>(1 << 16, est / 64);
         if (s->pipe && nwaves > 1) s->pipe = false;   // (cannot happen with the sub-rounds chosen for it, but stay safe)
         const uint32_t halves = s->pipe ? 2 : 1;
-        s->bin_rec_bytes = (uint64_t)halves * buckets * 3 * bv.cap * 4;
+        const uint64_t need = (uint64_t)halves * buckets * 3 * bv.cap * 4;
+        if (s->d_bin_rec && s->bin_rec_bytes == need) break;   // kept from the previous call
+        if (s->d_bin_rec) { CK(dev_free(s->d_bin_rec, s->stream)); s->d_bin_rec = nullptr; }
+        s->bin_rec_bytes = need;
         cudaError_t e = dev_alloc(&s->d_bin_rec, s->bin_rec_bytes, s->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
         if (e == cudaErrorMemoryAllocation && attempt < 4 && !s->bin_budget_bytes) {
@@ -703,8 +711,22 @@ static int binned_setup(tpc_session* s, const KParams& kp) {
         break;
     }
     const uint32_t halves = s->pipe ? 2 : 1;
-    CK(dev_alloc(&s->d_bin_count, (uint64_t)halves * (buckets + 1) * 8, s->stream));
-    CK(dev_alloc(&s->d_bin_ov, (uint64_t)halves * bv.ov_cap * 16, s->stream));
+    const uint64_t count_bytes = (uint64_t)halves * (buckets + 1) * 8, ov_bytes = (uint64_t)halves * bv.ov_cap * 16;
+    if (!s->d_bin_count || s->bin_count_bytes != count_bytes) {
+        if (s->d_bin_count) CK(dev_free(s->d_bin_count, s->stream));
+        CK(dev_alloc(&s->d_bin_count, count_bytes, s->stream));
+        s->bin_count_bytes = count_bytes;
+    }
+    if (!s->d_bin_ov || s->bin_ov_bytes != ov_bytes) {
+        if (s->d_bin_ov) CK(dev_free(s->d_bin_ov, s->stream));
+        CK(dev_alloc(&s->d_bin_ov, ov_bytes, s->stream));
+        s->bin_ov_bytes = ov_bytes;
+    }
+    {   // keep the scratch for the next call when at least a quarter of the device stays free beside it (index, image, tables)
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        s->bin_keep = !s->bin_budget_bytes && available_bytes(s->device) >= total_b / 4 && !(getenv("TPC_KEEP_SCRATCH") && atoi(getenv("TPC_KEEP_SCRATCH")) == 0);
+    }
     bv.rec = s->d_bin_rec; bv.count = s->d_bin_count; bv.ov_count = s->d_bin_count + buckets; bv.ov = s->d_bin_ov;
     s->bin_view = bv;
     for (uint32_t h = 0; h < 2; ++h) {
@@ -730,12 +752,13 @@ static int binned_setup(tpc_session* s, const KParams& kp) {
 }
 
 static int binned_release(tpc_session* s) {
+    s->bin_ready = false;
+    if (s->bin_keep && s->d_bin_rec) return 0;   // (binned_setup of the next call reuses or replaces it; the session's destructor frees it)
     for (void** p : {(void**)&s->d_bin_rec, (void**)&s->d_bin_count, (void**)&s->d_bin_ov}) {
         if (*p) CK(dev_free(*p, s->stream));
         *p = nullptr;
     }
-    s->bin_rec_bytes = 0;
-    s->bin_ready = false;
+    s->bin_rec_bytes = 0; s->bin_count_bytes = 0; s->bin_ov_bytes = 0;
     return 0;
 }
 
@@ -998,9 +1021,11 @@ int tpc_session_find_candidates(tpc_session* s) {
         s->own.n = std::max<uint32_t>(planes, 1);
         s->own_shared = planes > 0;
         s->own_done_tiles = 0;
-        if (s->d_own_extra) { CK(dev_free(s->d_own_extra, s->stream)); s->d_own_extra = nullptr; }
+        const uint64_t extra_bytes = planes > 1 && binned_applies(s, nullptr) ? (uint64_t)(planes - 1) * std::max<uint64_t>(mask_words, 1) * 4 : 0;
+        if (s->d_own_extra && s->own_extra_bytes != extra_bytes) { CK(dev_free(s->d_own_extra, s->stream)); s->d_own_extra = nullptr; s->own_extra_bytes = 0; }
         if (planes > 1 && binned_applies(s, nullptr)) {
-            CK(dev_alloc(&s->d_own_extra, (uint64_t)(planes - 1) * std::max<uint64_t>(mask_words, 1) * 4, s->stream));
+            if (!s->d_own_extra) CK(dev_alloc(&s->d_own_extra, extra_bytes, s->stream));
+            s->own_extra_bytes = extra_bytes;
             for (uint32_t j = 1; j < planes; ++j) s->own.p[j] = s->d_own_extra + (uint64_t)(j - 1) * mask_words;
         } else if (planes > 1) {
             s->own_shared = false;  // direct path: ownership is decided inline
@@ -1147,7 +1172,7 @@ int tpc_session_find_candidates(tpc_session* s) {
     }
     if (s->d_T) { CK(dev_free(s->d_T, s->stream)); s->d_T = nullptr; s->T_bytes = 0; }
     if (int rc = binned_release(s)) return rc;
-    if (s->d_own_extra) { CK(dev_free(s->d_own_extra, s->stream)); s->d_own_extra = nullptr; }
+    if (s->d_own_extra && !s->bin_keep) { CK(dev_free(s->d_own_extra, s->stream)); s->d_own_extra = nullptr; s->own_extra_bytes = 0; }
     s->st.candidate_marks = cur.marks;
     s->st.candidate_kmers = cur.distinct;
     s->st.filter_edges_set = cur.filter_new;
