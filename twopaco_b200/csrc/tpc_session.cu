@@ -50,6 +50,12 @@ const char* last_error() { return g_error.c_str(); }
 static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+// TPC_VERBOSE: host-side trace points with one clock for the whole process (where does the time outside the kernels go?)
+static void trace(const char* what) {
+    static const bool on = getenv("TPC_VERBOSE") != nullptr;
+    static const double t0 = now_ms();
+    if (on) fprintf(stderr, "[tpc trace] %12.3f ms  %s\n", now_ms() - t0, what);
+}
 // host wall clock of a scope, added to *acc on exit (also on the early returns of CK())
 struct WallTimer {
     float* acc;
@@ -438,6 +444,7 @@ int tpc_session_create(const tpc_params* params, void* stream, tpc_session** out
 
 void tpc_session_destroy(tpc_session* s) {
     if (!s) return;
+    trace("session destroy: enter");
     cudaStreamSynchronize(s->stream);
     if (s->windowed) { s->d_mask = nullptr; s->d_stubmask = nullptr; }   // (views of d_wmask / d_wstub)
     void* ptrs[] = {s->d_codes, s->d_nmask, s->d_rec_start, s->d_rec_len, s->d_sep_before, s->d_filter, s->d_mask,
@@ -456,6 +463,7 @@ void tpc_session_destroy(tpc_session* s) {
     for (auto& ev : s->pipe_ev)
         if (ev) cudaEventDestroy(ev);
     delete s;
+    trace("session destroy: done");
 }
 
 static int adopt_records(tpc_session* s, const tpc_genome* g) {
@@ -766,7 +774,9 @@ static int binned_release(tpc_session* s) {
 // apply and -2 when a slice overflowed beyond the overflow area (then the caller uses k_fill /
 // k_query), 0 on success, >0 on error.
 static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin, float* ms_fill, float* ms_query) {
+    trace("filter passes (binned): enter");
     if (int rc = binned_setup(s, kp)) return rc;
+    trace("record scratch ready");
     LaunchCtx lc = s->lctx();
     BinView bv = s->bin_view;       // (uniform layout; a skewed round switches this copy to per-slice capacities)
     SliceLayout sl;
@@ -823,13 +833,16 @@ static int filter_passes_binned(tpc_session* s, const KParams& kp, float* ms_bin
                 if (int brc = bin_range(t0, t1, base)) return brc;
             }
             CK(cudaEventRecord(e1, s->stream));
+            trace(rebin ? "binning enqueued" : "(records shared with the fill pass)");
             for (uint32_t b = 0; b < buckets; ++b) {
                 if (pass == 0) CK(launch_apply_fill(lc, s->d_filter, bv, sl, b, s->d_ctr));
                 else CK(launch_apply_query(lc, s->d_filter, bv, sl, b, s->d_mask, base, s->d_ctr, s->d_hll, s->mark_list(true)));
             }
             CK(launch_apply_overflow(lc, s->d_filter, bv, pass, s->d_mask, base, s->d_ctr, s->d_hll, s->mark_list(pass == 1)));
             CK(cudaEventRecord(e2, s->stream));
+            trace("apply kernels enqueued");
             rc = finish_wave(ms_bin, pass == 0 ? ms_fill : ms_query);
+            trace(pass == 0 ? "fill pass synchronised" : "query pass synchronised");
             if (rc == 0 && pass == 0 && nwaves == 1 && ov_now > bv.ov_cap && !skew_layout) {
                 // Skewed input: slices ran over their arrays AND the overflow list.  The reservation counters hold the exact
                 // number of records of every slice: re-bin this round into arrays of exactly those sizes (one more binning
@@ -960,6 +973,7 @@ namespace tpc { static int find_candidates_windowed(tpc_session* s); }
 int tpc_session_find_candidates(tpc_session* s) {
     if (s && s->windowed) return tpc::find_candidates_windowed(s);
     if (!s || !s->g.codes) return set_error("no genome set");
+    trace("find_candidates: enter");
     LaunchCtx lc = s->lctx();
     const uint64_t mask_words = s->ntiles * kTileThreads;
     const uint64_t filter_bytes = (1ull << s->filter_bits_eff) / 8;
@@ -1009,9 +1023,12 @@ int tpc_session_find_candidates(tpc_session* s) {
             s->marklist_regions = regions; s->marklist_region_cap = region_cap;
         }
     }
+    trace("filter / masks / mark list allocated (enqueued)");
     CK(cudaStreamSynchronize(s->stream));  // the allocations above are visible to available_bytes()
+    trace("... and synchronised");
     vlog("buffers allocated, mask cleared", -1);
     s->sub_rounds = choose_sub_rounds(s);
+    trace("sub-rounds chosen");
     s->rounds_eff = s->prm.rounds * s->sub_rounds;
     s->st.sub_rounds = s->sub_rounds;
     {   // ownership planes shared by all rounds of this call
@@ -1037,6 +1054,7 @@ int tpc_session_find_candidates(tpc_session* s) {
     // (one table, sized from the HyperLogLog sketch accumulated over the sub-rounds) replaces one scan per
     // sub-round.  With -r > 1 the table stays per round, as in the reference (h:337-338).
     const bool merge_insert = s->prm.rounds == 1 && s->sub_rounds > 1;
+    trace("ownership planes ready");
     for (uint32_t r = 0; r < s->rounds_eff; ++r) {
         KParams kp = s->kparams(s->prm.shard_index * s->rounds_eff + r);
         const Counters round_start = cur;
@@ -1070,6 +1088,7 @@ int tpc_session_find_candidates(tpc_session* s) {
         CK(cudaMemcpyAsync(&cur, s->d_ctr, sizeof cur, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
         vlog("filter passes done", (int)r);
+        trace("filter passes done");
         {
             float t;
             if (brc < 0) {
@@ -1180,6 +1199,7 @@ int tpc_session_find_candidates(tpc_session* s) {
     s->have_candidates = true;
     s->have_index = false;
     vlog("scratch released", -1);
+    trace("find_candidates: done");
     return 0;
 }
 
