@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -110,17 +111,39 @@ static void configure_pool(int device) {
     }
 }
 
-// memory a new allocation can use: free device memory + what the pool holds but does not use
-static uint64_t available_bytes(int device) {
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
+// memory a new allocation can use: free device memory + what the pool holds but does not use.
+// cudaMemGetInfo goes through the driver and was measured (B200 box shared with other tenants, profiles/r2_host_trace.md) to
+// block for 30-100 ms every few calls; it sat three times on the critical path of every find_candidates call.  What this
+// process can use in total -- free memory + what its pool has reserved -- only changes when somebody else (another library
+// of the process, another process) allocates or frees, so that sum is cached per device: refreshed when it is older than
+// five seconds or after an allocation failed (invalidate_memory_budget), and what the pool currently uses (a counter of the
+// pool, no driver call) is subtracted.
+namespace {
+struct MemoryBudget { double measured_ms = -1e30; uint64_t usable = 0, total = 0; };
+MemoryBudget g_budget[64];
+std::mutex g_budget_mu;
+}  // namespace
+static void invalidate_memory_budget() {
+    std::lock_guard<std::mutex> lock(g_budget_mu);
+    for (MemoryBudget& b : g_budget) b.measured_ms = -1e30;
+}
+static uint64_t available_bytes(int device, uint64_t* total_out = nullptr) {
     cudaMemPool_t pool;
     uint64_t reserved = 0, used = 0;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
-        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    const bool have_pool = cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess;
+    if (have_pool) cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    std::lock_guard<std::mutex> lock(g_budget_mu);
+    MemoryBudget& b = g_budget[(unsigned)device % 64];
+    if (now_ms() - b.measured_ms > 5000.0) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (have_pool) cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        b.usable = (uint64_t)free_b + reserved;
+        b.total = total_b;
+        b.measured_ms = now_ms();
     }
-    return (uint64_t)free_b + (reserved > used ? reserved - used : 0);
+    if (total_out) *total_out = b.total;
+    return b.usable > used ? b.usable - used : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -709,6 +732,7 @@ static int binned_setup(tpc_session* s, const KParams& kp) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
         if (e == cudaErrorMemoryAllocation && attempt < 4 && !s->bin_budget_bytes) {
             cudaGetLastError();  // not enough contiguous memory after all: one scratch, then smaller waves
+            invalidate_memory_budget();
             s->d_bin_rec = nullptr;
             s->bin_rec_bytes = 0;
             if (s->pipe) s->pipe = false;
@@ -731,9 +755,9 @@ static int binned_setup(tpc_session* s, const KParams& kp) {
         s->bin_ov_bytes = ov_bytes;
     }
     {   // keep the scratch for the next call when at least a quarter of the device stays free beside it (index, image, tables)
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        s->bin_keep = !s->bin_budget_bytes && available_bytes(s->device) >= total_b / 4 && !(getenv("TPC_KEEP_SCRATCH") && atoi(getenv("TPC_KEEP_SCRATCH")) == 0);
+        uint64_t total_b = 0;
+        const uint64_t avail = available_bytes(s->device, &total_b);
+        s->bin_keep = !s->bin_budget_bytes && avail >= total_b / 4 && !(getenv("TPC_KEEP_SCRATCH") && atoi(getenv("TPC_KEEP_SCRATCH")) == 0);
     }
     bv.rec = s->d_bin_rec; bv.count = s->d_bin_count; bv.ov_count = s->d_bin_count + buckets; bv.ov = s->d_bin_ov;
     s->bin_view = bv;
