@@ -14,6 +14,8 @@
 #include <thread>
 #include <vector>
 
+#include <unistd.h>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/twopaco_b200.h"
@@ -55,7 +57,7 @@ static double now_ms() {
 static void trace(const char* what) {
     static const bool on = getenv("TPC_VERBOSE") != nullptr;
     static const double t0 = now_ms();
-    if (on) fprintf(stderr, "[tpc trace] %12.3f ms  %s\n", now_ms() - t0, what);
+    if (on) fprintf(stderr, "[tpc trace %d] %12.3f ms  %s\n", (int)getpid(), now_ms() - t0, what);
 }
 // host wall clock of a scope, added to *acc on exit (also on the early returns of CK())
 struct WallTimer {
