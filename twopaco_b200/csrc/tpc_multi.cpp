@@ -379,19 +379,13 @@ static int shard_worker(MultiImpl* mi, Shared* sh, int r, const tpc_params& base
             off += sh->jcount[i];
         }
         CKN(nc.GroupEnd());
-        // ---- 2. OR-reduce-scatter of the disjoint candidate masks straight into the position slices: on the side stream,
-        // beside the index build of set_junctions (sort + k_build_index), which does not touch the masks
+        if (int e = tpc_session_set_junctions(s, (const uint64_t*)d_allj, total_j)) return e;
+        // ---- 2. OR-reduce-scatter of the disjoint candidate masks straight into the position slices
         uint32_t* mask = nullptr;
         uint64_t mwords = 0;
         if (int e = tpc_session_candidate_mask(s, &mask, &mwords)) return e;
         const uint64_t chunk = mwords / N;
-        cudaEvent_t e_rs;
-        CKM(cudaEventCreateWithFlags(&e_rs, cudaEventDisableTiming));
-        ev_tmp.push_back(e_rs);
-        CKN(nc.ReduceScatter(mask, mask + (uint64_t)r * chunk, chunk, ncclUint32, ncclSum, sh->comm[r], ag));   // (find_candidates has synchronised st)
-        CKM(cudaEventRecord(e_rs, ag));
-        if (int e = tpc_session_set_junctions(s, (const uint64_t*)d_allj, total_j)) return e;
-        CKM(cudaStreamWaitEvent(st, e_rs, 0));
+        CKN(nc.ReduceScatter(mask, mask + (uint64_t)r * chunk, chunk, ncclUint32, ncclSum, sh->comm[r], st));
         // ---- 3. position-sharded emit
         uint64_t nr = 0, ns = 0;
         if (int e = tpc_session_emit_count(s, slice_cut(src.n_positions, N, r), slice_cut(src.n_positions, N, r + 1), &nr, &ns)) return e;

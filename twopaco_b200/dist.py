@@ -110,22 +110,11 @@ def sharded_run(session, genome, rank: int, world: int, out=None):
         if ev: ev[0].record()
         allj = allgather_varlen(api.as_torch(ptr, n, torch.int64))            # exchange 1
         if ev: ev[1].record()
-        # exchange 2 runs on a side stream beside the index build of set_junctions (sort + k_build_index), which does not touch
-        # the masks (issued after exchange 1: the collectives of one communicator execute in issue order)
-        mptr, mw = s.candidate_mask()
-        side = None
-        if ev:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                ev[2].record()
-                or_reduce_scatter_disjoint_(api.as_torch(mptr, mw, torch.int32), rank, world)
-                ev[3].record()
-        else:
-            or_reduce_scatter_disjoint_(api.as_torch(mptr, mw, torch.int32), rank, world)
         s.set_junctions(allj.data_ptr(), allj.numel())
-        if side is not None:
-            torch.cuda.current_stream().wait_stream(side)
+        mptr, mw = s.candidate_mask()
+        if ev: ev[2].record()
+        or_reduce_scatter_disjoint_(api.as_torch(mptr, mw, torch.int32), rank, world)   # exchange 2
+        if ev: ev[3].record()
         cut = position_cuts(genome.n_positions, world)
         nrec, nstub = s.emit_count(cut[rank], cut[rank + 1])
         (rb, sb), (trec, tstub) = exclusive_prefix([nrec, nstub], "cuda")     # exchange 3
