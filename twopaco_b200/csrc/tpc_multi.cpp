@@ -685,12 +685,19 @@ uint32_t tpc_multi_gpus(const tpc_multi* m) { return m ? (uint32_t)m->impl.dev.s
 // packed genome (0.375 B per position), the candidate and stub masks (0.25 B) and the filter side by side
 static uint64_t choose_window_tiles(const tpc_multi* m, const tpc_params* params, uint64_t n_positions) {
     if (const char* e = getenv("TPC_WINDOW_TILES")) return (uint64_t)std::max(0ll, atoll(e));
-    int prev = 0;
-    cudaGetDevice(&prev);
-    cudaSetDevice(m->impl.dev[0]);
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    cudaSetDevice(prev);
+    // (the size of the device's memory, asked once: cudaMemGetInfo was measured to block for tens of ms on shared hosts)
+    static std::atomic<uint64_t> cached_total{0};
+    uint64_t total_b = cached_total.load();
+    if (!total_b) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(m->impl.dev[0]);
+        size_t free_b = 0, tot = 0;
+        cudaMemGetInfo(&free_b, &tot);
+        cudaSetDevice(prev);
+        total_b = tot;
+        cached_total.store(total_b);
+    }
     const double resident = 0.75 * (double)n_positions + (double)((1ull << std::max<uint32_t>(params->filter_bits, 9u)) / 8);
     return resident > 0.85 * (double)total_b ? (1u << 17) : 0;   // 2^30 positions per window
 }
