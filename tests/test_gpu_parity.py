@@ -681,7 +681,7 @@ def test_gpu_graphdump_seq_and_group(name, tmp_path):
     assert api.graphdump(b"", "seq") == b"" and api.graphdump(b"", "group") == b""
 
 
-@pytest.mark.parametrize("name", ["example_k11", "family_k25", "family_twofiles_k25", "gfa_mixed_k11", "gfa_mixed_k5"])
+@pytest.mark.parametrize("name", ["example_k11", "family_k25", "family_twofiles_k25", "gfa_long_k25", "gfa_mixed_k11", "gfa_mixed_k5"])
 def test_gpu_graphdump_gfa1_gfa2_fasta(name, tmp_path, monkeypatch):
     """tpc_graphdump_gfa_file == what the reference's graphdump prints for -f gfa1 / gfa2 / fasta (graphdump.cpp:377-582): the committed
     fixtures of the unmodified binary (tests/golden/gfa_golden.json) for our image, and for a relabelled image (random ids and

@@ -86,7 +86,7 @@ def test_oracle_vs_live_reference(seed, k, r, tmp_path):
 
 
 # ---- graphdump -f gfa1 / gfa2 / fasta: pin the Python restatement (oracle/graphdump_gfa.py) to the reference binary's output
-@pytest.mark.parametrize("name", ["example_k11", "family_twofiles_k25", "gfa_mixed_k11", "gfa_mixed_k5"])
+@pytest.mark.parametrize("name", ["example_k11", "family_twofiles_k25", "gfa_long_k25", "gfa_mixed_k11", "gfa_mixed_k5"])
 def test_gfa_restatement_matches_reference_golden(name, monkeypatch):
     import json
     from oracle import graphdump_gfa as G
