@@ -451,24 +451,23 @@ int tpc_graphdump_gfa_device(const uint8_t* dev_image, uint64_t image_bytes, uin
     CKD(cudaMemcpyAsync(&total, off + m, 8, cudaMemcpyDeviceToHost, st));
     CKD(cudaStreamSynchronize(st));
 
+    // long bodies: counted first (cap 0), then listed -- any number of them
     uint32_t *long_list = nullptr, *long_count = nullptr;
-    const uint32_t long_cap = 1u << 16;
-    CKD(sc.alloc(&long_list, long_cap));
     CKD(sc.alloc(&long_count, 1));
     CKD(cudaMemsetAsync(long_count, 0, 4, st));
+    k_gfa_long_list<<<grid_for(m), 256, 0, st>>>(ctx, m, nullptr, long_count, 0);
+    uint32_t n_long = 0;
+    CKD(cudaMemcpyAsync(&n_long, long_count, 4, cudaMemcpyDeviceToHost, st));
+    CKD(cudaStreamSynchronize(st));
+    CKD(sc.alloc(&long_list, n_long));
     char* text = nullptr;
     CKD(cudaMallocAsync((void**)&text, std::max<unsigned long long>(total, 16), st));
     k_gfa_write<<<grid_for(m), 256, 0, st>>>(ctx, m, off, len_a, piece_off, chr_first, chr_last, text);
     k_gfa_bodies_warp<<<grid_for(m), 256, 0, st>>>(ctx, m, off, text);
-    k_gfa_long_list<<<grid_for(m), 256, 0, st>>>(ctx, m, long_list, long_count, long_cap);
-    uint32_t n_long = 0;
-    cudaError_t e = cudaMemcpyAsync(&n_long, long_count, 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess && n_long > long_cap) {
-        cudaFreeAsync(text, st);
-        return set_error("more than %u segments of %llu and more characters", long_cap, kLongBody);
-    }
-    if (e == cudaSuccess && n_long) {
+    cudaError_t e = cudaSuccess;
+    if (n_long) {
+        e = cudaMemsetAsync(long_count, 0, 4, st);
+        k_gfa_long_list<<<grid_for(m), 256, 0, st>>>(ctx, m, long_list, long_count, n_long);
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
