@@ -118,7 +118,7 @@ static void configure_pool(int device) {
 // block for 30-100 ms every few calls; it sat three times on the critical path of every find_candidates call.  What this
 // process can use in total -- free memory + what its pool has reserved -- only changes when somebody else (another library
 // of the process, another process) allocates or frees, so that sum is cached per device: refreshed when it is older than
-// five seconds or after an allocation failed (invalidate_memory_budget), and what the pool currently uses (a counter of the
+// a minute or after an allocation failed (invalidate_memory_budget), and what the pool currently uses (a counter of the
 // pool, no driver call) is subtracted.
 namespace {
 struct MemoryBudget { double measured_ms = -1e30; uint64_t usable = 0, total = 0; };
@@ -136,7 +136,7 @@ static uint64_t available_bytes(int device, uint64_t* total_out = nullptr) {
     if (have_pool) cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
     std::lock_guard<std::mutex> lock(g_budget_mu);
     MemoryBudget& b = g_budget[(unsigned)device % 64];
-    if (now_ms() - b.measured_ms > 5000.0) {
+    if (now_ms() - b.measured_ms > 60000.0) {   // (a stale value costs at most a retry: a failed allocation invalidates it)
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         if (have_pool) cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
