@@ -1,6 +1,7 @@
 """CPU: the C-ABI library loads and exports every symbol include/twopaco_b200.h declares; the
 host-side pieces (FASTA framing, 2-bit packing) match the oracle / a numpy restatement.
 No GPU compute is called here."""
+import os
 import re
 from pathlib import Path
 
@@ -174,3 +175,21 @@ def test_ingest_fuzz_against_the_scalar_parsers(seed, tmp_path, monkeypatch):
     f.write_bytes(bad)
     with pytest.raises(api.TpcError, match="invalid character '!' in sequence z"):
         api.ingest_fasta([str(f)], threads=2)
+
+
+def test_graphdump_cli_argument_errors(tmp_path):
+    """`graphdump` (host/graphdump.cpp) keeps the reference's flags and exit codes (graphdump.cpp:608-710); argument errors
+    are reported before any GPU work, so they are checked here."""
+    import subprocess
+    cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "twopaco_b200", "bin", "graphdump")
+    if not os.path.exists(cli):
+        pytest.skip("CLI not built")
+    run = lambda *a: subprocess.run([cli, *a], capture_output=True, text=True, cwd=tmp_path)
+    for args, text in ((( ), "infile"), (("-f", "gfa1", "-k", "11", "x.dbg"), "seqfilename"), (("-f", "nope", "-k", "11", "x.dbg"), "does not meet constraint"),
+                       (("-f", "seq", "x.dbg"), "kvalue"), (("-k", "11", "x.dbg"), "format"), (("-f", "seq", "-k", "11", "a", "b"), "Too many arguments"),
+                       (("-f", "seq", "-k", "eleven", "x.dbg"), "Couldn't read argument value"), (("-f", "seq", "-k", "11", "missing.dbg"), "Can't open file"),
+                       (("--bogus", "x.dbg"), "Couldn't find match")):
+        r = run(*args)
+        assert r.returncode == 1 and r.stderr.startswith("error: ") and text in r.stderr, (args, r.stderr)
+    r = run("--help")
+    assert r.returncode == 0 and "--prefix" in r.stdout
