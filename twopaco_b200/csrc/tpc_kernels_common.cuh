@@ -244,7 +244,18 @@ __device__ __forceinline__ void mark_list_end(const MarkList& ml, uint32_t* s_li
     if (threadIdx.x == 0 && ml.entries && blockIdx.x < ml.regions) ml.counts[blockIdx.x] = *s_list_count;
 }
 
-template <int Q>
+// Candidates are rare (1-2 % of the records) but nearly every warp iteration (128 records) holds one, and a lane that handles its
+// mark inline drags the whole warp through the ~60 instructions of apply_mark (position word from HBM, sketch update, mask
+// atomicOr, list append) with one or two lanes active: measured, the query kernel ran at 0.79 of the rate of the same loads and
+// tests without the marks.  AGG: the warp queues its marks in shared memory -- slots handed out by ballot, the count is a
+// warp-uniform register, no atomics -- and handles them 32 at a time with every lane busy.
+struct MarkQueueEntry {
+    unsigned long long idx;   // record index inside the slice's arrays (its position word is only read when it is a candidate)
+    uint32_t w1, m;
+};
+constexpr int kMarkQueueCap = 64;   // < 32 queued + at most 32 new per ballot
+
+template <int Q, bool AGG>
 __global__ void __launch_bounds__(256, 4)
 k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ rec, const unsigned long long* __restrict__ count,
               uint64_t cap, uint32_t sib_bits, uint32_t* __restrict__ mask, uint64_t wave_base, Counters* ctr,
@@ -252,6 +263,7 @@ k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ r
     __shared__ unsigned long long red[8];
     __shared__ ApplyRing ring;
     __shared__ uint32_t s_list_count;
+    __shared__ MarkQueueEntry s_queue[AGG ? 8 : 1][AGG ? kMarkQueueCap : 1];
     mark_list_begin(ml, &s_list_count);
     unsigned long long n64 = *count;
     const uint64_t n = n64 > cap ? cap : n64;
@@ -264,21 +276,68 @@ k_apply_query(const uint32_t* __restrict__ slice, const uint32_t* __restrict__ r
     ApplyStream st;
     st.start(ring, rec, rec_b, gtid, gsize, nvec);
     prefetch_slice(slice, sib_mask + 1u, gtid, gsize);
-    for (uint64_t v = gtid; v < nvec; v += gsize) {
-        uint4 sd, w1;
-        st.take(ring, sd, w1);
-        Sector s[kApplyU];
+    if (!AGG) {
+        for (uint64_t v = gtid; v < nvec; v += gsize) {
+            uint4 sd, w1;
+            st.take(ring, sd, w1);
+            Sector s[kApplyU];
 #pragma unroll
-        for (int j = 0; j < kApplyU; ++j) s[j] = ld_sector_nc(slice + ((uint64_t)(u4_get(w1, j) & sib_mask) << 3));
-        st.refill(ring);
+            for (int j = 0; j < kApplyU; ++j) s[j] = ld_sector_nc(slice + ((uint64_t)(u4_get(w1, j) & sib_mask) << 3));
+            st.refill(ring);
 #pragma unroll
-        for (int j = 0; j < kApplyU; ++j) {
-            const uint32_t m = mask_from_seed<Q>(u4_get(sd, j));
-            if (query_sector(s[j], m)) {
-                apply_mark(mask, hll, m, u4_get(w1, j), __ldcs(rec_c + v * kApplyU + j), sib_bits, wave_base, slice_first_sector, ml, &s_list_count);
-                ++marks;
+            for (int j = 0; j < kApplyU; ++j) {
+                const uint32_t m = mask_from_seed<Q>(u4_get(sd, j));
+                if (query_sector(s[j], m)) {
+                    apply_mark(mask, hll, m, u4_get(w1, j), __ldcs(rec_c + v * kApplyU + j), sib_bits, wave_base, slice_first_sector, ml, &s_list_count);
+                    ++marks;
+                }
             }
         }
+    } else {
+        const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        MarkQueueEntry* q = s_queue[wid];
+        uint32_t queued = 0;   // warp-uniform
+        // handle the first `cnt` (<= 32) queued marks, one per lane
+        auto flush = [&](uint32_t cnt) {
+            __syncwarp();
+            if (lane < cnt) {
+                const MarkQueueEntry e = q[lane];
+                apply_mark(mask, hll, e.m, e.w1, __ldcs(rec_c + e.idx), sib_bits, wave_base, slice_first_sector, ml, &s_list_count);
+            }
+            __syncwarp();
+        };
+        // whole warps iterate together (lanes past the end carry no record), so that the ballots below are full-mask
+        for (uint64_t v0 = (uint64_t)gtid - lane; v0 < nvec; v0 += gsize) {
+            const uint64_t v = v0 + lane;
+            const bool act = v < nvec;
+            uint4 sd = make_uint4(0u, 0u, 0u, 0u), w1 = make_uint4(0u, 0u, 0u, 0u);
+            if (act) st.take(ring, sd, w1);
+            Sector s[kApplyU];
+#pragma unroll
+            for (int j = 0; j < kApplyU; ++j) s[j] = ld_sector_nc(slice + ((uint64_t)(u4_get(w1, j) & sib_mask) << 3));
+            if (act) st.refill(ring);
+#pragma unroll
+            for (int j = 0; j < kApplyU; ++j) {
+                const uint32_t m = mask_from_seed<Q>(u4_get(sd, j));
+                const bool hit = act && query_sector(s[j], m);
+                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                if (bal == 0) continue;
+                if (hit) {
+                    MarkQueueEntry e;
+                    e.idx = v * kApplyU + j; e.w1 = u4_get(w1, j); e.m = m;
+                    q[queued + __popc(bal & ((1u << lane) - 1u))] = e;
+                    ++marks;
+                }
+                queued += __popc(bal);
+                if (queued >= 32) {
+                    flush(32);
+                    queued -= 32;
+                    if (lane < queued) q[lane] = q[32 + lane];   // the rest (< 32 entries) moves to the front: disjoint halves
+                    __syncwarp();
+                }
+            }
+        }
+        flush(queued);
     }
     cp_async_wait<0>();
     for (uint64_t i = nvec * kApplyU + gtid; i < n; i += gsize) {

@@ -217,12 +217,23 @@ cudaError_t launch_apply_fill(const LaunchCtx& c, uint32_t* filter, const BinVie
     return cudaGetLastError();
 }
 
+constexpr bool kQueryAggDefault = false;
+
 cudaError_t launch_apply_query(const LaunchCtx& c, const uint32_t* filter, const BinView& bv, const SliceLayout& sl, uint32_t bucket,
                                uint32_t* mask, uint64_t wave_base, Counters* ctr, uint32_t* hll, const MarkList& ml) {
     const uint32_t* slice = filter + (((uint64_t)bucket << bv.sib_bits) << 3);
-    TPC_APPLY_Q_SWITCH(bv.q, (k_apply_query<Q><<<apply_grid(c), 256, 0, c.stream>>>(
-        slice, sl.base(bv, bucket), bv.count + bucket, sl.cap(bv, bucket), bv.sib_bits, mask, wave_base, ctr, hll,
-        (uint64_t)bucket << bv.sib_bits, ml)));
+    // (TPC_QUERY_AGG=0 / 1: marks handled inline by the lane that finds them / queued per warp and handled 32 at a time)
+    const char* agg_env = getenv("TPC_QUERY_AGG");
+    const bool agg = agg_env ? atoi(agg_env) != 0 : kQueryAggDefault;
+    if (agg) {
+        TPC_APPLY_Q_SWITCH(bv.q, (k_apply_query<Q, true><<<apply_grid(c), 256, 0, c.stream>>>(
+            slice, sl.base(bv, bucket), bv.count + bucket, sl.cap(bv, bucket), bv.sib_bits, mask, wave_base, ctr, hll,
+            (uint64_t)bucket << bv.sib_bits, ml)));
+    } else {
+        TPC_APPLY_Q_SWITCH(bv.q, (k_apply_query<Q, false><<<apply_grid(c), 256, 0, c.stream>>>(
+            slice, sl.base(bv, bucket), bv.count + bucket, sl.cap(bv, bucket), bv.sib_bits, mask, wave_base, ctr, hll,
+            (uint64_t)bucket << bv.sib_bits, ml)));
+    }
     ++*c.launches;
     return cudaGetLastError();
 }
