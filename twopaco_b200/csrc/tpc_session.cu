@@ -217,7 +217,7 @@ cudaError_t launch_apply_fill(const LaunchCtx& c, uint32_t* filter, const BinVie
     return cudaGetLastError();
 }
 
-constexpr bool kQueryAggDefault = false;
+constexpr bool kQueryAggDefault = true;   // measured at C3, one GPU, same box: query 117.4 -> 109.5 ms (profiles/r2_query_agg.md)
 
 cudaError_t launch_apply_query(const LaunchCtx& c, const uint32_t* filter, const BinView& bv, const SliceLayout& sl, uint32_t bucket,
                                uint32_t* mask, uint64_t wave_base, Counters* ctr, uint32_t* hll, const MarkList& ml) {
