@@ -111,3 +111,33 @@ def test_gfa_restatement_rejects_what_the_reference_rejects(tmp_path, monkeypatc
     img, _, _ = O.find_junctions(O.parse_fasta("x.fa"), 5)
     with pytest.raises(G.GraphdumpError, match="corrupted"):
         G.graphdump_text(img, "gfa1", 5, ["x.fa"])
+
+
+@pytest.mark.skipif(not O.REF_GRAPHDUMP.exists(), reason="oracle/_ref/graphdump was not built")
+@pytest.mark.parametrize("name", ["family_twofiles_k25", "gfa_long_k25", "gfa_mixed_k11"])
+def test_gfa_restatement_matches_the_live_reference_on_relabelled_images(name, monkeypatch):
+    """Ids and signs as a differently seeded reference run would write them (the fixtures only hold first-appearance numbering):
+    the restatement must still print what the unmodified graphdump prints."""
+    import subprocess
+    from oracle import graphdump_gfa as G
+    from tests.cases import GFA_CASES, GFA_FORMATS
+    spec = GFA_CASES[name]
+    with case_files(spec) as (paths, files, d):
+        monkeypatch.chdir(d)
+        img, _, _ = oracle_on_paths(paths, spec["k"])
+        seq, pos, ids = O.decode(img)
+        rng = np.random.default_rng(23)
+        uniq = np.unique(np.abs(ids))
+        perm = dict(zip(uniq.tolist(), (rng.permutation(len(uniq)) + 3).tolist()))
+        flip = {u: int(rng.integers(0, 2)) * 2 - 1 for u in uniq.tolist()}
+        rec = np.frombuffer(img, dtype=O.REC_DTYPE).copy()
+        sep = (rec["pos"] == O.SEP_POS) | (rec["id"] == O.SEP_ID)
+        rec["id"][~sep] = [perm[abs(v)] * (1 if v > 0 else -1) * flip[abs(v)] for v in ids.tolist()]
+        with open("relabelled.dbg", "wb") as fh:
+            fh.write(rec.tobytes())
+        names = [f for f, _ in files]
+        for fmt, prefix in GFA_FORMATS:
+            cmd = [str(O.REF_GRAPHDUMP), "-f", fmt, "-k", str(spec["k"])] + [a for n in names for a in ("-s", n)] + (["--prefix"] if prefix else [])
+            q = subprocess.run(cmd + ["relabelled.dbg"], capture_output=True)
+            assert q.returncode == 0, q.stderr
+            assert G.graphdump_text(rec.tobytes(), fmt, spec["k"], names, prefix) == q.stdout, (fmt, prefix)
